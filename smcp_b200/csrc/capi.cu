@@ -1,0 +1,738 @@
+// C ABI of libsmcp_b200.so (see include/smcp_b200.h): context, symbolic object, chordal
+// matrix buffers, constraint operator, Schur complement assembly / factorisation / solve.
+#include "internal.cuh"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <algorithm>
+#include <dlfcn.h>
+
+static thread_local char g_err[1024] = "";
+
+void smcp_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *smcp_last_error(void) { return g_err; }
+extern "C" int smcp_version(void) { return 100; }
+
+int grow(void **p, size_t *cap, size_t bytes) {
+    if (bytes <= *cap) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess) {
+        smcp_set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        return -1;
+    }
+    *cap = want;
+    return 0;
+}
+
+LaunchScope::LaunchScope(smcp_ctx *c, const char *nm, int nlaunch) : ctx(c), name(nm), n(nlaunch) {
+    ctx->launches += n;
+    if (ctx->prof) cudaEventRecord(ctx->pev0, ctx->stream);
+}
+LaunchScope::~LaunchScope() {
+    if (ctx->prof) {
+        cudaEventRecord(ctx->pev1, ctx->stream);
+        cudaEventSynchronize(ctx->pev1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->pev0, ctx->pev1);
+        ProfEntry &e = ctx->prof_acc[name];
+        e.ms += ms;
+        e.launches += n;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+extern "C" int smcp_ctx_create(int device, smcp_ctx **out) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        smcp_set_error("no CUDA device available (%s); this library has no CPU fallback",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return -1;
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    smcp_ctx *ctx = new smcp_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    ctx->num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&ctx->ev0));
+    CUDA_TRY(cudaEventCreate(&ctx->ev1));
+    CUDA_TRY(cudaEventCreate(&ctx->pev0));
+    CUDA_TRY(cudaEventCreate(&ctx->pev1));
+    ctx->pinned_bytes = 1 << 20;
+    CUDA_TRY(cudaMallocHost(&ctx->pinned, ctx->pinned_bytes));
+    *out = ctx;
+    return 0;
+}
+
+extern "C" int smcp_ctx_destroy(smcp_ctx *ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaEventDestroy(ctx->pev0);
+    cudaEventDestroy(ctx->pev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+extern "C" int smcp_ctx_sync(smcp_ctx *ctx) {
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int64_t smcp_ctx_launch_count(smcp_ctx *ctx) { return ctx->launches; }
+extern "C" int smcp_timer_start(smcp_ctx *ctx) {
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    return 0;
+}
+extern "C" int smcp_timer_stop(smcp_ctx *ctx, double *ms_out) {
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    *ms_out = ms;
+    return 0;
+}
+extern "C" int smcp_prof_enable(smcp_ctx *ctx, int on) {
+    ctx->prof = on != 0;
+    return 0;
+}
+extern "C" int smcp_prof_get(smcp_ctx *ctx, const char *name, double *ms_out, int64_t *launches_out) {
+    auto it = ctx->prof_acc.find(name);
+    if (it == ctx->prof_acc.end()) {
+        *ms_out = 0.0;
+        *launches_out = 0;
+        return 0;
+    }
+    *ms_out = it->second.ms;
+    *launches_out = it->second.launches;
+    return 0;
+}
+extern "C" int smcp_prof_reset(smcp_ctx *ctx) {
+    ctx->prof_acc.clear();
+    return 0;
+}
+extern "C" int smcp_flush_l2(smcp_ctx *ctx) {
+    size_t bytes = (size_t)256 << 20;
+    if (!ctx->flush_buf) {
+        CUDA_TRY(cudaMalloc(&ctx->flush_buf, bytes));
+        ctx->flush_bytes = bytes;
+    }
+    CUDA_TRY(cudaMemsetAsync(ctx->flush_buf, 1, ctx->flush_bytes, ctx->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// symbolic object
+// ---------------------------------------------------------------------------------------
+template <class T, class S>
+static int upload(smcp_sym *s, const S *src, size_t n, const T **dst) {
+    std::vector<T> tmp(n ? n : 1);
+    for (size_t i = 0; i < n; ++i) tmp[i] = (T)src[i];
+    void *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, (n ? n : 1) * sizeof(T)));
+    CUDA_TRY(cudaMemcpy(d, tmp.data(), (n ? n : 1) * sizeof(T), cudaMemcpyHostToDevice));
+    s->allocs.push_back(d);
+    *dst = (const T *)d;
+    return 0;
+}
+
+static int upload_sched(smcp_sym *s, int ntask, const std::vector<int> &tp, const std::vector<int> &ts,
+                        const std::vector<int> &dp, const std::vector<int> &di, TaskSched *out) {
+    out->ntask = ntask;
+    if (upload<int, int>(s, tp.data(), tp.size(), &out->task_ptr)) return -1;
+    if (upload<int, int>(s, ts.data(), ts.size(), &out->task_sn)) return -1;
+    if (upload<int, int>(s, dp.data(), dp.size(), &out->dep_ptr)) return -1;
+    if (upload<int, int>(s, di.data(), di.size(), &out->dep_idx)) return -1;
+    return 0;
+}
+
+extern "C" int smcp_sym_create(smcp_ctx *ctx, const smcp_sym_desc *D, smcp_sym **out) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (D->nblk >= (1LL << 31) || D->nupd >= (1LL << 31)) {
+        smcp_set_error("pattern too large for 32-bit block offsets");
+        return -2;
+    }
+    smcp_sym *s = new smcp_sym();
+    s->ctx = ctx;
+    SymDev &d = s->d;
+    d.n = (int)D->n; d.nsn = (int)D->nsn; d.nvp = (int)D->nvp; d.nblk = (int)D->nblk; d.nupd = (int)D->nupd;
+    const int nsn = d.nsn;
+    std::vector<int> nn(nsn), na(nsn);
+    s->max_nj = s->max_nn = s->max_na = 0;
+    for (int k = 0; k < nsn; ++k) {
+        nn[k] = (int)(D->snptr[k + 1] - D->snptr[k]);
+        na[k] = (int)(D->rowptr[k + 1] - D->rowptr[k]) - nn[k];
+        s->max_nn = std::max(s->max_nn, nn[k]);
+        s->max_na = std::max(s->max_na, na[k]);
+        s->max_nj = std::max(s->max_nj, nn[k] + na[k]);
+    }
+    int rc = 0;
+    rc |= upload<int, int64_t>(s, D->snptr, nsn + 1, &d.snptr);
+    rc |= upload<int, int64_t>(s, D->snpar, nsn, &d.snpar);
+    rc |= upload<int, int64_t>(s, D->rowptr, nsn + 1, &d.rowptr);
+    rc |= upload<int, int64_t>(s, D->rowidx, D->rowptr[nsn], &d.rowidx);
+    rc |= upload<int, int64_t>(s, D->chptr, nsn + 1, &d.chptr);
+    rc |= upload<int, int64_t>(s, D->chidx, D->chptr[nsn], &d.chidx);
+    rc |= upload<int, int64_t>(s, D->relptr, nsn + 1, &d.relptr);
+    rc |= upload<int, int64_t>(s, D->relidx, D->relptr[nsn], &d.relidx);
+    rc |= upload<int, int>(s, nn.data(), nsn, &d.nn);
+    rc |= upload<int, int>(s, na.data(), nsn, &d.na);
+    rc |= upload<int, int64_t>(s, D->aaidx, D->nupd, &d.aaidx);
+    rc |= upload<int, int64_t>(s, D->vec2blk, D->nvp, &d.vec2blk);
+    rc |= upload<int, int64_t>(s, D->diagblk, D->n, &d.diagblk);
+    rc |= upload<long long, int64_t>(s, D->blkptr, nsn + 1, &d.blkptr);
+    rc |= upload<long long, int64_t>(s, D->updptr, nsn + 1, &d.updptr);
+    rc |= upload<double, double>(s, D->wdot, D->nblk, &d.wdot);
+    if (rc) return -1;
+    s->h_vec2blk.assign(D->nvp, 0);
+    for (int64_t i = 0; i < D->nvp; ++i) s->h_vec2blk[i] = (int)D->vec2blk[i];
+
+    // schedules
+    const int nt = (int)D->ntask;
+    std::vector<int> tp(nt + 1), ts(nsn), dp(nt + 1), di(D->dep_ptr[nt]);
+    for (int i = 0; i <= nt; ++i) { tp[i] = (int)D->task_ptr[i]; dp[i] = (int)D->dep_ptr[i]; }
+    for (int i = 0; i < nsn; ++i) ts[i] = (int)D->task_sn[i];
+    for (size_t i = 0; i < di.size(); ++i) di[i] = (int)D->dep_idx[i];
+    if (upload_sched(s, nt, tp, ts, dp, di, &s->up)) return -1;
+    // top-down: reversed task order, reversed supernode order, dependency = parent's task
+    std::vector<int> task_of(nsn);
+    for (int t = 0; t < nt; ++t)
+        for (int p = tp[t]; p < tp[t + 1]; ++p) task_of[ts[p]] = t;
+    std::vector<int> tp2(nt + 1), ts2(nsn), dp2(nt + 1), di2;
+    tp2[0] = 0; dp2[0] = 0;
+    for (int t2 = 0; t2 < nt; ++t2) {
+        int t = nt - 1 - t2;
+        int len = tp[t + 1] - tp[t];
+        for (int p = 0; p < len; ++p) ts2[tp2[t2] + p] = ts[tp[t + 1] - 1 - p];
+        tp2[t2 + 1] = tp2[t2] + len;
+        int top = ts[tp[t + 1] - 1];
+        int64_t par = D->snpar[top];
+        if (par >= 0) di2.push_back(nt - 1 - task_of[par]);
+        dp2[t2 + 1] = (int)di2.size();
+    }
+    if (upload_sched(s, nt, tp2, ts2, dp2, di2, &s->down)) return -1;
+    std::vector<int> tp3(nsn + 1), ts3(nsn), dp3(nsn + 1, 0), di3;
+    for (int i = 0; i <= nsn; ++i) tp3[i] = i;
+    for (int i = 0; i < nsn; ++i) ts3[i] = i;
+    if (upload_sched(s, nsn, tp3, ts3, dp3, di3, &s->flat)) return -1;
+
+    CUDA_TRY(cudaMalloc(&s->counter, 64));
+    CUDA_TRY(cudaMemset(s->counter, 0, 64));
+    if (sym_ensure(s, 1, true)) return -1;
+    *out = s;
+    return 0;
+}
+
+extern "C" int smcp_sym_destroy(smcp_sym *s) {
+    if (!s) return 0;
+    cudaStreamSynchronize(s->ctx->stream);
+    for (void *p : s->allocs) cudaFree(p);
+    if (s->counter) cudaFree(s->counter);
+    if (s->done) cudaFree(s->done);
+    if (s->fail) cudaFree(s->fail);
+    if (s->upd) cudaFree(s->upd);
+    if (s->cta_ws) cudaFree(s->cta_ws);
+    if (s->tmp) cudaFree(s->tmp);
+    if (s->red) cudaFree(s->red);
+    delete s;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// chordal matrices
+// ---------------------------------------------------------------------------------------
+extern "C" int smcp_csp_alloc(smcp_sym *s, int64_t count, double **dev_out) {
+    size_t bytes = (size_t)count * s->d.nblk * sizeof(double);
+    CUDA_TRY(cudaMalloc((void **)dev_out, bytes ? bytes : 8));
+    CUDA_TRY(cudaMemsetAsync(*dev_out, 0, bytes, s->ctx->stream));
+    return 0;
+}
+extern "C" int smcp_csp_free(smcp_sym *s, double *dev) {
+    (void)s;
+    if (dev) CUDA_TRY(cudaFree(dev));
+    return 0;
+}
+extern "C" int smcp_csp_copy(smcp_sym *s, double *dst, const double *src, int64_t count) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)count * s->d.nblk * sizeof(double), cudaMemcpyDeviceToDevice, s->ctx->stream));
+    return 0;
+}
+
+static int stage_buf(smcp_sym *s, size_t bytes, double **out) {
+    // device staging area for host vectors (reuses the reduction scratch)
+    if (grow((void **)&s->red, &s->red_cap, bytes + 4096)) return -1;
+    *out = s->red;
+    return 0;
+}
+
+extern "C" int smcp_csp_from_vec(smcp_sym *s, double *dst, const double *host_vec) {
+    double *dv;
+    if (stage_buf(s, (size_t)s->d.nvp * sizeof(double), &dv)) return -1;
+    CUDA_TRY(cudaMemcpyAsync(dv, host_vec, (size_t)s->d.nvp * sizeof(double), cudaMemcpyHostToDevice, s->ctx->stream));
+    if (k_scatter_vec(s, dst, dv)) return -1;
+    CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));   // host_vec may be pageable / reused
+    return 0;
+}
+extern "C" int smcp_csp_to_vec(smcp_sym *s, const double *src, double *host_vec) {
+    double *dv;
+    if (stage_buf(s, (size_t)s->d.nvp * sizeof(double), &dv)) return -1;
+    if (k_gather_vec(s, src, dv)) return -1;
+    CUDA_TRY(cudaMemcpyAsync(host_vec, dv, (size_t)s->d.nvp * sizeof(double), cudaMemcpyDeviceToHost, s->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
+    return 0;
+}
+extern "C" int smcp_csp_get(smcp_sym *s, const double *src, double *host_blk) {
+    CUDA_TRY(cudaMemcpyAsync(host_blk, src, (size_t)s->d.nblk * sizeof(double), cudaMemcpyDeviceToHost, s->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
+    return 0;
+}
+extern "C" int smcp_csp_set(smcp_sym *s, double *dst, const double *host_blk) {
+    CUDA_TRY(cudaMemcpyAsync(dst, host_blk, (size_t)s->d.nblk * sizeof(double), cudaMemcpyHostToDevice, s->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
+    return 0;
+}
+extern "C" int smcp_csp_axpy(smcp_sym *s, double a, const double *x, double *y) { return k_axpy(s, a, x, y, s->d.nblk); }
+extern "C" int smcp_csp_scal(smcp_sym *s, double a, double *x) { return k_scal(s, a, x, s->d.nblk); }
+extern "C" int smcp_csp_dot(smcp_sym *s, const double *x, const double *y, double *out) { return k_dot(s, x, y, out); }
+extern "C" int smcp_csp_sumlogdiag(smcp_sym *s, const double *x, double *out) { return k_sumlogdiag(s, x, 1, out); }
+extern "C" int smcp_csp_cholesky(smcp_sym *s, double *x, int64_t batch, int32_t *info) { return k_cholesky(s, x, batch, info); }
+extern "C" int smcp_csp_completion(smcp_sym *s, double *x, int64_t batch, int32_t *info) { return k_completion(s, x, batch, info); }
+extern "C" int smcp_csp_projected_inverse(smcp_sym *s, double *x, int64_t batch) { return k_projinv(s, x, batch); }
+extern "C" int smcp_csp_llt(smcp_sym *s, double *x, int64_t batch) { return k_llt(s, x, batch); }
+
+static double *g_probe_buf = nullptr;
+static size_t g_probe_cap = 0;
+
+extern "C" int smcp_csp_probe(smcp_sym *s, int kind, const double *x, const double *dx, const double *gammas_host,
+                              int64_t count, int32_t *info_host, double *sumlogdiag_host) {
+    smcp_ctx *ctx = s->ctx;
+    if (count <= 0) return 0;
+    if (grow((void **)&g_probe_buf, &g_probe_cap, ((size_t)count * s->d.nblk + count + 16) * sizeof(double))) return -1;
+    double *gam = g_probe_buf + (size_t)count * s->d.nblk;
+    CUDA_TRY(cudaMemcpyAsync(gam, gammas_host, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (k_axpy_batch(s, x, dx, gam, g_probe_buf, count)) return -1;
+    int rc = kind == 0 ? k_cholesky(s, g_probe_buf, count, info_host) : k_completion(s, g_probe_buf, count, info_host);
+    if (rc) return rc;
+    if (sumlogdiag_host) return k_sumlogdiag(s, g_probe_buf, count, sumlogdiag_host);
+    return 0;
+}
+
+extern "C" int smcp_csp_trsm(smcp_sym *s, const double *L, double *B_dev, int64_t ldb, int64_t nrhs, int trans) {
+    return k_trsm(s, L, B_dev, ldb, nrhs, trans);
+}
+
+// ---------------------------------------------------------------------------------------
+// Hessian factor
+// ---------------------------------------------------------------------------------------
+extern "C" int smcp_hess_create(smcp_sym *s, const double *L, const double *Y, smcp_hess **out) {
+    smcp_hess *h = new smcp_hess();
+    h->sym = s;
+    h->L = L;
+    CUDA_TRY(cudaMalloc(&h->Lt, (size_t)(s->d.nblk + 1) * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->Yaa, (size_t)(s->d.nupd + 1) * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->Raa, (size_t)(s->d.nupd + 1) * sizeof(double)));
+    if (k_hess_prep(h, L, Y)) return -1;
+    *out = h;
+    return 0;
+}
+extern "C" int smcp_hess_destroy(smcp_hess *h) {
+    if (!h) return 0;
+    cudaStreamSynchronize(h->sym->ctx->stream);
+    cudaFree(h->Lt);
+    cudaFree(h->Yaa);
+    cudaFree(h->Raa);
+    delete h;
+    return 0;
+}
+extern "C" int smcp_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) { return k_hess_apply(h, U, batch, inv); }
+
+// ---------------------------------------------------------------------------------------
+// constraint operator, Schur complement
+// ---------------------------------------------------------------------------------------
+struct smcp_op {
+    smcp_sym *sym = nullptr;
+    int64_t m = 0, Ns = 0, md = 0, nnz = 0;
+    // CSC (rows = blkval offsets)
+    long long *colptr = nullptr;
+    int *rowblk = nullptr;
+    double *vals = nullptr, *valsw = nullptr;
+    int *ent_r = nullptr, *ent_c = nullptr;      // internal (row, col) of each entry
+    // CSR over blkval rows
+    long long *r_ptr = nullptr;
+    int *r_col = nullptr;
+    double *r_val = nullptr;
+    // dense weighted copy w.Av (nblk x m) for the DMMA assembly (only if md > 0)
+    double *AvW = nullptr;
+    double *H = nullptr;
+    int *info_dev = nullptr;
+    double *yv = nullptr;
+    double *Ub = nullptr;
+    size_t Ub_cap = 0;
+    double *Zinv = nullptr;       // n x n dense inverse for the sparse-constraint technique
+    std::vector<long long> h_colptr;
+    void *allocs[16] = {0};
+};
+
+__global__ void amap_kernel(const long long *__restrict__ colptr, const int *__restrict__ rowblk,
+                            const double *__restrict__ valsw, const double *__restrict__ X, double *out,
+                            long long col0, int ncols) {
+    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (w >= ncols) return;
+    long long c = col0 + w;
+    double s = 0.0;
+    for (long long p = colptr[c] + lane; p < colptr[c + 1]; p += 32) s = fma(valsw[p], X[rowblk[p]], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) out[w] = s;
+}
+
+__global__ void aadj_kernel(const long long *__restrict__ r_ptr, const int *__restrict__ r_col,
+                            const double *__restrict__ r_val, const double *__restrict__ y, double *X, int nrows) {
+    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (w >= nrows) return;
+    double s = 0.0;
+    for (long long p = r_ptr[w] + lane; p < r_ptr[w + 1]; p += 32) s = fma(r_val[p], y[r_col[p]], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) X[w] = s;
+}
+
+__global__ void scatter_cols_kernel(const long long *__restrict__ colptr, const int *__restrict__ rowblk,
+                                    const double *__restrict__ vals, double *U, long long ldu, long long c0, int ncols) {
+    // one CTA per column
+    int c = blockIdx.x;
+    if (c >= ncols) return;
+    double *u = U + (long long)c * ldu;
+    for (long long p = colptr[c0 + c] + threadIdx.x; p < colptr[c0 + c + 1]; p += blockDim.x) u[rowblk[p]] = vals[p];
+}
+
+template <class T>
+static int dev_upload(const std::vector<T> &v, T **out) {
+    size_t n = v.size() ? v.size() : 1;
+    CUDA_TRY(cudaMalloc((void **)out, n * sizeof(T)));
+    if (v.size()) CUDA_TRY(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int smcp_op_create(smcp_sym *s, int64_t m, int64_t Ns, const int64_t *colptr, const int64_t *rowind,
+                              const double *values, smcp_op **out) {
+    smcp_ctx *ctx = s->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    smcp_op *op = new smcp_op();
+    op->sym = s;
+    op->m = m;
+    op->Ns = Ns;
+    op->md = m - Ns;
+    const int64_t nnz = colptr[m];
+    op->nnz = nnz;
+    const int nblk = s->d.nblk;
+    std::vector<long long> cp(m + 1);
+    for (int64_t i = 0; i <= m; ++i) cp[i] = colptr[i];
+    op->h_colptr = cp;
+    std::vector<int> rb(nnz);
+    std::vector<double> wd(nblk);
+    CUDA_TRY(cudaMemcpy(wd.data(), s->d.wdot, (size_t)nblk * sizeof(double), cudaMemcpyDeviceToHost));
+    std::vector<double> vw(nnz);
+    for (int64_t p = 0; p < nnz; ++p) {
+        rb[p] = s->h_vec2blk[rowind[p]];
+        vw[p] = values[p] * wd[rb[p]];
+    }
+    // CSR over blkval rows (deterministic: columns ascending inside each row)
+    std::vector<long long> rp(nblk + 1, 0);
+    for (int64_t p = 0; p < nnz; ++p) rp[rb[p] + 1]++;
+    for (int i = 0; i < nblk; ++i) rp[i + 1] += rp[i];
+    std::vector<int> rc(nnz);
+    std::vector<double> rv(nnz);
+    {
+        std::vector<long long> fill(rp.begin(), rp.end() - 1);
+        for (int64_t c = 0; c < m; ++c)
+            for (int64_t p = colptr[c]; p < colptr[c + 1]; ++p) {
+                long long q = fill[rb[p]]++;
+                rc[q] = (int)c;
+                rv[q] = values[p];
+            }
+    }
+    std::vector<double> vals(values, values + nnz);
+    if (dev_upload(cp, &op->colptr) || dev_upload(rb, &op->rowblk) || dev_upload(vals, &op->vals) ||
+        dev_upload(vw, &op->valsw) || dev_upload(rp, &op->r_ptr) || dev_upload(rc, &op->r_col) ||
+        dev_upload(rv, &op->r_val))
+        return -1;
+    CUDA_TRY(cudaMalloc(&op->H, (size_t)std::max<int64_t>(m * m, 1) * sizeof(double)));
+    CUDA_TRY(cudaMemset(op->H, 0, (size_t)std::max<int64_t>(m * m, 1) * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&op->info_dev, 64));
+    CUDA_TRY(cudaMalloc(&op->yv, (size_t)(m + 1) * sizeof(double)));
+    if (op->md > 0) {
+        // dense weighted copy of all m columns (rows of H below the dense block included)
+        size_t bytes = (size_t)nblk * (size_t)m * sizeof(double);
+        CUDA_TRY(cudaMalloc(&op->AvW, bytes));
+        CUDA_TRY(cudaMemsetAsync(op->AvW, 0, bytes, ctx->stream));
+        LaunchScope ls(ctx, "setup");
+        scatter_cols_kernel<<<(unsigned)m, 128, 0, ctx->stream>>>(op->colptr, op->rowblk, op->valsw, op->AvW, nblk, 0, (int)m);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *out = op;
+    return 0;
+}
+
+// (row, col) in the internal order of every entry of Av, needed by the sparse technique
+extern "C" int smcp_op_set_entry_coords(smcp_op *op, const int64_t *rows_int, const int64_t *cols_int) {
+    std::vector<int> r(op->nnz), c(op->nnz);
+    for (int64_t p = 0; p < op->nnz; ++p) { r[p] = (int)rows_int[p]; c[p] = (int)cols_int[p]; }
+    if (dev_upload(r, &op->ent_r) || dev_upload(c, &op->ent_c)) return -1;
+    return 0;
+}
+
+extern "C" int smcp_op_destroy(smcp_op *op) {
+    if (!op) return 0;
+    cudaStreamSynchronize(op->sym->ctx->stream);
+    cudaFree(op->colptr); cudaFree(op->rowblk); cudaFree(op->vals); cudaFree(op->valsw);
+    cudaFree(op->r_ptr); cudaFree(op->r_col); cudaFree(op->r_val);
+    if (op->ent_r) cudaFree(op->ent_r);
+    if (op->ent_c) cudaFree(op->ent_c);
+    if (op->AvW) cudaFree(op->AvW);
+    if (op->Ub) cudaFree(op->Ub);
+    if (op->Zinv) cudaFree(op->Zinv);
+    cudaFree(op->H); cudaFree(op->info_dev); cudaFree(op->yv);
+    delete op;
+    return 0;
+}
+
+extern "C" int smcp_op_amap(smcp_op *op, const double *X, int64_t col, double *host_out) {
+    smcp_ctx *ctx = op->sym->ctx;
+    int64_t c0 = col >= 0 ? col : 0;
+    int ncols = col >= 0 ? 1 : (int)op->m;
+    if (ncols == 0) return 0;
+    {
+        LaunchScope ls(ctx, "amap");
+        amap_kernel<<<(ncols * 32 + 255) / 256, 256, 0, ctx->stream>>>(op->colptr, op->rowblk, op->valsw, X, op->yv, c0, ncols);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(host_out, op->yv, (size_t)ncols * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int smcp_op_aadj(smcp_op *op, const double *host_y, double *X) {
+    smcp_ctx *ctx = op->sym->ctx;
+    CUDA_TRY(cudaMemcpyAsync(op->yv, host_y, (size_t)op->m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    int nrows = op->sym->d.nblk;
+    {
+        LaunchScope ls(ctx, "aadj");
+        aadj_kernel<<<(unsigned)(((long long)nrows * 32 + 255) / 256), 256, 0, ctx->stream>>>(op->r_ptr, op->r_col, op->r_val, op->yv, X, nrows);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));   // host_y may be reused by the caller
+    return 0;
+}
+
+// sparse-constraint technique (solvers.py:489-497 + misc.c:620-663) on the dense inverse
+// Z = S^{-1} (internal order): H[i, j] = sum_{(r,c) in A_j} sum_{(r1,c1) in A_i}
+//   alpha beta [Z(r1,r) Z(c1,c) + (r1 != c1) Z(c1,r) Z(r1,c)],  alpha doubled off the diagonal.
+__global__ void scm_sparse_kernel(const long long *__restrict__ colptr, const double *__restrict__ vals,
+                                  const int *__restrict__ er, const int *__restrict__ ec,
+                                  const double *__restrict__ Z, long long n, double *H, long long m,
+                                  long long j0) {
+    long long j = j0 + blockIdx.x;
+    long long pj0 = colptr[j], pj1 = colptr[j + 1];
+    for (long long i = j + threadIdx.x; i < m; i += blockDim.x) {
+        double acc = 0.0;
+        for (long long p = pj0; p < pj1; ++p) {
+            int r = er[p], c = ec[p];
+            double alpha = vals[p] * (r != c ? 2.0 : 1.0);
+            const double *Zr = Z + (long long)r * n, *Zc = Z + (long long)c * n;
+            double t = 0.0;
+            for (long long q = colptr[i]; q < colptr[i + 1]; ++q) {
+                int r1 = er[q], c1 = ec[q];
+                double beta = vals[q];
+                double v = Zr[r1] * Zc[c1];
+                if (r1 != c1) v = fma(Zr[c1], Zc[r1], v);
+                t = fma(beta, v, t);
+            }
+            acc = fma(alpha, t, acc);
+        }
+        H[i + j * m] = acc;
+    }
+}
+
+__global__ void set_identity_kernel(double *Z, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) Z[i + i * n] = 1.0;
+}
+
+extern "C" int smcp_kkt_assemble(smcp_op *op, smcp_hess *h, int64_t j0, int64_t j1) {
+    smcp_sym *s = op->sym;
+    smcp_ctx *ctx = s->ctx;
+    const int64_t m = op->m, md = op->md;
+    const long long nblk = s->d.nblk;
+    if (j1 > m) j1 = m;
+    // technique 1: batched Hessian + DMMA contraction
+    int64_t d0 = std::max<int64_t>(j0, 0), d1 = std::min<int64_t>(j1, md);
+    if (d1 > d0) {
+        size_t per_col = ((size_t)nblk + (size_t)s->d.nupd) * sizeof(double);
+        int64_t chunk = (int64_t)std::max<size_t>(1, ((size_t)6 << 30) / per_col);
+        chunk = std::min<int64_t>(chunk, 2048);
+        chunk = std::min<int64_t>(chunk, d1 - d0);
+        if (grow((void **)&op->Ub, &op->Ub_cap, (size_t)chunk * nblk * sizeof(double))) return -1;
+        for (int64_t c0 = d0; c0 < d1; c0 += chunk) {
+            int64_t nc = std::min<int64_t>(chunk, d1 - c0);
+            CUDA_TRY(cudaMemsetAsync(op->Ub, 0, (size_t)nc * nblk * sizeof(double), ctx->stream));
+            {
+                LaunchScope ls(ctx, "scatter_cols");
+                scatter_cols_kernel<<<(unsigned)nc, 128, 0, ctx->stream>>>(op->colptr, op->rowblk, op->vals, op->Ub, nblk, c0, (int)nc);
+            }
+            if (k_hess_apply(h, op->Ub, nc, 0)) return -1;
+            // H[c0:m, c0:c0+nc] = (w.Av[:, c0:m])^T W
+            if (d_gemm_tn(ctx, op->AvW + (size_t)c0 * nblk, nblk, op->Ub, nblk, op->H + c0 + c0 * m, m, m - c0, nc, nblk, 0)) return -1;
+        }
+    }
+    // technique 2: sparse constraints through the dense inverse of S
+    int64_t s0 = std::max<int64_t>(j0, md), s1 = j1;
+    if (s1 > s0) {
+        if (!op->ent_r) { smcp_set_error("entry coordinates not set (smcp_op_set_entry_coords)"); return -2; }
+        const long long n = s->d.n;
+        if (!op->Zinv) CUDA_TRY(cudaMalloc(&op->Zinv, (size_t)n * n * sizeof(double)));
+        CUDA_TRY(cudaMemsetAsync(op->Zinv, 0, (size_t)n * n * sizeof(double), ctx->stream));
+        {
+            LaunchScope ls(ctx, "setup");
+            set_identity_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(op->Zinv, n);
+        }
+        if (k_trsm(s, h->L, op->Zinv, n, n, 0)) return -1;
+        if (k_trsm(s, h->L, op->Zinv, n, n, 1)) return -1;
+        {
+            LaunchScope ls(ctx, "scm_sparse");
+            scm_sparse_kernel<<<(unsigned)(s1 - s0), 128, 0, ctx->stream>>>(op->colptr, op->vals, op->ent_r, op->ent_c, op->Zinv, n, op->H, m, s0);
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int smcp_kkt_factor(smcp_op *op, int32_t *info_host) {
+    smcp_ctx *ctx = op->sym->ctx;
+    if (d_potrf(ctx, op->H, op->m, op->info_dev)) return -1;
+    CUDA_TRY(cudaMemcpyAsync(info_host, op->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int smcp_kkt_solve(smcp_op *op, double *host_y) {
+    smcp_ctx *ctx = op->sym->ctx;
+    CUDA_TRY(cudaMemcpyAsync(op->yv, host_y, (size_t)op->m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (d_potrs(ctx, op->H, op->m, op->yv)) return -1;
+    CUDA_TRY(cudaMemcpyAsync(host_y, op->yv, (size_t)op->m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int smcp_kkt_get_H(smcp_op *op, double *host_H) {
+    smcp_ctx *ctx = op->sym->ctx;
+    CUDA_TRY(cudaMemcpyAsync(host_H, op->H, (size_t)op->m * op->m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int smcp_kkt_set_H(smcp_op *op, const double *host_H) {
+    smcp_ctx *ctx = op->sym->ctx;
+    CUDA_TRY(cudaMemcpyAsync(op->H, host_H, (size_t)op->m * op->m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int smcp_kkt_H_devptr(smcp_op *op, double **dev_out) {
+    *dev_out = op->H;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// NCCL (loaded lazily so that the library works without it on a single GPU)
+// ---------------------------------------------------------------------------------------
+typedef struct { char internal[128]; } nccl_uid;
+typedef int (*fn_getuid)(nccl_uid *);
+typedef int (*fn_init)(void **, int, nccl_uid, int);
+typedef int (*fn_destroy)(void *);
+typedef int (*fn_bcast)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*fn_group)(void);
+static void *g_nccl = nullptr;
+static fn_getuid p_getuid;
+static fn_init p_init;
+static fn_destroy p_destroy;
+static fn_bcast p_bcast;
+static fn_group p_gstart, p_gend;
+
+static int load_nccl() {
+    if (g_nccl) return 0;
+    g_nccl = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!g_nccl) g_nccl = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!g_nccl) { smcp_set_error("cannot load libnccl.so.2: %s", dlerror()); return -1; }
+    p_getuid = (fn_getuid)dlsym(g_nccl, "ncclGetUniqueId");
+    p_init = (fn_init)dlsym(g_nccl, "ncclCommInitRank");
+    p_destroy = (fn_destroy)dlsym(g_nccl, "ncclCommDestroy");
+    p_bcast = (fn_bcast)dlsym(g_nccl, "ncclBroadcast");
+    p_gstart = (fn_group)dlsym(g_nccl, "ncclGroupStart");
+    p_gend = (fn_group)dlsym(g_nccl, "ncclGroupEnd");
+    if (!p_getuid || !p_init || !p_destroy || !p_bcast || !p_gstart || !p_gend) {
+        smcp_set_error("libnccl is missing required symbols");
+        return -1;
+    }
+    return 0;
+}
+
+extern "C" int smcp_comm_unique_id(char *id_out_128) {
+    if (load_nccl()) return -1;
+    nccl_uid id;
+    int rc = p_getuid(&id);
+    if (rc) { smcp_set_error("ncclGetUniqueId failed (%d)", rc); return -1; }
+    memcpy(id_out_128, id.internal, 128);
+    return 0;
+}
+extern "C" int smcp_comm_init(smcp_ctx *ctx, int rank, int nranks, const char *id_128) {
+    if (load_nccl()) return -1;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    nccl_uid id;
+    memcpy(id.internal, id_128, 128);
+    int rc = p_init(&ctx->nccl_comm, nranks, id, rank);
+    if (rc) { smcp_set_error("ncclCommInitRank failed (%d)", rc); return -1; }
+    return 0;
+}
+extern "C" int smcp_comm_destroy(smcp_ctx *ctx) {
+    if (ctx->nccl_comm) p_destroy(ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+    return 0;
+}
+
+// Column blocks of H are owned block-cyclically: block q (columns [q*block, (q+1)*block))
+// belongs to rank q % nranks.  Every owner broadcasts its blocks (rows j.. of each column
+// block, i.e. the lower trapezoid) so that all ranks end up with the full lower triangle.
+extern "C" int smcp_kkt_allgather(smcp_op *op, int64_t block, int rank, int nranks) {
+    smcp_ctx *ctx = op->sym->ctx;
+    (void)rank;
+    if (!ctx->nccl_comm) { smcp_set_error("NCCL communicator not initialised"); return -2; }
+    const int64_t m = op->m;
+    p_gstart();
+    for (int64_t q = 0, c0 = 0; c0 < m; ++q, c0 += block) {
+        int64_t nc = std::min(block, m - c0);
+        double *ptr = op->H + c0 * m;       // whole columns (contiguous)
+        int rc = p_bcast(ptr, ptr, (size_t)nc * m, 8 /* ncclFloat64 */, (int)(q % nranks), ctx->nccl_comm, ctx->stream);
+        if (rc) { p_gend(); smcp_set_error("ncclBroadcast failed (%d)", rc); return -1; }
+    }
+    p_gend();
+    ctx->launches += 1;
+    return 0;
+}

@@ -1,0 +1,129 @@
+// Internal declarations shared by the translation units of libsmcp_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/smcp_b200.h"
+
+void smcp_set_error(const char *fmt, ...);
+
+#define CUDA_TRY(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            smcp_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                 \
+                           cudaGetErrorString(_e));                                      \
+            return -1;                                                                   \
+        }                                                                                \
+    } while (0)
+
+struct ProfEntry {
+    double ms = 0.0;
+    int64_t launches = 0;
+};
+
+struct smcp_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;       // user timer
+    cudaEvent_t pev0 = nullptr, pev1 = nullptr;     // profiling events
+    int64_t launches = 0;
+    bool prof = false;
+    std::map<std::string, ProfEntry> prof_acc;
+    double *flush_buf = nullptr;
+    size_t flush_bytes = 0;
+    void *nccl_comm = nullptr;
+    // pinned staging for small host<->device transfers
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
+};
+
+// RAII helper: counts a launch and (when profiling) times the enclosed kernel(s).
+struct LaunchScope {
+    smcp_ctx *ctx;
+    const char *name;
+    int n;
+    LaunchScope(smcp_ctx *c, const char *nm, int nlaunch = 1);
+    ~LaunchScope();
+};
+
+// Device-side view of the symbolic object (int32 indices).
+struct SymDev {
+    int n, nsn, nvp, nblk, nupd;
+    const int *snptr, *snpar, *rowptr, *rowidx, *chptr, *chidx, *relptr, *relidx;
+    const int *nn, *na;
+    const int *aaidx, *vec2blk, *diagblk;
+    const long long *blkptr, *updptr;      // 64-bit: nblk*batch can exceed 2^31
+    const double *wdot;
+};
+
+struct TaskSched {
+    int ntask;
+    const int *task_ptr, *task_sn, *dep_ptr, *dep_idx;
+};
+
+struct smcp_sym {
+    smcp_ctx *ctx;
+    SymDev d;
+    TaskSched up, down, flat;    // bottom-up, top-down and dependency-free schedules
+    int max_nj, max_nn, max_na;
+    std::vector<void *> allocs;  // device allocations owned by the object
+    // scheduler state
+    unsigned *counter = nullptr;     // work-queue head
+    unsigned *done = nullptr;        // per (task, batch) completion epoch
+    size_t done_cap = 0;
+    unsigned epoch = 0;
+    int *fail = nullptr;             // per batch element failure flags (device)
+    size_t fail_cap = 0;
+    // workspaces (grown on demand)
+    double *upd = nullptr;           // batch x nupd update matrices
+    size_t upd_cap = 0;
+    double *cta_ws = nullptr;        // per-CTA scratch
+    size_t cta_ws_cap = 0;
+    double *tmp = nullptr;           // batch x nblk temporary (out-of-place ops)
+    size_t tmp_cap = 0;
+    double *red = nullptr;           // reduction scratch
+    size_t red_cap = 0;
+    // host copies used by the operator setup
+    std::vector<int> h_vec2blk;
+    std::vector<int64_t> h_snptr;
+};
+
+struct smcp_hess {
+    smcp_sym *sym;
+    double *Lt = nullptr;      // nblk: nu-nu part = L_nn (lower), alpha-nu part = L_an L_nn^{-1}
+    double *Yaa = nullptr;     // nupd: Y_{alpha alpha}, full symmetric
+    double *Raa = nullptr;     // nupd: chol(Y_aa) (lazily, for the inverse map)
+    bool have_Raa = false;
+    const double *L = nullptr; // the factor it was built from (not owned)
+};
+
+int sym_ensure(smcp_sym *s, int64_t batch, bool need_tmp);
+int grow(void **p, size_t *cap, size_t bytes);
+
+// chordal kernels (chordal.cu)
+int k_cholesky(smcp_sym *s, double *x, int64_t batch, int32_t *info_host);
+int k_completion(smcp_sym *s, double *x, int64_t batch, int32_t *info_host);
+int k_projinv(smcp_sym *s, double *x, int64_t batch);
+int k_llt(smcp_sym *s, double *x, int64_t batch);
+int k_hess_prep(smcp_hess *h, const double *L, const double *Y);
+int k_hess_prep_inv(smcp_hess *h);
+int k_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv);
+int k_trsm(smcp_sym *s, const double *L, double *B, int64_t ldb, int64_t nrhs, int trans);
+int k_axpy(smcp_sym *s, double a, const double *x, double *y, int64_t len);
+int k_scal(smcp_sym *s, double a, double *x, int64_t len);
+int k_dot(smcp_sym *s, const double *x, const double *y, double *out_host);
+int k_sumlogdiag(smcp_sym *s, const double *x, int64_t batch, double *out_host);
+int k_scatter_vec(smcp_sym *s, double *dst, const double *dev_vec);
+int k_gather_vec(smcp_sym *s, const double *src, double *dev_vec);
+int k_axpy_batch(smcp_sym *s, const double *x, const double *dx, const double *gam_dev, double *out, int64_t count);
+
+// dense kernels (dense.cu)
+int d_potrf(smcp_ctx *ctx, double *H, int64_t m, int32_t *info_dev);
+int d_potrs(smcp_ctx *ctx, const double *H, int64_t m, double *y_dev);
+// C(lower blocks, rows i0.. ) = A^T * B : A is K x M (col-major, ld K), B is K x N
+int d_gemm_tn(smcp_ctx *ctx, const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
+              int64_t ldc, int64_t M, int64_t N, int64_t K, int64_t row_lo_of_col0);

@@ -1,0 +1,71 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(autouse=True)
+def _reset_solver_state():
+    from smcp_b200 import solvers
+    saved = dict(solvers.options)
+    yield
+    solvers.options.clear()
+    solvers.options.update(saved)
+    solvers.set_backend_factory(None)
+
+
+def random_pattern(n, nextra, bw, seed):
+    """Lower pattern: band of width bw plus nextra random off-diagonal pairs."""
+    from smcp_b200.symbolic import lower_pattern
+    rng = np.random.default_rng(seed)
+    I, J = [], []
+    for j in range(n):
+        for i in range(j, min(n, j + bw + 1)):
+            I.append(i)
+            J.append(j)
+    e = rng.integers(0, n, size=(nextra, 2))
+    I += list(e[:, 0])
+    J += list(e[:, 1])
+    return lower_pattern(n, I, J)
+
+
+def make_symbolic(n, nextra, bw, seed):
+    from smcp_b200.symbolic import Symbolic, embed, min_degree, maxcardsearch
+    cp, ri = random_pattern(n, nextra, bw, seed)
+    p = maxcardsearch(n, cp, ri)
+    fc, fr, _ = embed(n, cp, ri, p)
+    if fc[-1] != cp[-1]:
+        p = min_degree(n, cp, ri)
+        fc, fr, _ = embed(n, cp, ri, p)
+    return Symbolic(n, fc, fr)
+
+
+def random_pd(symb, seed, shift=0.5):
+    """blkval array of a random positive definite chordal matrix."""
+    from oracle import dense as dn
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(symb.nblk) * (symb.wdot > 0)
+    M = dn.to_dense(symb, x)
+    M += np.diag(np.abs(M).sum(1) + shift)
+    return dn.project(symb, M)
+
+
+PATTERNS = [
+    # (n, extra edges, bandwidth, seed)
+    (40, 30, 1, 0),      # sparse random, mixed supernodes
+    (60, 40, 2, 1),
+    (30, 0, 3, 2),       # band: chain of tiny cliques
+    (25, 200, 1, 3),     # nearly dense: one large supernode
+    (1, 0, 0, 4),        # 1 x 1
+    (12, 0, 0, 5),       # diagonal: n independent 1 x 1 supernodes (forest)
+    (150, 120, 2, 6),
+]

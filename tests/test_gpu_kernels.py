@@ -1,0 +1,148 @@
+"""Parity of every CUDA kernel family with the CPU oracle, through the C ABI
+(``smcp_b200.device.DeviceBackend`` -> ``libsmcp_b200.so``).  FP64 throughout; tolerance
+1e-11 relative (Frobenius) unless stated — far inside the north star's 1e-8."""
+import numpy as np
+import pytest
+
+from conftest import PATTERNS, make_symbolic, random_pd
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-11
+
+
+def relerr(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+@pytest.fixture(scope="module", params=PATTERNS, ids=lambda p: "n%d_e%d_bw%d" % p[:3])
+def setup(request):
+    from smcp_b200.device import DeviceBackend
+    from oracle import supernodal as sn
+    n, ne, bw, seed = request.param
+    symb = make_symbolic(n, ne, bw, seed)
+    dev = DeviceBackend(symb, small_work=2000)
+    s = random_pd(symb, seed)
+    l = s.copy()
+    sn.cholesky(symb, l)
+    y = l.copy()
+    sn.projected_inverse(symb, y)
+    return symb, dev, s, l, y
+
+
+def test_roundtrip_vec(setup):
+    symb, dev, s, l, y = setup
+    v = np.random.default_rng(0).standard_normal(symb.nvp)
+    b = dev.from_vec(v)
+    assert np.array_equal(dev.to_vec(b), v)
+    blk = dev.get_blk(b)
+    assert np.array_equal(blk[symb.vec2blk], v)
+    assert np.count_nonzero(blk) <= symb.nvp
+
+
+def test_cholesky(setup):
+    from oracle import supernodal as sn
+    symb, dev, s, l, y = setup
+    b = dev.set_blk(s)
+    dev.cholesky(b)
+    assert relerr(dev.get_blk(b), l) < TOL
+    assert abs(dev.sumlogdiag(b) - sn.sumlogdiag(symb, l)) < 1e-10 * max(1, symb.n)
+
+
+def test_cholesky_not_pd(setup):
+    symb, dev, s, l, y = setup
+    bad = s.copy()
+    bad[symb.diag_blk[symb.n // 2]] = -1.0
+    b = dev.set_blk(bad)
+    with pytest.raises(ArithmeticError):
+        dev.cholesky(b)
+    nanm = s.copy()
+    nanm[symb.diag_blk[0]] = np.nan
+    with pytest.raises(ArithmeticError):
+        dev.cholesky(dev.set_blk(nanm))
+
+
+def test_llt(setup):
+    symb, dev, s, l, y = setup
+    b = dev.set_blk(l)
+    dev.llt(b)
+    assert relerr(dev.get_blk(b), s) < TOL
+
+
+def test_projected_inverse(setup):
+    symb, dev, s, l, y = setup
+    b = dev.set_blk(l)
+    dev.projected_inverse(b)
+    assert relerr(dev.get_blk(b), y) < TOL
+
+
+def test_completion(setup):
+    from oracle import supernodal as sn
+    symb, dev, s, l, y = setup
+    b = dev.set_blk(y)
+    dev.completion(b)
+    lc = y.copy()
+    sn.completion(symb, lc)
+    assert relerr(dev.get_blk(b), lc) < 1e-9          # conditioning of the completion map
+    assert relerr(dev.get_blk(b), l) < 1e-9           # completion(P(S^-1)) recovers chol(S)
+    bad = y.copy()
+    bad[symb.diag_blk[symb.n // 2]] = -1.0
+    with pytest.raises(ArithmeticError):
+        dev.completion(dev.set_blk(bad))
+
+
+def test_dot_axpy_scal(setup):
+    from oracle import supernodal as sn
+    symb, dev, s, l, y = setup
+    bs, by = dev.set_blk(s), dev.set_blk(y)
+    assert abs(dev.dot(bs, by) - sn.dot(symb, s, y)) <= 1e-12 * abs(sn.dot(symb, s, y)) + 1e-300
+    dev.axpy(0.37, bs, by)
+    assert np.array_equal(dev.get_blk(by), y + 0.37 * s)     # mul then add, no FMA: bit-exact
+    dev.scal(-1.7, by)
+    assert np.array_equal(dev.get_blk(by), (y + 0.37 * s) * -1.7)
+
+
+@pytest.mark.parametrize("batch", [1, 5])
+def test_hessian_forward_inverse(setup, batch):
+    from oracle import supernodal as sn
+    symb, dev, s, l, y = setup
+    rng = np.random.default_rng(11)
+    hf = sn.HessianFactor(symb, l, y)
+    tok = dev.hessian_factor(dev.set_blk(l), dev.set_blk(y))
+    U = rng.standard_normal((batch, symb.nblk)) * (symb.wdot > 0)
+    W = U.copy()
+    sn.hessian(hf, W)
+    bufs = [dev.set_blk(u) for u in U]
+    dev.hessian_apply(tok, bufs, False)
+    got = np.array([dev.get_blk(b) for b in bufs])
+    assert relerr(got, W) < TOL
+    dev.hessian_apply(tok, bufs, True)
+    back = np.array([dev.get_blk(b) for b in bufs])
+    Wi = W.copy()
+    sn.hessian_inv(hf, Wi)
+    assert relerr(back, Wi) < 1e-9
+    assert relerr(back, U) < 1e-8
+
+
+def test_probe_batch(setup):
+    symb, dev, s, l, y = setup
+    rng = np.random.default_rng(5)
+    d = rng.standard_normal(symb.nblk) * (symb.wdot > 0)
+    gam = np.array([0.0, 1e-3, 0.1, 0.5, 1.0, 4.0, 50.0])
+    ok, sld = dev.probe("cholesky", dev.set_blk(s), dev.set_blk(d), gam)
+    from oracle import supernodal as sn
+    for g, o, v in zip(gam, ok, sld):
+        t = s + g * d
+        try:
+            sn.cholesky(symb, t)
+            assert o and abs(v - sn.sumlogdiag(symb, t)) < 1e-9 * max(1, symb.n)
+        except ArithmeticError:
+            assert not o
+    ok2, _ = dev.probe("completion", dev.set_blk(y), dev.set_blk(d), gam * 1e-2)
+    for g, o in zip(gam * 1e-2, ok2):
+        t = y + g * d
+        try:
+            sn.completion(symb, t)
+            assert o
+        except ArithmeticError:
+            assert not o

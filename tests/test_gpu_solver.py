@@ -1,0 +1,184 @@
+"""Operator / Schur-complement parity and end-to-end driver parity (CUDA vs CPU oracle)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(P, backend_factory):
+    from smcp_b200 import solvers
+    from smcp_b200.solvers import _Problem, _read_options
+    solvers.set_backend_factory(backend_factory)
+    opt = _read_options(P.n, False)
+    return _Problem(P.A, P.b, opt, "chol", None)
+
+
+def _factories():
+    from smcp_b200.device import DeviceBackend
+    from oracle.backend import OracleBackend
+    return (lambda symb: OracleBackend(symb, batch_columns=16)), (lambda symb: DeviceBackend(symb, small_work=5000))
+
+
+def _make(kind):
+    import smcp_b200 as S
+    from smcp_b200 import solvers
+    from oracle.backend import OracleBackend
+    solvers.set_backend_factory(lambda symb: OracleBackend(symb))      # generators probe the cone
+    if kind == "band":
+        return S.band_SDP(40, 12, 3, seed=2)
+    if kind == "mtxnorm":
+        return S.mtxnorm_SDP(12, 4, 9, density=0.6, seed=1)
+    if kind == "rand_sparse":
+        rng = np.random.default_rng(3)
+        n = 60
+        e = rng.integers(0, n, size=(50, 2))
+        V = sp.coo_matrix((np.ones(50 + n), (np.concatenate([e[:, 0], np.arange(n)]),
+                                             np.concatenate([e[:, 1], np.arange(n)]))), shape=(n, n))
+        return S.rand_SDP(V, 25, density=0.03, seed=4)     # few non-zeros -> "sparse" constraints
+    if kind == "maxcut":
+        rng = np.random.default_rng(5)
+        n = 40
+        e = rng.integers(0, n, size=(70, 2))
+        return S.maxcut_SDP(n, e)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["band", "mtxnorm", "rand_sparse", "maxcut"])
+def test_operator_and_schur(kind):
+    from smcp_b200.chordal import cspmatrix, cholesky, projected_inverse, schur_token
+    fo, fd = _factories()
+    P = _make(kind)
+    po, pd = _problem(P, fo), _problem(P, fd)
+    assert po.Ns == pd.Ns and po.symb.nblk == pd.symb.nblk
+    symb = po.symb
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal(symb.nvp)
+    y = rng.standard_normal(po.m)
+    # Amap / Aadj
+    ao = po.Amap(cspmatrix.from_vec(po.ops, v))
+    ad = pd.Amap(cspmatrix.from_vec(pd.ops, v))
+    assert np.linalg.norm(ao - ad) <= 1e-12 * np.linalg.norm(ao) + 1e-300
+    i = po.m // 2
+    assert abs(pd.Amap(cspmatrix.from_vec(pd.ops, v), i) - ao[i]) <= 1e-12 * abs(ao[i]) + 1e-14
+    xo, xd = po.Aadj(y).to_vec(), pd.Aadj(y).to_vec()
+    assert np.linalg.norm(xo - xd) <= 1e-12 * np.linalg.norm(xo) + 1e-300
+    # scaling point: S = I + small symmetric perturbation on the pattern
+    s = np.zeros(symb.nvp)
+    s[symb.diag_vec] = 2.0
+    s += 0.05 * rng.standard_normal(symb.nvp)
+    Ls, Ys, Hs = [], [], []
+    for pr in (po, pd):
+        L = cspmatrix.from_vec(pr.ops, s)
+        cholesky(L)
+        Y = L.copy()
+        projected_inverse(Y)
+        tok = schur_token(L, Y)
+        pr.ops.schur_assemble(tok)
+        H = pr.ops.H.copy() if hasattr(pr.ops, "H") and pr.ops.H is not None else None
+        if H is None or pr is pd:
+            H = pr.ops.get_H()
+        Hs.append(np.tril(H))
+        Ls.append(L)
+        Ys.append(Y)
+    assert np.linalg.norm(Hs[0] - Hs[1]) <= 1e-11 * np.linalg.norm(Hs[0])
+    # potrf / potrs
+    rhs = rng.standard_normal(po.m)
+    po.ops.schur_factor(schur_token(Ls[0], Ys[0]))
+    pd.ops.schur_factor(schur_token(Ls[1], Ys[1]))
+    zo, zd = po.ops.schur_solve(rhs), pd.ops.schur_solve(rhs)
+    assert np.linalg.norm(zo - zd) <= 1e-9 * np.linalg.norm(zo)
+
+
+def test_schur_not_pd_raises():
+    from smcp_b200.device import DeviceBackend
+    fo, fd = _factories()
+    P = _make("band")
+    pd = _problem(P, fd)
+    m = pd.m
+    H = -np.eye(m)
+    from smcp_b200.device import _ck
+    ops = pd.ops
+    _ck(ops.lib, ops.lib.smcp_kkt_set_H(ops._op, np.asfortranarray(H).reshape(-1, order="F")))
+    info = np.zeros(1, dtype=np.int32)
+    _ck(ops.lib, ops.lib.smcp_kkt_factor(ops._op, info))
+    assert info[0] == 1
+
+
+@pytest.mark.parametrize("m", [1, 63, 64, 65, 200, 333])
+def test_dense_potrf_potrs(m):
+    """lapack.potrf / potrs replacement on its own, against numpy."""
+    from smcp_b200.device import _ck
+    import smcp_b200 as S
+    fo, fd = _factories()
+    P = _make("band")
+    pd = _problem(P, fd)
+    # a second operator with m columns on the same pattern just to get an m x m H buffer
+    from smcp_b200.device import DeviceBackend
+    ops = DeviceBackend(pd.symb)
+    Av = sp.random(pd.symb.nvp, m, density=min(1.0, 3.0 / m), random_state=1, format="csc")
+    ops.set_operator(Av, 0)
+    rng = np.random.default_rng(m)
+    G = rng.standard_normal((m, m))
+    H = G @ G.T + m * np.eye(m)
+    _ck(ops.lib, ops.lib.smcp_kkt_set_H(ops._op, np.asfortranarray(np.tril(H)).reshape(-1, order="F")))
+    info = np.zeros(1, dtype=np.int32)
+    _ck(ops.lib, ops.lib.smcp_kkt_factor(ops._op, info))
+    assert info[0] == 0
+    Lh = np.tril(ops.get_H())
+    Lref = np.linalg.cholesky(H)
+    assert np.linalg.norm(Lh - Lref) <= 1e-12 * np.linalg.norm(Lref)
+    rhs = rng.standard_normal(m)
+    z = ops.schur_solve(rhs)
+    assert np.linalg.norm(H @ z - rhs) <= 1e-10 * np.linalg.norm(rhs)
+
+
+def _solve(P, factory, method, scaling):
+    from smcp_b200 import solvers
+    solvers.options["show_progress"] = False
+    solvers.set_backend_factory(factory)
+    if method == "feas":
+        return P.solve_feas(kktsolver="chol", scaling=scaling)
+    return P.solve_esd(kktsolver="chol", scaling=scaling)
+
+
+@pytest.mark.parametrize("kind,method,scaling", [
+    ("band", "feas", "primal"), ("band", "feas", "dual"), ("band", "esd", "primal"),
+    ("band", "esd", "dual"), ("rand_sparse", "feas", "primal"), ("maxcut", "esd", "dual"),
+])
+def test_driver_parity(kind, method, scaling):
+    """North-star parity bar: same iteration count (+-1); objectives, residuals and X/S
+    iterates within 1e-8 relative of the CPU restatement on the same inputs."""
+    from smcp_b200 import solvers
+    fo, fd = _factories()
+    P = _make(kind)
+    if method == "esd":
+        solvers.options["maxiters"] = 12        # compare the first 12 iterates exactly
+    a = _solve(P, fo, method, scaling)
+    b = _solve(P, fd, method, scaling)
+    assert a["status"] == b["status"]
+    assert abs(a["iterations"] - b["iterations"]) <= 1
+    if a["iterations"] == b["iterations"]:
+        for key in ("primal objective", "dual objective"):
+            assert abs(a[key] - b[key]) <= 1e-8 * max(1.0, abs(a[key]))
+        for key in ("x", "s"):
+            d = abs(a[key] - b[key]).max()
+            assert d <= 1e-7 * abs(a[key]).max(), (key, d)
+        ta, tb = a["trace"], b["trace"]
+        for ra, rb in zip(ta[:8], tb[:8]):
+            for key in ("pcost", "dcost", "gap"):
+                if ra.get(key) is not None:
+                    assert abs(ra[key] - rb[key]) <= 1e-8 * max(1.0, abs(ra[key])), (key, ra, rb)
+
+
+def test_conelp_known_answer_gpu():
+    """The reference's only test problem (tests/test_basic.py:9-19): CVXOPT's cone-LP example,
+    optimum x = (-1.22, 0.0966, 3.58)."""
+    from smcp_b200 import solvers
+    from smcp_b200.device import DeviceBackend
+    from test_oracle_drivers import CONELP
+    solvers.options["show_progress"] = False
+    solvers.set_backend_factory(lambda symb: DeviceBackend(symb))
+    sol = solvers.conelp(*CONELP)
+    assert sol["status"] == "optimal"
+    assert np.allclose(sol["x"], [-1.22091527, 0.09663315, 3.57750167], atol=2e-6)

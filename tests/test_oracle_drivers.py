@@ -1,0 +1,119 @@
+"""CPU tests: the drivers on the oracle backend (host logic + oracle numerics)."""
+import numpy as np
+import pytest
+
+c = np.array([-6., -4., -5.])
+G = np.array([[16., 7., 24., -8., 8., -1., 0., -1., 0., 0., 7., -5., 1., -5., 1., -7., 1., -7., -4.],
+              [-14., 2., 7., -13., -18., 3., 0., 0., -1., 0., 3., 13., -6., 13., 12., -10., -6., -10., -28.],
+              [5., 0., -15., 12., -6., 17., 0., 0., 0., -1., 9., 6., -6., 6., -7., -7., -6., -7., -11.]]).T
+h = np.array([-3., 5., 12., -2., -14., -13., 10., 0., 0., 0., 68., -30., -19., -30., 99., 23., -19., 23., 10.])
+CONELP = (c, G, h, {'l': 2, 'q': [4, 4], 's': [3]})
+
+
+@pytest.fixture
+def oracle_backend():
+    from smcp_b200 import solvers
+    from oracle.backend import OracleBackend
+    solvers.options["show_progress"] = False
+    solvers.set_backend_factory(lambda symb: OracleBackend(symb, batch_columns=32))
+    yield
+
+
+def test_conelp_known_answer(oracle_backend):
+    """Data of the reference's own test (tests/test_basic.py:9-19); the optimum is the one
+    printed in the CVXOPT user guide for this cone LP."""
+    from smcp_b200 import solvers
+    sol = solvers.conelp(*CONELP)
+    assert sol["status"] == "optimal"
+    assert np.allclose(sol["x"], [-1.22091527, 0.09663315, 3.57750167], atol=2e-6)
+    assert abs(sol["primal objective"] - sol["dual objective"]) < 1e-5
+
+
+def test_structural_doc_pins(oracle_backend):
+    """The structural known answers of the docs (doc/source/documentation/index.rst:593-596,
+    605-608): <SDP: n=100, m=100, nnz=297> and mtxnorm(200,10,200) -> n=210, m=201, nnz=2210."""
+    import smcp_b200 as S
+    P = S.band_SDP(100, 100, 2, seed=10)
+    assert (P.n, P.m, P.nnz) == (100, 100, 297)
+    Q = S.mtxnorm_SDP(200, 10, 200, seed=0)
+    assert (Q.n, Q.m, Q.nnz) == (210, 201, 2210)
+
+
+@pytest.mark.parametrize("scaling", ["primal", "dual"])
+def test_feas_band(oracle_backend, scaling):
+    import smcp_b200 as S
+    P = S.band_SDP(30, 10, 2, seed=1)
+    sol = P.solve_feas(scaling=scaling)
+    assert sol["status"] == "optimal"
+    assert sol["primal infeasibility"] < 1e-8 and sol["dual infeasibility"] < 1e-8
+    assert abs(sol["primal objective"] - sol["dual objective"]) < 1e-5
+    # known strictly feasible pair => optimal value between the generator's bounds
+    X, Sm, y = sol["x"], sol["s"], sol["y"]
+    n = P.n
+    A = P.A
+    Cm = P.get_A(0)
+    Cfull = Cm + sp_tril_t(Cm)
+    assert abs((Cfull.multiply(X)).sum() - sol["primal objective"]) < 1e-8
+    # dual feasibility: C - sum y_i A_i = S
+    R = Cfull.copy()
+    for i in range(P.m):
+        Ai = P.get_A(i + 1)
+        R = R - y[i] * (Ai + sp_tril_t(Ai))
+    assert abs(R - Sm).max() < 1e-7
+    assert np.linalg.eigvalsh(Sm.toarray()).min() > -1e-9
+
+
+def sp_tril_t(M):
+    import scipy.sparse as sp
+    return sp.tril(M, -1).T
+
+
+def test_esd_band(oracle_backend):
+    import smcp_b200 as S
+    P = S.band_SDP(30, 10, 2, seed=1)
+    sol = P.solve_esd()
+    assert sol["status"] == "optimal"
+    assert abs(sol["primal objective"] - 3.1762985) < 1e-5
+
+
+def test_phase1_then_feas(oracle_backend):
+    """example.py:22-35 flow: mtxnorm problem, phase 1 for a primal start, then solve_feas."""
+    import smcp_b200 as S
+    P = S.mtxnorm_SDP(12, 3, 8, seed=0)
+    X0, info = P.solve_phase1()
+    assert X0 is not None
+    sol = P.solve_feas(primalstart={"x": X0})
+    assert sol["status"] == "optimal"
+    assert sol["primal objective"] < 0
+
+
+def test_options_validation(oracle_backend):
+    import smcp_b200 as S
+    from smcp_b200 import solvers
+    P = S.band_SDP(10, 3, 1, seed=0)
+    solvers.options["maxiters"] = 0
+    with pytest.raises(ValueError):
+        P.solve_feas()
+    solvers.options["maxiters"] = 1.5
+    with pytest.raises(TypeError):
+        P.solve_esd()
+    solvers.options["maxiters"] = 100
+    with pytest.raises(ValueError):
+        P.solve_feas(scaling="both")
+    with pytest.raises(NotImplementedError):
+        P.solve_feas(kktsolver="qr")
+
+
+def test_product_backend_fails_loudly_without_cuda():
+    """No CPU fallback: with no CUDA device the default backend must raise."""
+    import smcp_b200 as S
+    from smcp_b200 import solvers
+    from smcp_b200.device import Context
+    solvers.set_backend_factory(None)
+    try:
+        Context.get(0)
+        pytest.skip("a CUDA device is present")
+    except RuntimeError:
+        pass
+    with pytest.raises(RuntimeError):
+        S.band_SDP(10, 3, 1, seed=0)
