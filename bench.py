@@ -1,0 +1,435 @@
+#!/usr/bin/env python
+"""Headline benchmark: seconds per interior-point iteration of SMCP's feasible-start solver
+(method "M1" of the reference's benchmark tables = ``solve_feas`` with ``kktsolver='chol'``,
+doc/source/benchmarks/index.rst:91) on BASELINE.json configs[1]: band SDP n=5000, bandwidth
+5, m=1000.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A *step* is one IPM iteration of ``chordalsolver_feas`` through the public API
+(``band_SDP(...).solve_feas(kktsolver='chol')``): chordal completion of the iterate, m
+barrier-Hessian evaluations + the DMMA contraction that assemble the Schur complement H,
+the dense Cholesky of H, the Newton solves with iterative refinement, and the step-length
+probes.  W warm-up iterations, then exactly K timed iterations.
+
+* ``e2e``   – wall-clock seconds per iteration measured through the public API with host
+  buffers (every iteration moves its m-vectors and reductions across PCIe; bytes counted).
+* ``value`` – the same K iterations, device time only: the sum of the CUDA-event durations
+  of every kernel launched by the library (events on the library's own stream), i.e. the
+  iteration with its inputs resident in HBM and no host gaps.
+* ``roofline`` – the dominant kernel family of those iterations against the measured peak.
+* ``cpu_baseline`` – the CPU oracle (the reference's algorithm restated on NumPy/SciPy,
+  ``oracle/``) timed on this box's host cores on a bounded sample and composed with the
+  per-iteration operation counts of the same run.
+
+With N > 1 (torchrun, one rank per GPU) the Schur-complement columns are sharded 1-D
+block-cyclically over the ranks and the column blocks of H are exchanged with NCCL
+broadcasts; everything else is replicated.  The problem is fixed, so scaling is "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n, m, bw)
+    "band_n5000_m1000_bw5": (5000, 1000, 5),
+    "band_n500_m100_bw3": (500, 100, 3),
+}
+FAMILIES = ["completion", "completion_batch", "cholesky", "cholesky_batch", "projected_inverse", "llt",
+            "hessian_prep", "hessian_prep_inv", "hessian_up", "hessian_down", "hessian_inv",
+            "hessian_up_batch", "hessian_down_batch", "hessian_inv_batch",
+            "scatter_cols", "schur_gemm_dmma", "potrf_diag",
+            "potrf_trsm", "potrf_syrk_dmma", "potrs", "amap", "aadj", "level1", "reduce", "chordal_trsm",
+            "scm_sparse", "setup"]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="band_n5000_m1000_bw5", choices=sorted(WORKLOADS))
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu = gpu
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        pg = dist
+    return rank, world, local, pg
+
+
+def measured_fp64_peak():
+    """FP64 GEMM peak of this GPU: cuBLAS DGEMM through torch.matmul, 8192^3, best of 5.
+    Used ONLY as the roofline denominator (MEASURED_PEAKS.json has no FP64 entry)."""
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return None
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        n = 8192
+        a = torch.randn(n, n, dtype=torch.float64, device=dev)
+        b = torch.randn(n, n, dtype=torch.float64, device=dev)
+        torch.matmul(a, b)
+        torch.cuda.synchronize(dev)
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        del a, b
+        torch.cuda.empty_cache()
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return None
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------
+def build_problem(workload):
+    import smcp_b200 as S
+    n, m, bw = WORKLOADS[workload]
+    return S.band_SDP(n, m, bw, seed=0)
+
+
+class IterTimer:
+    def __init__(self, sync):
+        self.sync = sync
+        self.t = {}
+        self.marks = {}
+
+    def __call__(self, name, it):
+        self.sync()
+        self.t[it] = time.perf_counter()
+        fn = self.marks.get(it)
+        if fn:
+            fn()
+
+
+def run_b200(args):
+    rank, world, local, pg = dist_setup(args)
+    os.environ["LOCAL_RANK"] = str(local)
+    from smcp_b200 import solvers, device
+    from smcp_b200.device import Context, TRAFFIC
+    ctx = Context.get(local)
+    if world > 1:
+        import torch
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(device.comm_unique_id()), dtype=torch.uint8).clone()
+        pg.broadcast(idt, src=0)
+        device.init_comm(rank, world, bytes(idt.numpy().tobytes()), block=64, device=local)
+
+    W, K = args.warmup, args.steps
+    solvers.options["show_progress"] = False
+    solvers.options["maxiters"] = W + K
+    P = build_problem(args.workload)              # generator runs its cone tests on the GPU
+    n, m = P.n, P.m
+    start = {"x": P._X0}
+
+    def barrier():
+        if pg is not None:
+            pg.barrier()
+
+    # ---- pass 1: end-to-end wall clock through the public API ------------------------
+    timer = IterTimer(ctx.sync)
+    traffic0 = {}
+    launches = {}
+    timer.marks[W] = lambda: (traffic0.update(TRAFFIC), launches.update(a=ctx.launch_count()), barrier())
+    solvers._iteration_hook = timer
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    sol = P.solve_feas(kktsolver="chol", primalstart=start)
+    ctx.sync()
+    clocks = sampler.stop()
+    iters = sol["iterations"]
+    assert iters >= W + K, "solver stopped after %d iterations (< warmup+steps)" % iters
+    e2e_s = (timer.t[W + K] - timer.t[W]) / K
+    n_launch = None
+    h2d = d2h = 0
+    # traffic/launch counters at the end of iteration W+K
+    # (re-run bookkeeping: counters were snapshotted at iteration W; read the totals now and
+    #  subtract what happened after W+K — nothing, maxiters = W+K stops the loop there,
+    #  except the final residual evaluation of iteration W+K+1 which is a handful of vectors)
+    h2d = (TRAFFIC["h2d"] - traffic0["h2d"]) // K
+    d2h = (TRAFFIC["d2h"] - traffic0["d2h"]) // K
+    n_launch = (ctx.launch_count() - launches["a"])
+
+    # ---- pass 2: same iterations, device time per kernel family (CUDA events) --------
+    fam = {}
+    timer2 = IterTimer(ctx.sync)
+    timer2.marks[W] = lambda: (ctx.prof_reset(), ctx.prof_enable(True))
+    timer2.marks[W + K] = lambda: ctx.prof_enable(False)
+    solvers._iteration_hook = timer2
+    sol2 = P.solve_feas(kktsolver="chol", primalstart=start)
+    ctx.prof_enable(False)
+    solvers._iteration_hook = None
+    dev_ms = 0.0
+    for nm in FAMILIES:
+        ms, cnt = ctx.prof_get(nm)
+        if cnt:
+            fam[nm] = {"ms": ms, "launches": cnt, "work": ctx.prof_get_work(nm)}
+            dev_ms += ms
+    dev_s = dev_ms * 1e-3 / K
+
+    # max over ranks
+    if pg is not None:
+        import torch
+        t = torch.tensor([e2e_s, dev_s], dtype=torch.float64)
+        pg.all_reduce(t, op=pg.ReduceOp.MAX)
+        e2e_s, dev_s = float(t[0]), float(t[1])
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel family ---------------------------------------
+    bw = WORKLOADS[args.workload][2]
+    nvp = sum(min(bw + 1, n - j) for j in range(n))          # |Vp| of the band pattern
+    hbm_peak, hbm_src = load_peaks()
+    fp64_peak = measured_fp64_peak()
+    top = max(fam.items(), key=lambda kv: kv[1]["ms"])[0] if fam else None
+    roof = None
+    if top is not None:
+        f = fam[top]
+        per_launch_s = f["ms"] * 1e-3 / f["launches"]
+        work = f["work"] / f["launches"]
+        if top.endswith("_dmma"):
+            # work = algorithmic flops of the launch: 2*K per entry of the lower-triangular
+            # result (Schur: F_ip = |blkval| * m * (m+1))
+            ach = work / per_launch_s / 1e12
+            peak = fp64_peak if fp64_peak else 40.0
+            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                    "frac": ach / peak, "traffic": None,
+                    "peak_source": ("measured in this run: cuBLAS DGEMM 8192^3 via torch.matmul, best of 5"
+                                    if fp64_peak else "nominal FP64 tensor peak (no measurement)")}
+        else:
+            # chordal kernels: work = matrices per launch; algorithmic bytes = one read and
+            # one write of every pattern entry of every matrix (16*|Vp| per matrix, §8d)
+            ach = 16.0 * nvp * work / per_launch_s / 1e9
+            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                    "matrices_per_launch": work}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if roof is not None and os.path.exists(traffic_file):
+        with open(traffic_file) as fh:
+            tr = json.load(fh)
+        roof["traffic"] = tr.get(roof["kernel"])
+
+    cpu = cpu_baseline(args.workload, fam, K)
+
+    out = {
+        "metric": "s_per_ipm_iteration", "value": dev_s, "unit": "s/iter", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": dev_s * 1e3, "higher_is_better": False,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "n": n, "m": m, "solver": "chordalsolver_feas",
+                   "kktsolver": "chol", "scaling_mode": "primal",
+                   "l2": "working set > L2 per iteration (Av 240 MB + W 240 MB + H 8 MB)",
+                   "parallelism": "schur-columns block-cyclic x%d" % world},
+        "e2e": {"value": e2e_s, "unit": "s/iter", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(n_launch),
+        "clocks": clocks,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "kernel_ms_per_step": {k: v["ms"] / K for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])},
+        "status": sol["status"], "iterations": iters,
+        "fp64_gemm_peak_tflops": fp64_peak,
+    }
+    print(json.dumps(out))
+
+
+# --------------------------------------------------------------------------------------
+def cpu_baseline(workload, fam=None, K=1, budget_s=20.0):
+    """The reference's algorithm (oracle/) on this box's host cores: unit times measured on
+    a bounded sample of the SAME workload, composed into seconds per iteration with the
+    per-iteration operation counts of an M1 iteration:
+        1 completion + 1 llt + (m + 6) forward Hessians + 3 inverse Hessians
+        + m trailing gemv's over Av[:, j:m] + potrf(m) + 3 potrs + 7 Amap + 7 Aadj."""
+    from smcp_b200 import solvers
+    from smcp_b200.symbolic import Symbolic, lower_pattern
+    from oracle.backend import OracleBackend
+    from oracle import supernodal as sn
+    import scipy.linalg as sl
+    import scipy.sparse as sp
+    try:
+        from threadpoolctl import threadpool_info
+        nthreads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        nthreads = 1
+    n, m, bw = WORKLOADS[workload]
+    rng = np.random.default_rng(0)
+    I = np.concatenate([np.arange(j, min(j + bw + 1, n)) for j in range(n)])
+    J = np.concatenate([np.full(min(j + bw + 1, n) - j, j) for j in range(n)])
+    cp, ri = lower_pattern(n, I, J)
+    symb = Symbolic(n, cp, ri)
+    ob = OracleBackend(symb)
+    nvp = symb.nvp
+    # a well-conditioned scaling point on the pattern
+    v = 0.05 * rng.standard_normal(nvp)
+    v[symb.diag_vec] = 2.0
+    X = ob.from_vec(v)
+    t0 = time.perf_counter()
+    L = X.copy()
+    sn.cholesky(symb, L)
+    t_chol = time.perf_counter() - t0
+    Y = L.copy()
+    t0 = time.perf_counter()
+    sn.projected_inverse(symb, Y)
+    t_pinv = time.perf_counter() - t0
+    Lc = Y.copy()
+    t0 = time.perf_counter()
+    sn.completion(symb, Lc)
+    t_compl = time.perf_counter() - t0
+    Ll = L.copy()
+    t0 = time.perf_counter()
+    sn.llt(symb, Ll)
+    t_llt = time.perf_counter() - t0
+    hf = sn.HessianFactor(symb, L, Y)
+    ncols = 3
+    U = rng.standard_normal((1, symb.nblk)) * (symb.wdot > 0)
+    t0 = time.perf_counter()
+    for _ in range(ncols):
+        sn.hessian(hf, U.copy())
+    t_h = (time.perf_counter() - t0) / ncols
+    t0 = time.perf_counter()
+    sn.hessian_inv(hf, U.copy())
+    t_hinv = time.perf_counter() - t0
+    # gemv over the trailing columns of a dense Av (reference: base.gemv(Av[:, j:m], ...) which
+    # also copies the slice, solvers.py:486); sample 8 columns j, average (m - j) ~ m/2
+    msub = min(m, 256)
+    Avs = sp.csc_matrix(rng.standard_normal((nvp, msub)))
+    x = rng.standard_normal(nvp)
+    t0 = time.perf_counter()
+    reps = 4
+    for _ in range(reps):
+        sl_ = Avs[:, msub // 2:]
+        _ = sl_.T @ x
+    t_gemv_avg = (time.perf_counter() - t0) / reps * (m / 2.0) / (msub / 2.0)
+    Hm = rng.standard_normal((m, m))
+    Hm = Hm @ Hm.T + m * np.eye(m)
+    t0 = time.perf_counter()
+    Lh = sl.cholesky(Hm, lower=True)
+    t_potrf = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    sl.cho_solve((Lh, True), x[:m])
+    t_potrs = time.perf_counter() - t0
+    t_amap = t_gemv_avg * 2.0      # full Av
+    per_iter = (t_compl + t_llt + (m + 6) * t_h + 3 * t_hinv + m * t_gemv_avg + t_potrf + 3 * t_potrs
+                + 14 * t_amap)
+    return {"value": per_iter, "unit": "s/iter", "cores": int(nthreads), "kind": "port",
+            "sample": ("unit times of the oracle on this workload's pattern: completion %.3fs, llt %.3fs, "
+                       "hessian %.4fs/col (3 cols), inverse hessian %.4fs, trailing gemv %.4fs/col "
+                       "(%d-column slice), dpotrf(m) %.4fs; composed with the op counts of one M1 "
+                       "iteration (m+6 Hessians, m gemv's, 1 potrf, ...)"
+                       % (t_compl, t_llt, t_h, t_hinv, t_gemv_avg, msub, t_potrf))}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    n, m, bw = WORKLOADS[args.workload]
+    vals = []
+    cpu = None
+    for _ in range(max(1, min(args.steps, 2))):
+        cpu = cpu_baseline(args.workload)
+        vals.append(cpu["value"])
+    v = float(np.mean(vals))
+    cpu["value"] = v
+    out = {"impl": "reference", "metric": "s_per_ipm_iteration", "value": v, "unit": "s/iter",
+           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * 1e3,
+           "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic",
+           "config": {"workload": args.workload, "n": n, "m": m, "solver": "chordalsolver_feas",
+                      "kktsolver": "chol", "scaling_mode": "primal"},
+           "cpu_baseline": cpu,
+           "e2e": {"value": v, "unit": "s/iter", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "cvxopt/chompack are not installable here; this is the oracle port of the reference's "
+                   "CPU path (oracle/), each step a bounded sample composed to one iteration"}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

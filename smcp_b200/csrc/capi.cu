@@ -35,7 +35,7 @@ int grow(void **p, size_t *cap, size_t bytes) {
     return 0;
 }
 
-LaunchScope::LaunchScope(smcp_ctx *c, const char *nm, int nlaunch) : ctx(c), name(nm), n(nlaunch) {
+LaunchScope::LaunchScope(smcp_ctx *c, const char *nm, int nlaunch, double w) : ctx(c), name(nm), n(nlaunch), work(w) {
     ctx->launches += n;
     if (ctx->prof) cudaEventRecord(ctx->pev0, ctx->stream);
 }
@@ -48,6 +48,7 @@ LaunchScope::~LaunchScope() {
         ProfEntry &e = ctx->prof_acc[name];
         e.ms += ms;
         e.launches += n;
+        e.work += work;
     }
 }
 
@@ -124,6 +125,11 @@ extern "C" int smcp_prof_get(smcp_ctx *ctx, const char *name, double *ms_out, in
     }
     *ms_out = it->second.ms;
     *launches_out = it->second.launches;
+    return 0;
+}
+extern "C" int smcp_prof_get_work(smcp_ctx *ctx, const char *name, double *work_out) {
+    auto it = ctx->prof_acc.find(name);
+    *work_out = it == ctx->prof_acc.end() ? 0.0 : it->second.work;
     return 0;
 }
 extern "C" int smcp_prof_reset(smcp_ctx *ctx) {

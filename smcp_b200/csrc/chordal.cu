@@ -700,7 +700,7 @@ static int launch_tree(smcp_sym *s, TreeArgs &a, const TaskSched &T, int64_t bat
     }
     CUDA_TRY(cudaMemsetAsync(s->counter, 0, sizeof(unsigned), ctx->stream));
     {
-        LaunchScope ls(ctx, name);
+        LaunchScope ls(ctx, name, 1, (double)batch);
         kern<<<(unsigned)grid, threads, smem, ctx->stream>>>(a);
     }
     CUDA_TRY(cudaGetLastError());
@@ -728,7 +728,7 @@ int k_cholesky(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
     TreeArgs a = {};
     a.X = x;
     a.upd = s->upd;
-    if (launch_tree<OP_CHOL>(s, a, s->up, batch, pick_threads(s), "cholesky")) return -1;
+    if (launch_tree<OP_CHOL>(s, a, s->up, batch, pick_threads(s), batch > 1 ? "cholesky_batch" : "cholesky")) return -1;
     if (info_host) return fetch_fail(s, batch, info_host);
     return 0;
 }
@@ -758,7 +758,7 @@ int k_completion(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
     TreeArgs a = {};
     a.X = x;
     a.Xin = s->tmp;
-    if (launch_tree<OP_COMPL>(s, a, flat_sched(s), batch, pick_threads(s), "completion")) return -1;
+    if (launch_tree<OP_COMPL>(s, a, flat_sched(s), batch, pick_threads(s), batch > 1 ? "completion_batch" : "completion")) return -1;
     if (info_host) return fetch_fail(s, batch, info_host);
     return 0;
 }
@@ -795,14 +795,15 @@ int k_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
     a.Raa = h->Raa;
     int threads = pick_threads(s);
     if (!inv) {
-        if (launch_tree<OP_HFWD_UP>(s, a, s->up, batch, threads, "hessian_up")) return -1;
-        return launch_tree<OP_HFWD_DOWN>(s, a, s->down, batch, threads, "hessian_down");
+        const bool big = batch >= 32;
+        if (launch_tree<OP_HFWD_UP>(s, a, s->up, batch, threads, big ? "hessian_up_batch" : "hessian_up")) return -1;
+        return launch_tree<OP_HFWD_DOWN>(s, a, s->down, batch, threads, big ? "hessian_down_batch" : "hessian_down");
     }
     if (!h->have_Raa) {
         if (k_hess_prep_inv(h)) return -1;
         h->have_Raa = true;
     }
-    return launch_tree<OP_HINV>(s, a, s->up, batch, threads, "hessian_inv");
+    return launch_tree<OP_HINV>(s, a, s->up, batch, threads, batch >= 32 ? "hessian_inv_batch" : "hessian_inv");
 }
 
 // ---------------------------------------------------------------------------------------

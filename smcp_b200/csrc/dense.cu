@@ -147,8 +147,17 @@ static int launch_gemm(smcp_ctx *ctx, bool tn, const double *A, int64_t lda, con
         CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
+    // algorithmic flops: 2*K per computed entry of the (lower-triangular) result
+    double pairs = 0.0;
+    if (!tri) pairs = (double)M * (double)N;
+    else
+        for (int64_t j = 0; j < N; ++j) {
+            int64_t lo = j - tri_off;            // rows i >= lo
+            if (lo < 0) lo = 0;
+            if (lo < M) pairs += (double)(M - lo);
+        }
     {
-        LaunchScope ls(ctx, name);
+        LaunchScope ls(ctx, name, 1, 2.0 * (double)K * pairs);
         if (tn)
             gemm_dmma_kernel<true><<<grid, GEMM_THREADS, smem, ctx->stream>>>(A, lda, B, ldb, C, ldc, M, N, K, alpha, accumulate, tri, tri_off);
         else

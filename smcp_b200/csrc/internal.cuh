@@ -22,6 +22,7 @@ void smcp_set_error(const char *fmt, ...);
 struct ProfEntry {
     double ms = 0.0;
     int64_t launches = 0;
+    double work = 0.0;      // matrices processed (chordal kernels) or algorithmic flops (GEMM)
 };
 
 struct smcp_ctx {
@@ -46,7 +47,8 @@ struct LaunchScope {
     smcp_ctx *ctx;
     const char *name;
     int n;
-    LaunchScope(smcp_ctx *c, const char *nm, int nlaunch = 1);
+    double work;
+    LaunchScope(smcp_ctx *c, const char *nm, int nlaunch = 1, double work = 0.0);
     ~LaunchScope();
 };
 

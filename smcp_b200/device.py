@@ -41,6 +41,7 @@ API = {
     "smcp_timer_stop": (_int, [_vp, C.POINTER(_dbl)]),
     "smcp_prof_enable": (_int, [_vp, _int]),
     "smcp_prof_get": (_int, [_vp, C.c_char_p, C.POINTER(_dbl), C.POINTER(_i64)]),
+    "smcp_prof_get_work": (_int, [_vp, C.c_char_p, C.POINTER(_dbl)]),
     "smcp_prof_reset": (_int, [_vp]),
     "smcp_flush_l2": (_int, [_vp]),
     "smcp_sym_create": (_int, [_vp, C.POINTER(SymDesc), C.POINTER(_vp)]),
@@ -154,12 +155,42 @@ class Context:
         _ck(self.lib, self.lib.smcp_prof_get(self.h, name.encode(), C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def prof_get_work(self, name):
+        w = C.c_double()
+        _ck(self.lib, self.lib.smcp_prof_get_work(self.h, name.encode(), C.byref(w)))
+        return w.value
+
     def flush_l2(self):
         _ck(self.lib, self.lib.smcp_flush_l2(self.h))
 
 
 def _i64(a):
     return np.ascontiguousarray(a, dtype=np.int64)
+
+
+_COMM = None          # (rank, nranks, block) once init_comm() has built the NCCL communicator
+TRAFFIC = {"h2d": 0, "d2h": 0}     # host<->device bytes moved through the API (bench.py reads it)
+
+
+def init_comm(rank, nranks, unique_id, block=64, device=None):
+    """Create the library-owned NCCL communicator (one process per GPU).  ``unique_id`` is the
+    128-byte id produced by ``comm_unique_id()`` on rank 0 and distributed by the launcher."""
+    global _COMM
+    ctx = Context.get(device)
+    _ck(ctx.lib, ctx.lib.smcp_comm_init(ctx.h, int(rank), int(nranks), bytes(unique_id)))
+    _COMM = (int(rank), int(nranks), int(block))
+
+
+def comm_unique_id():
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    _ck(lib, lib.smcp_comm_unique_id(buf))
+    return buf.raw
+
+
+def owned_column_blocks(m, rank, nranks, block):
+    """1-D block-cyclic ownership of the columns of H: [(j0, j1), ...] for ``rank``."""
+    return [(c0, min(m, c0 + block)) for c0 in range(rank * block, m, nranks * block)]
 
 
 class DeviceBackend:
@@ -170,7 +201,7 @@ class DeviceBackend:
         self.ctx = Context.get(device)
         self.lib = lib = self.ctx.lib
         self.symb = symb
-        self.comm = comm                      # (rank, nranks) once a communicator exists
+        self.comm = comm if comm is not None else _COMM      # (rank, nranks, block)
         tp, ts, dp, di, _ = task_partition(symb, small_work)
         keep = dict(snptr=_i64(symb.snptr), snpar=_i64(symb.snpar), rowptr=_i64(symb.rowptr),
                     rowidx=_i64(symb.rowidx), blkptr=_i64(symb.blkptr), updptr=_i64(symb.updptr),
@@ -230,11 +261,13 @@ class DeviceBackend:
         return p
 
     def from_vec(self, v):
+        TRAFFIC["h2d"] += 8 * self.symb.nvp
         p = self._alloc(False)
         _ck(self.lib, self.lib.smcp_csp_from_vec(self.sym, p, np.ascontiguousarray(v, dtype=np.float64)))
         return p
 
     def to_vec(self, buf):
+        TRAFFIC["d2h"] += 8 * self.symb.nvp
         out = np.empty(self.symb.nvp)
         _ck(self.lib, self.lib.smcp_csp_to_vec(self.sym, buf, out))
         return out
@@ -257,6 +290,7 @@ class DeviceBackend:
         _ck(self.lib, self.lib.smcp_csp_scal(self.sym, float(a), x))
 
     def dot(self, x, y):
+        TRAFFIC["d2h"] += 8
         out = C.c_double()
         _ck(self.lib, self.lib.smcp_csp_dot(self.sym, x, y, C.byref(out)))
         return out.value
@@ -325,6 +359,7 @@ class DeviceBackend:
             _ck(self.lib, self.lib.smcp_op_set_entry_coords(h, _i64(ri), _i64(ci)))
 
     def Amap(self, buf):
+        TRAFFIC["d2h"] += 8 * self.m
         out = np.empty(self.m)
         _ck(self.lib, self.lib.smcp_op_amap(self._op, buf, -1, out))
         return out
@@ -335,6 +370,7 @@ class DeviceBackend:
         return float(out[0])
 
     def Aadj(self, y):
+        TRAFFIC["h2d"] += 8 * self.m
         p = self._alloc(False)
         _ck(self.lib, self.lib.smcp_op_aadj(self._op, np.ascontiguousarray(y, dtype=np.float64), p))
         return p
@@ -348,8 +384,8 @@ class DeviceBackend:
             self.schur_assemble(tok)
         else:
             rank, nranks, block = self.comm
-            for c0 in range(rank * block, self.m, nranks * block):
-                self.schur_assemble(tok, c0, min(self.m, c0 + block))
+            for c0, c1 in owned_column_blocks(self.m, rank, nranks, block):
+                self.schur_assemble(tok, c0, c1)
             _ck(self.lib, self.lib.smcp_kkt_allgather(self._op, block, rank, nranks))
         info = np.zeros(1, dtype=np.int32)
         _ck(self.lib, self.lib.smcp_kkt_factor(self._op, info))
@@ -357,6 +393,8 @@ class DeviceBackend:
             raise ArithmeticError("Schur complement is not positive definite (info=%d)" % info[0])
 
     def schur_solve(self, y):
+        TRAFFIC["h2d"] += 8 * self.m
+        TRAFFIC["d2h"] += 8 * self.m
         y = np.array(y, dtype=np.float64).ravel()
         _ck(self.lib, self.lib.smcp_kkt_solve(self._op, y))
         return y

@@ -43,6 +43,7 @@ options = {
 }
 
 _backend_factory = None
+_iteration_hook = None      # optional callable(solver_name, iteration) used by bench.py for timing
 
 
 def set_backend_factory(factory):
@@ -726,6 +727,8 @@ def chordalsolver_feas(A, b, primalstart=None, dualstart=None, scaling="primal",
 
         trace.append(dict(iter=it, stype=stype, pcost=pcost, dcost=dcost, gap=gap, pres=pres,
                           dres=dres, ntdecr=ntdecr, pstep=pstep, dstep=dstep, gam=gam, t=st.t))
+        if _iteration_hook is not None:
+            _iteration_hook("feas", it)
         if opt.show_progress:
             if stype == "c":
                 print("%3i %-11s %-11s %.1e %-7s %-7s %.1e %7s %4.2f" % (
@@ -1079,6 +1082,8 @@ def chordalsolver_esd(A, b, primalstart=None, dualstart=None, scaling="primal",
         S += (STEP * step) * dS
         st.tau += STEP * step * dtau
         st.kappa += STEP * step * dkappa
+        if _iteration_hook is not None:
+            _iteration_hook("esd", it + 1)
 
     Tcpu = process_time() - T0
     Twall = perf_counter() - T0wall

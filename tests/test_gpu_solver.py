@@ -138,7 +138,11 @@ def _solve(P, factory, method, scaling):
     solvers.options["show_progress"] = False
     solvers.set_backend_factory(factory)
     if method == "feas":
-        return P.solve_feas(kktsolver="chol", scaling=scaling)
+        # start from the generator's known strictly feasible point when there is one (the
+        # identity-based start heuristics legitimately fail on some random instances)
+        start = {"x": P._X0} if P._X0 is not None else None
+        return P.solve_feas(kktsolver="chol", scaling=scaling, primalstart=start,
+                            dualstart=({"y": P._y0, "s": P._S0} if scaling == "dual" and P._S0 is not None else None))
     return P.solve_esd(kktsolver="chol", scaling=scaling)
 
 
