@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <algorithm>
 #include <dlfcn.h>
@@ -240,6 +241,8 @@ extern "C" int smcp_sym_create(smcp_ctx *ctx, const smcp_sym_desc *D, smcp_sym *
     for (int i = 0; i <= nsn; ++i) tp3[i] = i;
     for (int i = 0; i < nsn; ++i) ts3[i] = i;
     if (upload_sched(s, nsn, tp3, ts3, dp3, di3, &s->flat)) return -1;
+    // tiny cliques: warp-per-chain kernels (SMCP_B200_NO_SMALL=1 forces the CTA kernels)
+    if (s->max_nj <= 8 && !getenv("SMCP_B200_NO_SMALL") && small_setup(s, D, tp, ts, tp2, ts2)) return -1;
 
     CUDA_TRY(cudaMalloc(&s->counter, 64));
     CUDA_TRY(cudaMemset(s->counter, 0, 64));
@@ -259,6 +262,7 @@ extern "C" int smcp_sym_destroy(smcp_sym *s) {
     if (s->cta_ws) cudaFree(s->cta_ws);
     if (s->tmp) cudaFree(s->tmp);
     if (s->red) cudaFree(s->red);
+    if (s->fbuf) cudaFree(s->fbuf);
     delete s;
     return 0;
 }

@@ -67,6 +67,24 @@ struct TaskSched {
     const int *task_ptr, *task_sn, *dep_ptr, *dep_idx;
 };
 
+// Extra device tables of the warp-per-chain kernels for tiny cliques (chordal_small.cu).
+// A "step" is one supernode visit of a sweep; its descriptor is two int4:
+//   up  : {nn | na<<4 | flags<<8 | run<<16, blkptr[k], rowslot, slotpos}, {upd tile, och_beg, och_cnt, sqptr[k]}
+//   down: {nn | na<<4 | flags<<8 | run<<16, blkptr[k], rowslot, slotpos}, {updptr[k], 0, 0, 0}
+// run = number of consecutive "uniform" steps starting here (same clique shape as the previous step,
+// separator = leading rows of the next clique), processed in the position layout.
+// rowslot: nibble q = slot of the q-th row of the clique; slotpos: nibble s = position of the row
+// that owns slot s (15 = slot unused).  A chunk is {p_begin, p_end, blk_lo, blk_hi}, {sq_lo, sq_hi, 0, 0}.
+struct SmallDev {
+    const int4 *up_steps, *down_steps;
+    const int4 *up_chunks, *down_chunks, *add_chunks;            // add: also bounded by the local fronts
+    const int *up_chunk_ptr, *down_chunk_ptr, *add_chunk_ptr;    // ntask+1 each
+    const int *och;           // update-matrix tiles of the children that are not the previous step
+    const long long *sqptr;   // nsn+1: offsets of the nj x nj local fronts in the F scratch
+    long long nsq;
+    int ntiles;               // supernodes whose update matrix goes through a global 8 x 8 tile
+};
+
 struct smcp_sym {
     smcp_ctx *ctx;
     SymDev d;
@@ -89,6 +107,11 @@ struct smcp_sym {
     size_t tmp_cap = 0;
     double *red = nullptr;           // reduction scratch
     size_t red_cap = 0;
+    // tiny-clique path (max_nj <= 8): warp-per-chain sweeps, see chordal_small.cu
+    bool small = false;
+    SmallDev sm = {};
+    double *fbuf = nullptr;          // batch x nsq local fronts (llt, inverse Hessian)
+    size_t fbuf_cap = 0;
     // host copies used by the operator setup
     std::vector<int> h_vec2blk;
     std::vector<int64_t> h_snptr;
@@ -105,6 +128,18 @@ struct smcp_hess {
 
 int sym_ensure(smcp_sym *s, int64_t batch, bool need_tmp);
 int grow(void **p, size_t *cap, size_t bytes);
+
+// tiny-clique kernels (chordal_small.cu); same contracts as the k_* functions below
+int small_setup(smcp_sym *s, const smcp_sym_desc *D, const std::vector<int> &tp, const std::vector<int> &ts,
+                const std::vector<int> &tp2, const std::vector<int> &ts2);
+int ks_cholesky(smcp_sym *s, double *x, int64_t batch, int32_t *info_host);
+int ks_completion(smcp_sym *s, double *x, int64_t batch, int32_t *info_host);
+int ks_projinv(smcp_sym *s, double *x, int64_t batch);
+int ks_llt(smcp_sym *s, double *x, int64_t batch);
+int ks_hess_prep(smcp_hess *h, const double *L, const double *Y);
+int ks_hess_prep_inv(smcp_hess *h);
+int ks_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv);
+int fetch_fail(smcp_sym *s, int64_t batch, int32_t *info_host);
 
 // chordal kernels (chordal.cu)
 int k_cholesky(smcp_sym *s, double *x, int64_t batch, int32_t *info_host);

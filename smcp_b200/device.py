@@ -89,7 +89,7 @@ def load_library(path=None):
     global _LIB
     if _LIB is not None and path is None:
         return _LIB
-    path = path or _LIB_PATH
+    path = path or os.environ.get("SMCP_B200_LIB") or _LIB_PATH
     if not os.path.exists(path):
         raise RuntimeError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(nvcc, sm_100a). There is no CPU fallback." % path)
@@ -326,6 +326,48 @@ class DeviceBackend:
         sld = np.zeros(len(g))
         _ck(self.lib, self.lib.smcp_csp_probe(self.sym, 0 if kind == "cholesky" else 1, x, dx, g, len(g), info, sld))
         return info == 0, sld
+
+    # -- contiguous batches (layout of the Schur assembly and the probes) ----------------
+    def alloc_batch(self, count):
+        p = C.c_void_p()
+        _ck(self.lib, self.lib.smcp_csp_alloc(self.sym, int(count), C.byref(p)))
+        return p
+
+    def free_batch(self, buf):
+        _ck(self.lib, self.lib.smcp_csp_free(self.sym, buf))
+
+    def _slot(self, buf, k):
+        return C.c_void_p(buf.value + 8 * k * self.symb.nblk)
+
+    def set_batch(self, buf, host):
+        host = np.ascontiguousarray(host, dtype=np.float64)
+        for k in range(host.shape[0]):
+            _ck(self.lib, self.lib.smcp_csp_set(self.sym, self._slot(buf, k), host[k]))
+
+    def get_batch(self, buf, count):
+        out = np.empty((count, self.symb.nblk))
+        for k in range(count):
+            _ck(self.lib, self.lib.smcp_csp_get(self.sym, self._slot(buf, k), out[k]))
+        return out
+
+    def cholesky_batch(self, buf, count):
+        info = np.zeros(count, dtype=np.int32)
+        _ck(self.lib, self.lib.smcp_csp_cholesky(self.sym, buf, int(count), info))
+        return info
+
+    def completion_batch(self, buf, count):
+        info = np.zeros(count, dtype=np.int32)
+        _ck(self.lib, self.lib.smcp_csp_completion(self.sym, buf, int(count), info))
+        return info
+
+    def llt_batch(self, buf, count):
+        _ck(self.lib, self.lib.smcp_csp_llt(self.sym, buf, int(count)))
+
+    def projected_inverse_batch(self, buf, count):
+        _ck(self.lib, self.lib.smcp_csp_projected_inverse(self.sym, buf, int(count)))
+
+    def hessian_batch(self, tok, buf, count, inv):
+        _ck(self.lib, self.lib.smcp_hess_apply(tok, buf, int(count), int(bool(inv))))
 
     # -- hessian ----------------------------------------------------------------------
     def hessian_factor(self, Lbuf, Ybuf):

@@ -23,9 +23,44 @@ def _reset_solver_state():
     solvers.set_backend_factory(None)
 
 
-def random_pattern(n, nextra, bw, seed):
-    """Lower pattern: band of width bw plus nextra random off-diagonal pairs."""
+def tree_pattern(n, depth, seed):
+    """Chordal lower pattern with tiny cliques: vertex j is joined to `depth` consecutive
+    ancestors in a random recursive tree (cliques of at most depth+1 vertices)."""
     from smcp_b200.symbolic import lower_pattern
+    rng = np.random.default_rng(seed)
+    par = np.full(n, -1, dtype=np.int64)
+    I, J = [], []
+    for j in range(1, n):
+        par[j] = rng.integers(max(0, j - 6), j)
+        a = j
+        for _ in range(depth):
+            a = par[a]
+            if a < 0:
+                break
+            I.append(j)
+            J.append(int(a))
+    return lower_pattern(n, I, J)
+
+
+def random_pattern(n, nextra, bw, seed):
+    """Lower pattern: band of width bw plus nextra random off-diagonal pairs (bw < 0: a
+    tree-structured pattern with cliques of at most |bw|+1 vertices)."""
+    from smcp_b200.symbolic import lower_pattern
+    if bw < 0:
+        return tree_pattern(n, -bw, seed)
+    if nextra < 0:
+        # chain of overlapping cliques {t*stride, ..., t*stride + bw - 1}: supernodes with
+        # several columns AND a separator (nn = stride, na = bw - stride)
+        stride = -nextra
+        I, J = [], []
+        for t0 in range(0, n, stride):
+            c = list(range(t0, min(n, t0 + bw)))
+            for a in c:
+                for b in c:
+                    if a >= b:
+                        I.append(a)
+                        J.append(b)
+        return lower_pattern(n, I, J)
     rng = np.random.default_rng(seed)
     I, J = [], []
     for j in range(n):
@@ -68,4 +103,12 @@ PATTERNS = [
     (1, 0, 0, 4),        # 1 x 1
     (12, 0, 0, 5),       # diagonal: n independent 1 x 1 supernodes (forest)
     (150, 120, 2, 6),
+    # tiny cliques (every clique <= 8 vertices): warp-per-chain kernels of chordal_small.cu
+    (300, 0, 5, 7),      # band, bandwidth 5: the benchmark's chain of 6 x 1 blocks
+    (90, 0, 7, 8),       # band, bandwidth 7: 8 x 8 fronts (the largest the small path takes)
+    (80, 0, 1, 9),       # tridiagonal
+    (400, 0, -3, 10),    # random tree, cliques of 4: many tasks, cross-task dependencies
+    (250, 0, -6, 11),    # random tree, cliques of 7
+    (120, -3, 6, 12),    # clique chain: 3-column supernodes with 3-row separators
+    (100, -2, 8, 13),    # clique chain: 2-column supernodes with 6-row separators
 ]

@@ -15,13 +15,31 @@ def relerr(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
 
-@pytest.fixture(scope="module", params=PATTERNS, ids=lambda p: "n%d_e%d_bw%d" % p[:3])
+def _cases():
+    out = []
+    for p in PATTERNS:
+        out.append(p + ("auto",))
+        if p[3] >= 7 or p[:3] in ((30, 0, 3), (12, 0, 0)):
+            # tiny-clique patterns also run through the CTA-per-supernode kernels, and with a
+            # task partition that cuts the tree into many tasks (cross-warp hand-off)
+            out.append(p + ("cta",))
+            out.append(p + ("split",))
+    return out
+
+
+@pytest.fixture(scope="module", params=_cases(), ids=lambda p: "n%d_e%d_bw%d_%s" % (p[0], p[1], p[2], p[4]))
 def setup(request):
+    import os
     from smcp_b200.device import DeviceBackend
     from oracle import supernodal as sn
-    n, ne, bw, seed = request.param
+    n, ne, bw, seed, mode = request.param
     symb = make_symbolic(n, ne, bw, seed)
-    dev = DeviceBackend(symb, small_work=2000)
+    if mode == "cta":
+        os.environ["SMCP_B200_NO_SMALL"] = "1"
+    try:
+        dev = DeviceBackend(symb, small_work=0 if mode == "split" else 2000)
+    finally:
+        os.environ.pop("SMCP_B200_NO_SMALL", None)
     s = random_pd(symb, seed)
     l = s.copy()
     sn.cholesky(symb, l)
@@ -146,3 +164,51 @@ def test_probe_batch(setup):
             assert o
         except ArithmeticError:
             assert not o
+
+
+@pytest.mark.parametrize("batch", [3, 40])
+def test_contiguous_batch(setup, batch):
+    """cholesky / llt / projected_inverse / completion / Hessian on `batch` matrices stored
+    contiguously (the layout of the Schur-complement assembly and of the probes)."""
+    from oracle import supernodal as sn
+    symb, dev, s, l, y = setup
+    rng = np.random.default_rng(3)
+    shifts = 1.0 + rng.random(batch)
+    S = np.array([s + sh * (symb.wdot == 1.0) for sh in shifts])      # s + sh*I, still PD
+    Ls = S.copy()
+    for r in Ls:
+        sn.cholesky(symb, r)
+    buf = dev.alloc_batch(batch)
+    dev.set_batch(buf, S)
+    info = dev.cholesky_batch(buf, batch)
+    assert not info.any()
+    assert relerr(dev.get_batch(buf, batch), Ls) < TOL
+    dev.llt_batch(buf, batch)
+    assert relerr(dev.get_batch(buf, batch), S) < TOL
+    dev.set_batch(buf, Ls)
+    dev.projected_inverse_batch(buf, batch)
+    Ys = Ls.copy()
+    for r in Ys:
+        sn.projected_inverse(symb, r)
+    assert relerr(dev.get_batch(buf, batch), Ys) < TOL
+    info = dev.completion_batch(buf, batch)
+    assert not info.any()
+    assert relerr(dev.get_batch(buf, batch), Ls) < 1e-9
+    # Hessian at the scaling point (l, y) applied to the whole batch in one call
+    hf = sn.HessianFactor(symb, l, y)
+    tok = dev.hessian_factor(dev.set_blk(l), dev.set_blk(y))
+    U = rng.standard_normal((batch, symb.nblk)) * (symb.wdot > 0)
+    W = U.copy()
+    sn.hessian(hf, W)
+    dev.set_batch(buf, U)
+    dev.hessian_batch(tok, buf, batch, False)
+    assert relerr(dev.get_batch(buf, batch), W) < TOL
+    dev.hessian_batch(tok, buf, batch, True)
+    assert relerr(dev.get_batch(buf, batch), U) < 1e-8
+    # one indefinite matrix in the middle of the batch is reported, the others are not
+    bad = S.copy()
+    bad[batch // 2, symb.diag_blk[symb.n // 2]] = -1.0
+    dev.set_batch(buf, bad)
+    info = dev.cholesky_batch(buf, batch)
+    assert info[batch // 2] != 0 and np.count_nonzero(info) == 1
+    dev.free_batch(buf)
