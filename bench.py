@@ -244,7 +244,7 @@ def run_b200(args):
     ctx.prof_enable(False)
     solvers._iteration_hook = None
     dev_ms = 0.0
-    for nm in FAMILIES:
+    for nm in ctx.prof_names():
         ms, cnt = ctx.prof_get(nm)
         if cnt:
             fam[nm] = {"ms": ms, "launches": cnt, "work": ctx.prof_get_work(nm)}

@@ -49,6 +49,8 @@ int smcp_prof_enable(smcp_ctx *ctx, int on);
 int smcp_prof_get(smcp_ctx *ctx, const char *name, double *ms_out, int64_t *launches_out);
 /* accumulated work of a family: matrices processed (chordal kernels), algorithmic flops (GEMM) */
 int smcp_prof_get_work(smcp_ctx *ctx, const char *name, double *work_out);
+/* comma-separated names of the families that have accumulated time since the last reset */
+int smcp_prof_list(smcp_ctx *ctx, char *buf, int64_t cap);
 int smcp_prof_reset(smcp_ctx *ctx);
 /* write (flush) a buffer larger than L2 */
 int smcp_flush_l2(smcp_ctx *ctx);

@@ -22,9 +22,7 @@ solvers.options["show_progress"] = False
 t0 = time.time()
 sol = P.solve_feas(primalstart={"x": P._X0})
 ctx.prof_enable(False)
-names = ["completion", "cholesky", "projected_inverse", "llt", "hessian_prep", "hessian_prep_inv", "hessian_up",
-         "hessian_down", "hessian_inv", "scatter_cols", "schur_gemm_dmma", "potrf_diag", "potrf_trsm",
-         "potrf_syrk_dmma", "potrs", "amap", "aadj", "level1", "reduce", "chordal_trsm", "scm_sparse", "setup"]
+names = ctx.prof_names()
 tot = 0.0
 rows = []
 for nm in names:

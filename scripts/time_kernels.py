@@ -46,10 +46,7 @@ for it in range(reps + 1):
     for b in (x, y, u):
         dev.release(b)
 ctx.prof_enable(False)
-names = ["cholesky", "cholesky_batch", "llt_local", "llt", "projected_inverse_prep", "projected_inverse",
-         "completion", "completion_batch", "hessian_prep", "hessian_prep_inv", "hessian_up", "hessian_scale",
-         "hessian_down", "hessian_inv_local", "hessian_inv", "hessian_up_batch", "hessian_scale_batch",
-         "hessian_down_batch", "hessian_inv_local_batch", "hessian_inv_batch", "level1", "reduce"]
+names = sorted(ctx.prof_names())
 print("pattern: band n=%d bw=%d, nsn=%d, nblk=%d, batch=%d" % (n, bw, symb.nsn, symb.nblk, batch))
 for nm in names:
     ms, cnt = ctx.prof_get(nm)

@@ -86,6 +86,7 @@ extern "C" int smcp_ctx_destroy(smcp_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
@@ -131,6 +132,16 @@ extern "C" int smcp_prof_get(smcp_ctx *ctx, const char *name, double *ms_out, in
 extern "C" int smcp_prof_get_work(smcp_ctx *ctx, const char *name, double *work_out) {
     auto it = ctx->prof_acc.find(name);
     *work_out = it == ctx->prof_acc.end() ? 0.0 : it->second.work;
+    return 0;
+}
+extern "C" int smcp_prof_list(smcp_ctx *ctx, char *buf, int64_t cap) {
+    std::string out;
+    for (auto &kv : ctx->prof_acc) {
+        if (!out.empty()) out += ",";
+        out += kv.first;
+    }
+    if ((int64_t)out.size() + 1 > cap) { smcp_set_error("smcp_prof_list: buffer too small"); return -2; }
+    memcpy(buf, out.c_str(), out.size() + 1);
     return 0;
 }
 extern "C" int smcp_prof_reset(smcp_ctx *ctx) {

@@ -40,6 +40,8 @@ struct SmallArgs {
     SmallDev M;
     double *F;             // B x nsq local fronts
     long long ltstride;    // 0: one factor for the whole batch (Hessian); nblk: one per matrix
+    const int *list;       // flat kernels: restrict to these supernodes (nullptr = all)
+    int nlist;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -213,6 +215,39 @@ __device__ void fl_pinv_prep(const TreeArgs &a, const Node &q, int b, double *ws
 #undef NT
 #undef SYNC
 
+// Hessian scaling for supernodes with a single column, one THREAD per (supernode, matrix):
+// M_nn = K_nn / l^4, M_an = Y_aa (K_an / l^2), l = L_nn.  Used for batches (Schur-complement
+// assembly), where one warp per supernode would be issue-bound; consecutive lanes take
+// consecutive supernodes of the same matrix so the block entries they touch are contiguous.
+__global__ void __launch_bounds__(256) hscale_nn1_kernel(SmallArgs a) {
+    const TreeArgs &t = a.t;
+    const long long nsn = t.S.nsn, total = nsn * t.B;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(idx / nsn), k = (int)(idx - (long long)b * nsn);
+        if (t.S.nn[k] != 1) continue;
+        const int na = t.S.na[k];
+        const long long boff = t.S.blkptr[k];
+        double *blk = t.X + (long long)b * t.S.nblk + boff;
+        const double *Y = t.Yaa + t.S.updptr[k];
+        const double l = t.Lt[boff];
+        const double inv = 1.0 / (l * l);
+        double kv[7];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) kv[q] = (q < na) ? blk[1 + q] * inv : 0.0;
+        blk[0] = blk[0] * inv * inv;
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+            if (r < na) {
+                double s = 0.0;
+#pragma unroll
+                for (int q = 0; q < 7; ++q)
+                    if (q < na) s = fma(Y[r + q * na], kv[q], s);
+                blk[1 + r] = s;
+            }
+        }
+    }
+}
+
 #define FLAT_THREADS 128
 #define FLAT_WS (4 * 64 + 8)
 
@@ -221,11 +256,13 @@ __global__ void __launch_bounds__(FLAT_THREADS) flat_small_kernel(SmallArgs a) {
     __shared__ double smem[(FLAT_THREADS / 32) * FLAT_WS];
     double *ws = smem + (threadIdx.x >> 5) * FLAT_WS;
     const TreeArgs &t = a.t;
-    const long long nsn = t.S.nsn;
+    const long long nsn = a.list ? a.nlist : t.S.nsn;     // all supernodes, or only those in `list`
     const long long total = nsn * t.B;
     const long long nwarps = (long long)gridDim.x * (FLAT_THREADS / 32);
     for (long long item = (long long)blockIdx.x * (FLAT_THREADS / 32) + (threadIdx.x >> 5); item < total; item += nwarps) {
-        const int b = (int)(item / nsn), k = (int)(item - (long long)b * nsn);
+        const int b = (int)(item / nsn);
+        int k = (int)(item - (long long)b * nsn);
+        if (a.list) k = a.list[k];
         Node q = node_of(t.S, k);
         if (OP == FL_COMPL) op_compl<true>(t, q, b, ws);
         else if (OP == FL_HPREP) op_hprep<true>(t, q);
@@ -733,10 +770,23 @@ __device__ __forceinline__ void down_run_fast(const DnCtx &c, int na, int run, i
         double m = 0.0, acc = 0.0, tsum = 0.0;
         if (col0) m = xs[i];
         if (p0) {
-            acc = m;
+            // all loads first (independent of each other), then the FMA chain
             const int zb = o + i + 8;
-            for (int r = 0; r < na; ++r) acc = fma(-Z[(zb + 8 * r) & 63], ls[1 + r], acc);
-            tsum = ls[i] * (m + acc);
+            double zr[7], lr[7];
+#pragma unroll
+            for (int r = 0; r < 7; ++r) {
+                zr[r] = (r < na) ? Z[(zb + 8 * r) & 63] : 0.0;
+                lr[r] = (r < na) ? ls[1 + r] : 0.0;
+            }
+            const double lself = ls[i];
+            double a0 = m, a1 = 0.0;
+#pragma unroll
+            for (int r = 0; r < 7; r += 2) {
+                a0 = fma(-zr[r], lr[r], a0);
+                if (r + 1 < 7) a1 = fma(-zr[r + 1], lr[r + 1], a1);
+            }
+            acc = a0 + a1;
+            tsum = lself * (m + acc);
         }
         tsum += __shfl_xor_sync(FULLMASK, tsum, 1);
         tsum += __shfl_xor_sync(FULLMASK, tsum, 2);
@@ -992,6 +1042,11 @@ int small_setup(smcp_sym *s, const smcp_sym_desc *D, const std::vector<int> &tp,
         up_vec(s, dcp, &M.down_chunk_ptr) || up_vec(s, dch, &M.down_chunks) || up_vec(s, acp, &M.add_chunk_ptr) ||
         up_vec(s, ach, &M.add_chunks))
         return -1;
+    std::vector<int> wide;
+    for (int k = 0; k < nsn; ++k)
+        if (nn[k] != 1) wide.push_back(k);
+    if (up_vec(s, wide, &M.wide_sn)) return -1;
+    M.nwide = (int)wide.size();
     M.nsq = sq[nsn];
     M.ntiles = ntiles;
     s->small = true;
@@ -1013,7 +1068,8 @@ template <int OP>
 static int launch_flat(smcp_sym *s, SmallArgs &a, int64_t batch, const char *name) {
     smcp_ctx *ctx = s->ctx;
     fill_common(s, a, s->flat, batch);
-    long long items = (long long)s->d.nsn * batch;
+    long long items = (long long)(a.list ? a.nlist : s->d.nsn) * batch;
+    if (items == 0) return 0;
     long long grid = (items + (FLAT_THREADS / 32) - 1) / (FLAT_THREADS / 32);
     long long cap = (long long)ctx->num_sms * 16;
     if (grid > cap) grid = cap;
@@ -1145,7 +1201,23 @@ int ks_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
         a.t.Lt = h->Lt;
         a.t.Yaa = h->Yaa;
         if (launch_sweep(s, sweep_up_kernel<SW_HUP>, WS_HUP, a, s->up, batch, big ? "hessian_up_batch" : "hessian_up")) return -1;
-        if (launch_flat<FL_HSCALE>(s, a, batch, big ? "hessian_scale_batch" : "hessian_scale")) return -1;
+        if (big) {
+            // one thread per (supernode, matrix) for the single-column supernodes, warps for the rest
+            smcp_ctx *ctx = s->ctx;
+            fill_common(s, a, s->flat, batch);
+            long long items = (long long)s->d.nsn * batch;
+            long long grid = std::min<long long>((items + 255) / 256, (long long)ctx->num_sms * 16);
+            {
+                LaunchScope ls(ctx, "hessian_scale_batch", 1, (double)batch);
+                hscale_nn1_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(a);
+            }
+            CUDA_TRY(cudaGetLastError());
+            a.list = s->sm.wide_sn;
+            a.nlist = s->sm.nwide;
+            if (launch_flat<FL_HSCALE>(s, a, batch, "hessian_scale_wide_batch")) return -1;
+            a.list = nullptr;
+            a.nlist = 0;
+        } else if (launch_flat<FL_HSCALE>(s, a, batch, "hessian_scale")) return -1;
         return launch_sweep(s, sweep_down_kernel, WS_DOWN, a, s->down, batch, big ? "hessian_down_batch" : "hessian_down");
     }
     if (!h->have_Raa) {

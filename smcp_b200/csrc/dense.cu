@@ -61,7 +61,7 @@ template <bool TN>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_dmma_kernel(const double *__restrict__ A, long long lda, const double *__restrict__ B, long long ldb,
                  double *__restrict__ C, long long ldc, long long M, long long N, long long K, double alpha,
-                 int accumulate, int tri, long long tri_off) {
+                 int accumulate, int tri, long long tri_off, long long kchunk, long long split_stride) {
     extern __shared__ double smem[];
     double *As = smem;                              // STAGES x 128 x LDK
     double *Bs = smem + STAGES * 128 * LDK;
@@ -79,11 +79,15 @@ gemm_dmma_kernel(const double *__restrict__ A, long long lda, const double *__re
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-    const long long nk = (K + BK - 1) / BK;
+    // split-K: slice blockIdx.z works on k in [kbeg, kend) and writes its own partial result
+    const long long kbeg = (long long)blockIdx.z * kchunk;
+    const long long kend = (kbeg + kchunk < K) ? kbeg + kchunk : K;
+    C += (long long)blockIdx.z * split_stride;
+    const long long nk = (kend - kbeg + BK - 1) / BK;
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < nk) {
-            load_tile<TN>(As + s * 128 * LDK, A, lda, i0, M, (long long)s * BK, K, tid);
-            load_tile<TN>(Bs + s * 128 * LDK, B, ldb, j0, N, (long long)s * BK, K, tid);
+            load_tile<TN>(As + s * 128 * LDK, A, lda, i0, M, kbeg + (long long)s * BK, kend, tid);
+            load_tile<TN>(Bs + s * 128 * LDK, B, ldb, j0, N, kbeg + (long long)s * BK, kend, tid);
         }
         cp_async_commit();
     }
@@ -94,8 +98,8 @@ gemm_dmma_kernel(const double *__restrict__ A, long long lda, const double *__re
             long long nx = kt + STAGES - 1;
             if (nx < nk) {
                 int s = (int)(nx % STAGES);
-                load_tile<TN>(As + s * 128 * LDK, A, lda, i0, M, nx * BK, K, tid);
-                load_tile<TN>(Bs + s * 128 * LDK, B, ldb, j0, N, nx * BK, K, tid);
+                load_tile<TN>(As + s * 128 * LDK, A, lda, i0, M, kbeg + nx * BK, kend, tid);
+                load_tile<TN>(Bs + s * 128 * LDK, B, ldb, j0, N, kbeg + nx * BK, kend, tid);
             }
             cp_async_commit();
         }
@@ -135,11 +139,48 @@ gemm_dmma_kernel(const double *__restrict__ A, long long lda, const double *__re
     }
 }
 
+// sum of the split-K partial results in a fixed order (deterministic), lower part only when tri
+__global__ void splitk_reduce_kernel(const double *__restrict__ P, long long split_stride, int splits, double *__restrict__ C,
+                                     long long ldc, long long M, long long N, int tri, long long tri_off) {
+    const long long total = M * N;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long i = idx % M, j = idx / M;
+        if (tri && i + tri_off < j) continue;
+        double s = 0.0;
+        for (int z = 0; z < splits; ++z) s += P[(long long)z * split_stride + idx];
+        C[i + j * ldc] = s;
+    }
+}
+
 static int launch_gemm(smcp_ctx *ctx, bool tn, const double *A, int64_t lda, const double *B, int64_t ldb,
                        double *C, int64_t ldc, int64_t M, int64_t N, int64_t K, double alpha, int accumulate,
                        int tri, int64_t tri_off, const char *name) {
     if (M <= 0 || N <= 0) return 0;
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
+    // split-K when the (lower-triangular) tile grid cannot fill the GPU and K is long: the Schur
+    // assembly contracts over |blkval| ~ 10^4..10^6 rows into an m x m block
+    long long ntiles = 0;
+    for (unsigned bj = 0; bj < grid.y; ++bj)
+        for (unsigned bi = 0; bi < grid.x; ++bi)
+            if (!tri || (long long)bi * BM + BM - 1 + tri_off >= (long long)bj * BN) ++ntiles;
+    int splits = 1;
+    if (!accumulate && alpha == 1.0 && K >= 2048 && ntiles > 0 && ntiles < ctx->num_sms) {
+        splits = (int)(ctx->num_sms / ntiles);
+        if (splits > 16) splits = 16;
+        if ((long long)splits * 512 > K) splits = (int)(K / 512);
+        if (splits < 1) splits = 1;
+    }
+    long long kchunk = K, split_stride = 0;
+    double *Cout = C;
+    int64_t ldout = ldc;
+    if (splits > 1) {
+        kchunk = ((K + splits - 1) / splits + BK - 1) / BK * BK;
+        split_stride = M * N;
+        if (grow((void **)&ctx->gemm_ws, &ctx->gemm_ws_cap, (size_t)splits * M * N * sizeof(double))) return -1;
+        Cout = ctx->gemm_ws;
+        ldout = M;
+        grid.z = splits;
+    }
     size_t smem = (size_t)2 * STAGES * 128 * LDK * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
@@ -159,9 +200,15 @@ static int launch_gemm(smcp_ctx *ctx, bool tn, const double *A, int64_t lda, con
     {
         LaunchScope ls(ctx, name, 1, 2.0 * (double)K * pairs);
         if (tn)
-            gemm_dmma_kernel<true><<<grid, GEMM_THREADS, smem, ctx->stream>>>(A, lda, B, ldb, C, ldc, M, N, K, alpha, accumulate, tri, tri_off);
+            gemm_dmma_kernel<true><<<grid, GEMM_THREADS, smem, ctx->stream>>>(A, lda, B, ldb, Cout, ldout, M, N, K, alpha, accumulate, tri, tri_off, kchunk, split_stride);
         else
-            gemm_dmma_kernel<false><<<grid, GEMM_THREADS, smem, ctx->stream>>>(A, lda, B, ldb, C, ldc, M, N, K, alpha, accumulate, tri, tri_off);
+            gemm_dmma_kernel<false><<<grid, GEMM_THREADS, smem, ctx->stream>>>(A, lda, B, ldb, Cout, ldout, M, N, K, alpha, accumulate, tri, tri_off, kchunk, split_stride);
+        if (splits > 1) {
+            ctx->launches += 1;
+            long long g = (M * N + 255) / 256;
+            if (g > (long long)ctx->num_sms * 8) g = (long long)ctx->num_sms * 8;
+            splitk_reduce_kernel<<<(unsigned)g, 256, 0, ctx->stream>>>(ctx->gemm_ws, split_stride, splits, C, ldc, M, N, tri, tri_off);
+        }
     }
     CUDA_TRY(cudaGetLastError());
     return 0;

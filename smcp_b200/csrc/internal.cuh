@@ -36,6 +36,8 @@ struct smcp_ctx {
     std::map<std::string, ProfEntry> prof_acc;
     double *flush_buf = nullptr;
     size_t flush_bytes = 0;
+    double *gemm_ws = nullptr;          // split-K partial results
+    size_t gemm_ws_cap = 0;
     void *nccl_comm = nullptr;
     // pinned staging for small host<->device transfers
     void *pinned = nullptr;
@@ -83,6 +85,8 @@ struct SmallDev {
     const long long *sqptr;   // nsn+1: offsets of the nj x nj local fronts in the F scratch
     long long nsq;
     int ntiles;               // supernodes whose update matrix goes through a global 8 x 8 tile
+    const int *wide_sn;       // supernodes with more than one column
+    int nwide;
 };
 
 struct smcp_sym {

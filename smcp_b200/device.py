@@ -42,6 +42,7 @@ API = {
     "smcp_prof_enable": (_int, [_vp, _int]),
     "smcp_prof_get": (_int, [_vp, C.c_char_p, C.POINTER(_dbl), C.POINTER(_i64)]),
     "smcp_prof_get_work": (_int, [_vp, C.c_char_p, C.POINTER(_dbl)]),
+    "smcp_prof_list": (_int, [_vp, C.c_char_p, _i64]),
     "smcp_prof_reset": (_int, [_vp]),
     "smcp_flush_l2": (_int, [_vp]),
     "smcp_sym_create": (_int, [_vp, C.POINTER(SymDesc), C.POINTER(_vp)]),
@@ -159,6 +160,12 @@ class Context:
         w = C.c_double()
         _ck(self.lib, self.lib.smcp_prof_get_work(self.h, name.encode(), C.byref(w)))
         return w.value
+
+    def prof_names(self):
+        buf = C.create_string_buffer(8192)
+        _ck(self.lib, self.lib.smcp_prof_list(self.h, buf, 8192))
+        s = buf.value.decode()
+        return s.split(",") if s else []
 
     def flush_l2(self):
         _ck(self.lib, self.lib.smcp_flush_l2(self.h))
