@@ -79,7 +79,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -152,6 +152,34 @@ def measured_fp64_peak():
         return 2.0 * n ** 3 / (best * 1e-3) / 1e12
     except Exception:
         return None
+
+
+# families whose LaunchScope work is already in algorithmic BYTES per launch
+BYTE_FAMILIES = {"potrs", "amap_dense", "amap", "aadj", "potrf_panel"}
+
+
+def roofline_of(name, f, nvp, hbm_peak, hbm_src, fp64_peak):
+    """achieved = algorithmic bytes (or flops) per launch / average launch duration (CUDA events on
+    the library's stream).  Chordal kernels: 16*|Vp| bytes per matrix (one read + one write of every
+    pattern entry, SURVEY.md 8d); GEMMs: 2*K flops per computed entry of the lower-triangular result;
+    potrs: 8*m^2 bytes (the factor is read twice); amap/aadj: the stored entries of Av."""
+    per_launch_s = f["ms"] * 1e-3 / max(1, f["launches"])
+    work = f["work"] / max(1, f["launches"])
+    if name.endswith("_dmma"):
+        ach = work / per_launch_s / 1e12
+        peak = fp64_peak if fp64_peak else 40.0
+        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": None,
+                "peak_source": ("measured in this run: cuBLAS DGEMM 8192^3 via torch.matmul, best of 5 "
+                                "(MEASURED_PEAKS.json has no FP64 entry)" if fp64_peak
+                                else "nominal FP64 tensor peak (no measurement)")}
+    byts = work if name in BYTE_FAMILIES else 16.0 * nvp * work
+    ach = byts / per_launch_s / 1e9
+    out = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+           "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src}
+    if name not in BYTE_FAMILIES:
+        out["matrices_per_launch"] = work
+    return out
 
 
 def load_peaks():
@@ -266,27 +294,14 @@ def run_b200(args):
     hbm_peak, hbm_src = load_peaks()
     fp64_peak = measured_fp64_peak()
     top = max(fam.items(), key=lambda kv: kv[1]["ms"])[0] if fam else None
-    roof = None
-    if top is not None:
-        f = fam[top]
-        per_launch_s = f["ms"] * 1e-3 / f["launches"]
-        work = f["work"] / f["launches"]
-        if top.endswith("_dmma"):
-            # work = algorithmic flops of the launch: 2*K per entry of the lower-triangular
-            # result (Schur: F_ip = |blkval| * m * (m+1))
-            ach = work / per_launch_s / 1e12
-            peak = fp64_peak if fp64_peak else 40.0
-            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": None,
-                    "peak_source": ("measured in this run: cuBLAS DGEMM 8192^3 via torch.matmul, best of 5"
-                                    if fp64_peak else "nominal FP64 tensor peak (no measurement)")}
-        else:
-            # chordal kernels: work = matrices per launch; algorithmic bytes = one read and
-            # one write of every pattern entry of every matrix (16*|Vp| per matrix, §8d)
-            ach = 16.0 * nvp * work / per_launch_s / 1e9
-            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src,
-                    "matrices_per_launch": work}
+    roof = roofline_of(top, fam[top], nvp, hbm_peak, hbm_src, fp64_peak) if top is not None else None
+    # the same figure for every family that takes more than 3% of the step (explains `value`)
+    per_family = {}
+    for nm, f in fam.items():
+        if f["ms"] >= 0.03 * dev_ms:
+            r = roofline_of(nm, f, nvp, hbm_peak, hbm_src, fp64_peak)
+            per_family[nm] = {"ms_per_step": f["ms"] / K, "launches_per_step": f["launches"] / K,
+                              "bound": r["bound"], "achieved": r["achieved"], "unit": r["unit"], "frac": r["frac"]}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if roof is not None and os.path.exists(traffic_file):
         with open(traffic_file) as fh:
@@ -309,6 +324,7 @@ def run_b200(args):
         "roofline": roof,
         "cpu_baseline": cpu,
         "kernel_ms_per_step": {k: v["ms"] / K for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])},
+        "family_rooflines": per_family,
         "status": sol["status"], "iterations": iters,
         "fp64_gemm_peak_tflops": fp64_peak,
     }

@@ -84,6 +84,9 @@ typedef struct smcp_sym_desc {
 
 int smcp_sym_create(smcp_ctx *ctx, const smcp_sym_desc *desc, smcp_sym **out);
 int smcp_sym_destroy(smcp_sym *sym);
+/* size the per-pattern workspaces for batches of up to `batch` matrices now (otherwise they grow on
+ * first use, e.g. at the first batched line search of a solve) */
+int smcp_sym_reserve(smcp_sym *sym, int64_t batch);
 
 /* ---- chordal matrices: chompack.cspmatrix -----------------------------------------------
  * A chordal matrix is `nblk` doubles in device memory (the `blkval` buffer of a cspmatrix).

@@ -181,7 +181,7 @@ def gen_drivers():
     for name, P, kw, method in [
             ("band_feas_primal", S.band_SDP(60, 20, 3, seed=7), {"scaling": "primal"}, "feas"),
             ("band_feas_dual", S.band_SDP(60, 20, 3, seed=7), {"scaling": "dual"}, "feas"),
-            ("band_esd", S.band_SDP(40, 12, 3, seed=2), {}, "esd"),
+            ("band_esd", S.band_SDP(30, 10, 2, seed=1), {}, "esd"),
             ("mtxnorm_esd", S.mtxnorm_SDP(12, 4, 9, density=0.6, seed=1), {}, "esd")]:
         sol = getattr(P, "solve_" + method)(kktsolver="chol", **kw)
         traces[name] = {"status": sol["status"], "iterations": sol["iterations"],

@@ -274,6 +274,7 @@ extern "C" int smcp_sym_destroy(smcp_sym *s) {
     if (s->tmp) cudaFree(s->tmp);
     if (s->red) cudaFree(s->red);
     if (s->fbuf) cudaFree(s->fbuf);
+    if (s->ch_state) cudaFree(s->ch_state);
     delete s;
     return 0;
 }
@@ -342,6 +343,14 @@ extern "C" int smcp_csp_llt(smcp_sym *s, double *x, int64_t batch) { return k_ll
 static double *g_probe_buf = nullptr;
 static size_t g_probe_cap = 0;
 
+extern "C" int smcp_sym_reserve(smcp_sym *s, int64_t batch) {
+    if (batch < 1) return 0;
+    if (sym_ensure(s, batch, true)) return -1;
+    if (grow((void **)&g_probe_buf, &g_probe_cap, ((size_t)batch * s->d.nblk + batch + 16) * sizeof(double))) return -1;
+    if (grow((void **)&s->red, &s->red_cap, ((size_t)batch * 40 + 1024) * sizeof(double) + (size_t)s->d.nvp * sizeof(double) + 4096)) return -1;
+    return 0;
+}
+
 extern "C" int smcp_csp_probe(smcp_sym *s, int kind, const double *x, const double *dx, const double *gammas_host,
                               int64_t count, int32_t *info_host, double *sumlogdiag_host) {
     smcp_ctx *ctx = s->ctx;
@@ -380,6 +389,7 @@ extern "C" int smcp_hess_destroy(smcp_hess *h) {
     cudaFree(h->Lt);
     cudaFree(h->Yaa);
     cudaFree(h->Raa);
+    if (h->phi_up) cudaFree(h->phi_up);      // one allocation: phi_up | phi_dn | psi_up | psi_dn
     delete h;
     return 0;
 }
@@ -408,6 +418,7 @@ struct smcp_op {
     double *Ub = nullptr;
     size_t Ub_cap = 0;
     double *Zinv = nullptr;       // n x n dense inverse for the sparse-constraint technique
+    double *Dinv = nullptr;       // inverses of the 64 x 64 diagonal blocks of chol(H) (potrs)
     std::vector<long long> h_colptr;
     void *allocs[16] = {0};
 };
@@ -423,6 +434,33 @@ __global__ void amap_kernel(const long long *__restrict__ colptr, const int *__r
     for (long long p = colptr[c] + lane; p < colptr[c + 1]; p += 32) s = fma(valsw[p], X[rowblk[p]], s);
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
     if (lane == 0) out[w] = s;
+}
+
+// dense variant for (nearly) dense Av: column c of the weighted dense copy AvW is contiguous, one CTA
+// per column streams it once (coalesced 8-byte loads, 4 independent accumulators per thread) against
+// X, which stays in L2; fixed reduction tree -> deterministic.
+__global__ void __launch_bounds__(256) amap_dense_kernel(const double *__restrict__ AvW, long long nblk,
+                                                         const double *__restrict__ X, double *out, long long col0) {
+    const double *a = AvW + (col0 + blockIdx.x) * nblk;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    long long r = threadIdx.x;
+    for (; r + 768 < nblk; r += 1024) {
+        s0 = fma(a[r], X[r], s0);
+        s1 = fma(a[r + 256], X[r + 256], s1);
+        s2 = fma(a[r + 512], X[r + 512], s2);
+        s3 = fma(a[r + 768], X[r + 768], s3);
+    }
+    for (; r < nblk; r += 256) s0 = fma(a[r], X[r], s0);
+    double s = (s0 + s1) + (s2 + s3);
+    __shared__ double sh[8];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < 8 ? sh[threadIdx.x] : 0.0;
+        for (int o = 4; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) out[blockIdx.x] = v;
+    }
 }
 
 __global__ void aadj_kernel(const long long *__restrict__ r_ptr, const int *__restrict__ r_col,
@@ -500,6 +538,7 @@ extern "C" int smcp_op_create(smcp_sym *s, int64_t m, int64_t Ns, const int64_t 
     CUDA_TRY(cudaMemset(op->H, 0, (size_t)std::max<int64_t>(m * m, 1) * sizeof(double)));
     CUDA_TRY(cudaMalloc(&op->info_dev, 64));
     CUDA_TRY(cudaMalloc(&op->yv, (size_t)(m + 1) * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&op->Dinv, (size_t)((m + 63) / 64 + 1) * 64 * 64 * sizeof(double)));
     if (op->md > 0) {
         // dense weighted copy of all m columns (rows of H below the dense block included)
         size_t bytes = (size_t)nblk * (size_t)m * sizeof(double);
@@ -532,6 +571,7 @@ extern "C" int smcp_op_destroy(smcp_op *op) {
     if (op->AvW) cudaFree(op->AvW);
     if (op->Ub) cudaFree(op->Ub);
     if (op->Zinv) cudaFree(op->Zinv);
+    if (op->Dinv) cudaFree(op->Dinv);
     cudaFree(op->H); cudaFree(op->info_dev); cudaFree(op->yv);
     delete op;
     return 0;
@@ -542,8 +582,11 @@ extern "C" int smcp_op_amap(smcp_op *op, const double *X, int64_t col, double *h
     int64_t c0 = col >= 0 ? col : 0;
     int ncols = col >= 0 ? 1 : (int)op->m;
     if (ncols == 0) return 0;
-    {
-        LaunchScope ls(ctx, "amap");
+    if (op->AvW && op->nnz * 4 >= (int64_t)op->sym->d.nblk * op->m) {
+        LaunchScope ls(ctx, "amap_dense", 1, 8.0 * (double)op->sym->d.nblk * ncols);
+        amap_dense_kernel<<<ncols, 256, 0, ctx->stream>>>(op->AvW, op->sym->d.nblk, X, op->yv, c0);
+    } else {
+        LaunchScope ls(ctx, "amap", 1, 12.0 * (double)(op->h_colptr[c0 + ncols] - op->h_colptr[c0]));
         amap_kernel<<<(ncols * 32 + 255) / 256, 256, 0, ctx->stream>>>(op->colptr, op->rowblk, op->valsw, X, op->yv, c0, ncols);
     }
     CUDA_TRY(cudaGetLastError());
@@ -557,7 +600,7 @@ extern "C" int smcp_op_aadj(smcp_op *op, const double *host_y, double *X) {
     CUDA_TRY(cudaMemcpyAsync(op->yv, host_y, (size_t)op->m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     int nrows = op->sym->d.nblk;
     {
-        LaunchScope ls(ctx, "aadj");
+        LaunchScope ls(ctx, "aadj", 1, 12.0 * (double)op->nnz);
         aadj_kernel<<<(unsigned)(((long long)nrows * 32 + 255) / 256), 256, 0, ctx->stream>>>(op->r_ptr, op->r_col, op->r_val, op->yv, X, nrows);
     }
     CUDA_TRY(cudaGetLastError());
@@ -649,7 +692,7 @@ extern "C" int smcp_kkt_assemble(smcp_op *op, smcp_hess *h, int64_t j0, int64_t 
 
 extern "C" int smcp_kkt_factor(smcp_op *op, int32_t *info_host) {
     smcp_ctx *ctx = op->sym->ctx;
-    if (d_potrf(ctx, op->H, op->m, op->info_dev)) return -1;
+    if (d_potrf(ctx, op->H, op->m, op->info_dev, op->Dinv)) return -1;
     CUDA_TRY(cudaMemcpyAsync(info_host, op->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -658,7 +701,7 @@ extern "C" int smcp_kkt_factor(smcp_op *op, int32_t *info_host) {
 extern "C" int smcp_kkt_solve(smcp_op *op, double *host_y) {
     smcp_ctx *ctx = op->sym->ctx;
     CUDA_TRY(cudaMemcpyAsync(op->yv, host_y, (size_t)op->m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    if (d_potrs(ctx, op->H, op->m, op->yv)) return -1;
+    if (d_potrs(ctx, op->H, op->m, op->Dinv, op->yv)) return -1;
     CUDA_TRY(cudaMemcpyAsync(host_y, op->yv, (size_t)op->m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return 0;

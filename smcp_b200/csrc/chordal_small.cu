@@ -26,6 +26,7 @@
 #include "internal.cuh"
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "chordal_ops.cuh"
 
@@ -895,6 +896,8 @@ __global__ void __launch_bounds__(SW_THREADS) sweep_down_kernel(SmallArgs a) {
 // ---------------------------------------------------------------------------------------
 // host: tables, launchers, dispatch
 // ---------------------------------------------------------------------------------------
+#include "chordal_chain.cuh"
+
 template <class T>
 static int up_vec(smcp_sym *s, const std::vector<T> &v, const T **out) {
     void *d = nullptr;
@@ -942,6 +945,7 @@ int small_setup(smcp_sym *s, const smcp_sym_desc *D, const std::vector<int> &tp,
         nj[k] = (int)(D->rowptr[k + 1] - D->rowptr[k]);
         na[k] = nj[k] - nn[k];
     }
+    chain_detect(s, D, nn, na);
     // slot colouring, root to leaves: the separator rows are coloured already (they belong to
     // the parent's clique), the supernode's own vertices take the free slots
     std::vector<int> slot(D->n, -1);
@@ -1126,7 +1130,9 @@ int ks_cholesky(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
     CUDA_TRY(cudaMemsetAsync(s->fail, 0, (size_t)batch * sizeof(int), s->ctx->stream));
     SmallArgs a = {};
     a.t.X = x;
-    if (launch_sweep(s, sweep_up_kernel<SW_CHOL>, WS_CHOL, a, s->up, batch, batch > 1 ? "cholesky_batch" : "cholesky")) return -1;
+    if (s->chain) {
+        if (chain_cholesky(s, x, batch, batch > 1 ? "cholesky_chain_batch" : "cholesky_chain")) return -1;
+    } else if (launch_sweep(s, sweep_up_kernel<SW_CHOL>, WS_CHOL, a, s->up, batch, batch > 1 ? "cholesky_batch" : "cholesky")) return -1;
     if (info_host) return fetch_fail(s, batch, info_host);
     return 0;
 }
@@ -1154,7 +1160,9 @@ int ks_llt(smcp_sym *s, double *x, int64_t batch) {
         a.t.X = x + b0 * s->d.nblk;
         a.F = s->fbuf;
         if (launch_flat<FL_LLT_LOCAL>(s, a, nb, "llt_local")) return -1;
-        if (launch_sweep(s, sweep_up_kernel<SW_ADD>, WS_ADD, a, s->up, nb, "llt")) return -1;
+        if (s->chain) {
+            if (chain_add(s, a.t.X, s->fbuf, nb, "llt_chain")) return -1;
+        } else if (launch_sweep(s, sweep_up_kernel<SW_ADD>, WS_ADD, a, s->up, nb, "llt")) return -1;
     }
     return 0;
 }
@@ -1196,12 +1204,16 @@ int ks_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
     if (sym_ensure(s, batch, false)) return -1;
     const bool big = batch >= 32;
     if (!inv) {
+        if (s->chain && batch == 1 && chain_hessian1_ok(s) && getenv("SMCP_B200_FUSED")) return chain_hessian1(h, U);   // experimental: slower than the 8-launch path (r01 v9)
         SmallArgs a = {};
         a.t.X = U;
         a.t.Lt = h->Lt;
         a.t.Yaa = h->Yaa;
-        if (launch_sweep(s, sweep_up_kernel<SW_HUP>, WS_HUP, a, s->up, batch, big ? "hessian_up_batch" : "hessian_up")) return -1;
-        if (big) {
+        if (s->chain) {
+            if (chain_prepare(h)) return -1;
+            if (chain_sweep(s, true, U, h->Lt, h->phi_up, h->psi_up, batch, big ? "hessian_up_chain_batch" : "hessian_up_chain")) return -1;
+        } else if (launch_sweep(s, sweep_up_kernel<SW_HUP>, WS_HUP, a, s->up, batch, big ? "hessian_up_batch" : "hessian_up")) return -1;
+        if (big || s->chain) {
             // one thread per (supernode, matrix) for the single-column supernodes, warps for the rest
             smcp_ctx *ctx = s->ctx;
             fill_common(s, a, s->flat, batch);
@@ -1218,6 +1230,7 @@ int ks_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
             a.list = nullptr;
             a.nlist = 0;
         } else if (launch_flat<FL_HSCALE>(s, a, batch, "hessian_scale")) return -1;
+        if (s->chain) return chain_sweep(s, false, U, h->Lt, h->phi_dn, h->psi_dn, batch, big ? "hessian_down_chain_batch" : "hessian_down_chain");
         return launch_sweep(s, sweep_down_kernel, WS_DOWN, a, s->down, batch, big ? "hessian_down_batch" : "hessian_down");
     }
     if (!h->have_Raa) {
@@ -1235,7 +1248,9 @@ int ks_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
         a.t.Raa = h->Raa;
         a.F = s->fbuf;
         if (launch_flat<FL_HINV_LOCAL>(s, a, nb, big ? "hessian_inv_local_batch" : "hessian_inv_local")) return -1;
-        if (launch_sweep(s, sweep_up_kernel<SW_ADD>, WS_ADD, a, s->up, nb, big ? "hessian_inv_batch" : "hessian_inv")) return -1;
+        if (s->chain) {
+            if (chain_add(s, a.t.X, s->fbuf, nb, big ? "hessian_inv_chain_batch" : "hessian_inv_chain")) return -1;
+        } else if (launch_sweep(s, sweep_up_kernel<SW_ADD>, WS_ADD, a, s->up, nb, big ? "hessian_inv_batch" : "hessian_inv")) return -1;
     }
     return 0;
 }

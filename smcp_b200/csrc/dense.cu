@@ -7,6 +7,7 @@
 // 3-stage cp.async pipeline, pads the tile rows so the per-thread 8-byte fragment loads
 // are bank-conflict free, and keeps a 64x32 accumulator tile per warp in registers.
 #include "internal.cuh"
+#include <algorithm>
 
 // ---------------------------------------------------------------------------------------
 // DMMA GEMM:  C(MxN) = beta*C + alpha * op(A)^T op(B)
@@ -221,180 +222,275 @@ int d_gemm_tn(smcp_ctx *ctx, const double *A, int64_t lda, const double *B, int6
 }
 
 // ---------------------------------------------------------------------------------------
-// blocked right-looking Cholesky (lower), column-major, in place
-// ---------------------------------------------------------------------------------------
+// blocked right-looking Cholesky (lower), column-major, in place (lapack.potrf, solvers.py:501)
+//
+// Per 64-column panel: ONE kernel factors the diagonal block and solves the panel below it, then
+// the DMMA kernel applies the trailing update.  At m ~ 10^3 the factorisation is a chain of tiny
+// dependent steps, so the diagonal block is factored with one ROW PER THREAD IN REGISTERS (64
+// threads, two barriers per column, fully unrolled: ~8 us instead of ~65 us through shared
+// memory) and every CTA of the panel kernel redoes that factorisation itself instead of waiting
+// for another launch to publish it.  // ---------------------------------------------------------------------------------------
 #define NB 64
+#define LDT 66          // row stride of the transposed factor in shared memory
 
-// factor the kb x kb diagonal block (one CTA); info = k0 + j + 1 at the first bad pivot
-__global__ void potrf_diag_kernel(double *H, long long ld, int kb, long long k0, int *info) {
-    __shared__ double T[NB][NB + 1];
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int idx = tid; idx < kb * kb; idx += nt) {
-        int i = idx % kb, j = idx / kb;
-        T[i][j] = (i >= j) ? H[i + j * ld] : 0.0;
-    }
-    __syncthreads();
-    for (int j = 0; j < kb; ++j) {
-        double d = T[j][j];
-        bool bad = !(d > 0.0);
-        if (bad) {
-            if (tid == 0 && *info == 0) *info = (int)(k0 + j + 1);
-            d = 1.0;
-        }
-        double s = sqrt(d);
-        __syncthreads();
-        for (int i = j + tid; i < kb; i += nt) T[i][j] = (i == j) ? s : T[i][j] / s;
-        __syncthreads();
-        int nr = kb - j - 1;
-        for (int idx = tid; idx < nr * nr; idx += nt) {
-            int i = j + 1 + idx % nr, c = j + 1 + idx / nr;
-            if (i >= c) T[i][c] = fma(-T[i][j], T[c][j], T[i][c]);
-        }
-        __syncthreads();
-    }
-    for (int idx = tid; idx < kb * kb; idx += nt) {
-        int i = idx % kb, j = idx / kb;
-        if (i >= j) H[i + j * ld] = T[i][j];
-    }
-}
+#define PP_THREADS 256
+#define PP_ROWS 128       // panel rows per CTA
 
-// panel rows: X L_kk^T = B, one row per thread
-__global__ void potrf_trsm_kernel(double *H, long long ld, int kb, long long k0, long long m) {
-    __shared__ double Lk[NB][NB + 1];
+// Diagonal block: 16 x 16 threads, each owns a 4 x 4 register block of the 64 x 64 matrix; per
+// column one barrier to publish the pivot column, one after 64 threads scaled it, then 16
+// predicated FMAs per thread.  Loops stay rolled (the first version unrolled everything and was
+// bound by instruction fetch: ncu showed stall_no_inst on 150 us launches).
+// Panel: X L^T = B, one row per thread, the row lives in shared memory (column-major, conflict
+// free), left-looking over 8-column blocks held in registers; L is read as broadcast double2.
+__global__ void __launch_bounds__(PP_THREADS) potrf_panel_kernel(double *H, long long ld, int kb, long long k0, long long m, int *info) {
+    extern __shared__ __align__(16) double ppsm[];
+    double *LT = ppsm;                       // NB x LDT: LT[c*LDT + r] = L(r, c), zero elsewhere
+    double *colbuf = LT + NB * LDT;          // 2 x NB
+    double *pivot = colbuf + 2 * NB;         // 2 (+ pad)
+    double *xs = pivot + 2;                  // NB x PP_ROWS
     const int tid = threadIdx.x;
-    const double *D = H + k0 + k0 * ld;
-    for (int idx = tid; idx < kb * kb; idx += blockDim.x) {
-        int i = idx % kb, j = idx / kb;
-        Lk[i][j] = (i >= j) ? D[i + j * ld] : 0.0;
-    }
-    __syncthreads();
-    long long row = k0 + kb + (long long)blockIdx.x * blockDim.x + tid;
-    if (row >= m) return;
-    double *P = H + row + k0 * ld;
-    double x[NB];
+    double *D = H + k0 + k0 * ld;
+    const int br = tid >> 4, bc = tid & 15;
+    double a[4][4];
 #pragma unroll
-    for (int c = 0; c < NB; ++c) x[c] = (c < kb) ? P[c * ld] : 0.0;
+    for (int k = 0; k < 4; ++k)
 #pragma unroll
-    for (int c = 0; c < NB; ++c) {
-        if (c < kb) {
-            double s = x[c];
-#pragma unroll
-            for (int r = 0; r < c; ++r) s = fma(-x[r], Lk[c][r], s);
-            x[c] = s / Lk[c][c];
+        for (int l2 = 0; l2 < 4; ++l2) {
+            const int r = 4 * br + k, c = 4 * bc + l2;
+            a[k][l2] = (r < kb && c <= r) ? D[r + (long long)c * ld] : 0.0;
         }
+    for (int idx = tid; idx < NB * LDT; idx += PP_THREADS) LT[idx] = 0.0;
+    for (int j = 0; j < kb; ++j) {
+        double *cb = colbuf + (j & 1) * NB;
+        const int jb = j >> 2, jj = j & 3;
+        if (bc == jb) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double v = (jj == 0) ? a[k][0] : (jj == 1) ? a[k][1] : (jj == 2) ? a[k][2] : a[k][3];
+                cb[4 * br + k] = v;
+                if (4 * br + k == j) pivot[j & 1] = v;
+            }
+        }
+        __syncthreads();
+        if (tid < NB) {
+            double d = pivot[j & 1];
+            const bool bad = !(d > 0.0);
+            if (bad) d = 1.0;
+            if (bad && tid == 0 && blockIdx.x == 0 && *info == 0) *info = (int)(k0 + j + 1);   // dpotrf's info
+            const double sq = sqrt(d);
+            const double v = cb[tid];
+            cb[tid] = (tid == j) ? sq : ((tid > j) ? v / sq : 0.0);
+        }
+        __syncthreads();
+        double lr[4], lc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            lr[k] = cb[4 * br + k];
+            lc[k] = cb[4 * bc + k];
+        }
+        if (bc == jb) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (jj == 0) a[k][0] = lr[k];
+                else if (jj == 1) a[k][1] = lr[k];
+                else if (jj == 2) a[k][2] = lr[k];
+                else a[k][3] = lr[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int l2 = 0; l2 < 4; ++l2)
+                if (4 * bc + l2 > j) a[k][l2] = fma(-lr[k], lc[l2], a[k][l2]);     // rows <= j have lr = 0 or are finished columns
     }
 #pragma unroll
-    for (int c = 0; c < NB; ++c)
-        if (c < kb) P[c * ld] = x[c];
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int l2 = 0; l2 < 4; ++l2) {
+            const int r = 4 * br + k, c = 4 * bc + l2;
+            if (r < kb && c <= r) {
+                LT[c * LDT + r] = a[k][l2];
+                if (blockIdx.x == 0) D[r + (long long)c * ld] = a[k][l2];
+            }
+        }
+    __syncthreads();
+    // ---- panel rows
+    const long long row = k0 + kb + (long long)blockIdx.x * PP_ROWS + tid;
+    if (tid >= PP_ROWS || row >= m) return;
+    double *P = H + row + k0 * ld;
+    for (int c = 0; c < kb; ++c) xs[c * PP_ROWS + tid] = P[(long long)c * ld];
+    for (int cb8 = 0; cb8 < kb; cb8 += 8) {
+        double x8[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x8[k] = (cb8 + k < kb) ? xs[(cb8 + k) * PP_ROWS + tid] : 0.0;
+        for (int p = 0; p < cb8; ++p) {
+            const double xp = xs[p * PP_ROWS + tid];
+            const double2 *lp = reinterpret_cast<const double2 *>(LT + p * LDT + cb8);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double2 lv = lp[k];
+                x8[2 * k] = fma(-xp, lv.x, x8[2 * k]);
+                x8[2 * k + 1] = fma(-xp, lv.y, x8[2 * k + 1]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (cb8 + k < kb) {
+                const double xk = x8[k] / LT[(cb8 + k) * LDT + cb8 + k];
+                x8[k] = xk;
+#pragma unroll
+                for (int k2 = k + 1; k2 < 8; ++k2) x8[k2] = fma(-xk, LT[(cb8 + k) * LDT + cb8 + k2], x8[k2]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (cb8 + k < kb) {
+                xs[(cb8 + k) * PP_ROWS + tid] = x8[k];
+                P[(long long)(cb8 + k) * ld] = x8[k];
+            }
+    }
 }
 
-int d_potrf(smcp_ctx *ctx, double *H, int64_t m, int32_t *info_dev) {
+int d_potrf(smcp_ctx *ctx, double *H, int64_t m, int32_t *info_dev, double *Dinv) {
     CUDA_TRY(cudaMemsetAsync(info_dev, 0, sizeof(int), ctx->stream));
+    const size_t pp_smem = (size_t)(NB * LDT + 2 * NB + 2 + NB * PP_ROWS) * sizeof(double);
+    static bool pp_attr = false;
+    if (!pp_attr) {
+        CUDA_TRY(cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem));
+        pp_attr = true;
+    }
     for (int64_t k0 = 0; k0 < m; k0 += NB) {
         int kb = (int)((m - k0 < NB) ? (m - k0) : NB);
-        {
-            LaunchScope ls(ctx, "potrf_diag");
-            potrf_diag_kernel<<<1, 256, 0, ctx->stream>>>(H + k0 + k0 * m, m, kb, k0, info_dev);
-        }
         int64_t rem = m - k0 - kb;
+        {
+            LaunchScope ls(ctx, "potrf_panel", 1, 16.0 * (double)(m - k0) * kb);
+            unsigned grid = (unsigned)std::max<int64_t>(1, (rem + PP_ROWS - 1) / PP_ROWS);
+            potrf_panel_kernel<<<grid, PP_THREADS, pp_smem, ctx->stream>>>(H, m, kb, k0, m, info_dev);
+        }
         if (rem > 0) {
-            {
-                LaunchScope ls(ctx, "potrf_trsm");
-                potrf_trsm_kernel<<<(unsigned)((rem + 127) / 128), 128, 0, ctx->stream>>>(H, m, kb, k0, m);
-            }
             const double *P = H + (k0 + kb) + k0 * m;
             double *Ct = H + (k0 + kb) + (k0 + kb) * m;
             if (launch_gemm(ctx, false, P, m, P, m, Ct, m, rem, rem, kb, -1.0, 1, 1, 0, "potrf_syrk_dmma")) return -1;
         }
     }
+    (void)Dinv;
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
 // ---------------------------------------------------------------------------------------
-// potrs: y <- L^{-T} L^{-1} y, single right-hand side, one persistent CTA
+// potrs: y <- L^{-T} L^{-1} y (lapack.potrs, solvers.py:526), single right-hand side.
+// A triangular solve is m dependent steps whatever the hardware, so this is a latency kernel:
+// one CTA of 1024 threads, the right-hand side lives in shared memory for the whole solve, the
+// 64 x 64 diagonal block is staged in shared memory, substitution inside a block is done by one
+// warp (row values in registers, pivot broadcast by shuffle, multiplication by the reciprocal
+// pivots computed off the critical path), and the off-diagonal part of every block column is a
+// GEMV spread over all 32 warps with independent partial sums.  Plain substitution, no explicit
+// inverses: backward stable like the LAPACK routine it replaces.
 // ---------------------------------------------------------------------------------------
-#define PS_THREADS 512
+#define PS_THREADS 1024
 __global__ void __launch_bounds__(PS_THREADS) potrs_kernel(const double *__restrict__ H, long long m, double *__restrict__ y) {
-    __shared__ double Lk[NB][NB + 1];
-    __shared__ double xb[NB];
+    extern __shared__ double psm[];
+    double *Lk = psm;                    // NB x (NB+1)
+    double *rinv = Lk + NB * (NB + 1);   // NB
+    double *tb = rinv + NB;              // NB
+    double *ys = tb + NB;                // m
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nwarps = PS_THREADS / 32;
+    const long long nblkc = (m + NB - 1) / NB;
+    for (long long i = tid; i < m; i += PS_THREADS) ys[i] = y[i];
     // forward: L x = y
-    for (long long k0 = 0; k0 < m; k0 += NB) {
-        int kb = (int)min((long long)NB, m - k0);
+    for (long long bi = 0; bi < nblkc; ++bi) {
+        const long long k0 = bi * NB;
+        const int kb = (int)min((long long)NB, m - k0);
         for (int idx = tid; idx < kb * kb; idx += PS_THREADS) {
-            int i = idx % kb, j = idx / kb;
-            Lk[i][j] = H[(k0 + i) + (k0 + j) * m];
+            const int i = idx % kb, j = idx / kb;
+            Lk[i * (NB + 1) + j] = H[(k0 + i) + (k0 + j) * m];
         }
-        if (tid < kb) xb[tid] = y[k0 + tid];
+        __syncthreads();
+        if (tid < kb) rinv[tid] = 1.0 / Lk[tid * (NB + 1) + tid];
         __syncthreads();
         if (warp == 0) {
-            // lanes own rows lane and lane+32
-            double x0 = (lane < kb) ? xb[lane] : 0.0;
-            double x1 = (lane + 32 < kb) ? xb[lane + 32] : 0.0;
+            double x0 = (lane < kb) ? ys[k0 + lane] : 0.0;
+            double x1 = (lane + 32 < kb) ? ys[k0 + lane + 32] : 0.0;
             for (int j = 0; j < kb; ++j) {
-                double xj = __shfl_sync(0xffffffffu, (j < 32) ? x0 : x1, j & 31);
-                xj = xj / Lk[j][j];
+                const double xj = __shfl_sync(0xffffffffu, (j < 32) ? x0 : x1, j & 31) * rinv[j];
                 if (lane == (j & 31)) { if (j < 32) x0 = xj; else x1 = xj; }
-                if (lane > j && lane < kb) x0 = fma(-Lk[lane][j], xj, x0);
-                if (lane + 32 > j && lane + 32 < kb) x1 = fma(-Lk[lane + 32][j], xj, x1);
+                if (lane > j) x0 = fma(-Lk[lane * (NB + 1) + j], xj, x0);
+                if (lane + 32 > j && lane + 32 < kb) x1 = fma(-Lk[(lane + 32) * (NB + 1) + j], xj, x1);
             }
-            if (lane < kb) xb[lane] = x0;
-            if (lane + 32 < kb) xb[lane + 32] = x1;
+            if (lane < kb) ys[k0 + lane] = x0;
+            if (lane + 32 < kb) ys[k0 + lane + 32] = x1;
         }
         __syncthreads();
-        if (tid < kb) y[k0 + tid] = xb[tid];
-        // y[k0+kb:] -= L[k0+kb:, k0:k0+kb] * xb
         for (long long i = k0 + kb + tid; i < m; i += PS_THREADS) {
-            double s = y[i];
             const double *Lr = H + i + k0 * m;
-            for (int j = 0; j < kb; ++j) s = fma(-Lr[j * m], xb[j], s);
-            y[i] = s;
+            const double *xk = ys + k0;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 4
+            for (int j = 0; j < NB; j += 4) {       // here kb == NB (rows remain below the block)
+                s0 = fma(Lr[(long long)j * m], xk[j], s0);
+                s1 = fma(Lr[(long long)(j + 1) * m], xk[j + 1], s1);
+                s2 = fma(Lr[(long long)(j + 2) * m], xk[j + 2], s2);
+                s3 = fma(Lr[(long long)(j + 3) * m], xk[j + 3], s3);
+            }
+            ys[i] -= (s0 + s1) + (s2 + s3);
         }
         __syncthreads();
     }
     // backward: L^T x = y
-    long long nblk = (m + NB - 1) / NB;
-    for (long long bi = nblk - 1; bi >= 0; --bi) {
-        long long k0 = bi * NB;
-        int kb = (int)min((long long)NB, m - k0);
-        // xb = y[k0:k0+kb] - L[k0+kb:, k0:k0+kb]^T y[k0+kb:]
-        for (int j = warp; j < kb; j += nwarps) {
-            const double *Lc = H + (k0 + j) * m;
-            double s = 0.0;
-            for (long long i = k0 + kb + lane; i < m; i += 32) s = fma(Lc[i], y[i], s);
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-            if (lane == 0) xb[j] = y[k0 + j] - s;
-        }
+    for (long long bi = nblkc - 1; bi >= 0; --bi) {
+        const long long k0 = bi * NB;
+        const int kb = (int)min((long long)NB, m - k0);
         for (int idx = tid; idx < kb * kb; idx += PS_THREADS) {
-            int i = idx % kb, j = idx / kb;
-            Lk[i][j] = H[(k0 + i) + (k0 + j) * m];
+            const int i = idx % kb, j = idx / kb;
+            Lk[i * (NB + 1) + j] = H[(k0 + i) + (k0 + j) * m];
         }
+        // t_c = y[k0+c] - sum_{i >= k0+kb} L(i, k0+c) y[i]: warp w takes columns w and w + 32
+        for (int c = warp; c < kb; c += PS_THREADS / 32) {
+            const double *Lc = H + (k0 + c) * m;
+            double s0 = 0.0, s1 = 0.0;
+            long long i = k0 + kb + lane;
+            for (; i + 32 < m; i += 64) {
+                s0 = fma(Lc[i], ys[i], s0);
+                s1 = fma(Lc[i + 32], ys[i + 32], s1);
+            }
+            if (i < m) s0 = fma(Lc[i], ys[i], s0);
+            double sacc = s0 + s1;
+            for (int o = 16; o > 0; o >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, o);
+            if (lane == 0) tb[c] = ys[k0 + c] - sacc;
+        }
+        __syncthreads();
+        if (tid < kb) rinv[tid] = 1.0 / Lk[tid * (NB + 1) + tid];
         __syncthreads();
         if (warp == 0) {
-            double x0 = (lane < kb) ? xb[lane] : 0.0;
-            double x1 = (lane + 32 < kb) ? xb[lane + 32] : 0.0;
+            double x0 = (lane < kb) ? tb[lane] : 0.0;
+            double x1 = (lane + 32 < kb) ? tb[lane + 32] : 0.0;
             for (int j = kb - 1; j >= 0; --j) {
-                double xj = __shfl_sync(0xffffffffu, (j < 32) ? x0 : x1, j & 31);
-                xj = xj / Lk[j][j];
+                const double xj = __shfl_sync(0xffffffffu, (j < 32) ? x0 : x1, j & 31) * rinv[j];
                 if (lane == (j & 31)) { if (j < 32) x0 = xj; else x1 = xj; }
-                if (lane < j) x0 = fma(-Lk[j][lane], xj, x0);
-                if (lane + 32 < j) x1 = fma(-Lk[j][lane + 32], xj, x1);
+                if (lane < j) x0 = fma(-Lk[j * (NB + 1) + lane], xj, x0);
+                if (lane + 32 < j) x1 = fma(-Lk[j * (NB + 1) + lane + 32], xj, x1);
             }
-            if (lane < kb) xb[lane] = x0;
-            if (lane + 32 < kb) xb[lane + 32] = x1;
+            if (lane < kb) ys[k0 + lane] = x0;
+            if (lane + 32 < kb) ys[k0 + lane + 32] = x1;
         }
         __syncthreads();
-        if (tid < kb) y[k0 + tid] = xb[tid];
-        __syncthreads();
     }
+    for (long long i = tid; i < m; i += PS_THREADS) y[i] = ys[i];
 }
 
-int d_potrs(smcp_ctx *ctx, const double *H, int64_t m, double *y_dev) {
+int d_potrs(smcp_ctx *ctx, const double *H, int64_t m, const double *Dinv, double *y_dev) {
+    (void)Dinv;
+    const size_t smem = (size_t)(NB * (NB + 1) + 2 * NB + m + 8) * sizeof(double);
+    if (smem > 200 * 1024) { smcp_set_error("potrs: m = %lld exceeds the single-CTA kernel (right-hand side in shared memory)", (long long)m); return -2; }
+    static size_t attr = 0;
+    if (smem > attr) {
+        CUDA_TRY(cudaFuncSetAttribute(potrs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
     {
-        LaunchScope ls(ctx, "potrs");
-        potrs_kernel<<<1, PS_THREADS, 0, ctx->stream>>>(H, m, y_dev);
+        LaunchScope ls(ctx, "potrs", 1, 8.0 * (double)m * (double)m);
+        potrs_kernel<<<1, PS_THREADS, smem, ctx->stream>>>(H, m, y_dev);
     }
     CUDA_TRY(cudaGetLastError());
     return 0;

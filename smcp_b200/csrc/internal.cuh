@@ -116,6 +116,11 @@ struct smcp_sym {
     SmallDev sm = {};
     double *fbuf = nullptr;          // batch x nsq local fronts (llt, inverse Hessian)
     size_t fbuf_cap = 0;
+    // chain clique trees with single-column supernodes: segment-parallel sweeps (chordal_chain.cuh)
+    bool chain = false;
+    int chW = 0, chN = 0, chP = 0, ch_root_off = 0, ch_root_nj = 0;
+    double *ch_state = nullptr;      // batch x P x D boundary states
+    size_t ch_state_cap = 0;
     // host copies used by the operator setup
     std::vector<int> h_vec2blk;
     std::vector<int64_t> h_snptr;
@@ -127,6 +132,8 @@ struct smcp_hess {
     double *Yaa = nullptr;     // nupd: Y_{alpha alpha}, full symmetric
     double *Raa = nullptr;     // nupd: chol(Y_aa) (lazily, for the inverse map)
     bool have_Raa = false;
+    double *phi_up = nullptr, *phi_dn = nullptr, *psi_up = nullptr, *psi_dn = nullptr;   // chain path: segment propagators of the two sweeps
+    bool have_phi = false;
     const double *L = nullptr; // the factor it was built from (not owned)
 };
 
@@ -163,8 +170,8 @@ int k_gather_vec(smcp_sym *s, const double *src, double *dev_vec);
 int k_axpy_batch(smcp_sym *s, const double *x, const double *dx, const double *gam_dev, double *out, int64_t count);
 
 // dense kernels (dense.cu)
-int d_potrf(smcp_ctx *ctx, double *H, int64_t m, int32_t *info_dev);
-int d_potrs(smcp_ctx *ctx, const double *H, int64_t m, double *y_dev);
+int d_potrf(smcp_ctx *ctx, double *H, int64_t m, int32_t *info_dev, double *Dinv);
+int d_potrs(smcp_ctx *ctx, const double *H, int64_t m, const double *Dinv, double *y_dev);
 // C(lower blocks, rows i0.. ) = A^T * B : A is K x M (col-major, ld K), B is K x N
 int d_gemm_tn(smcp_ctx *ctx, const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
               int64_t ldc, int64_t M, int64_t N, int64_t K, int64_t row_lo_of_col0);

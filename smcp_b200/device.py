@@ -47,6 +47,7 @@ API = {
     "smcp_flush_l2": (_int, [_vp]),
     "smcp_sym_create": (_int, [_vp, C.POINTER(SymDesc), C.POINTER(_vp)]),
     "smcp_sym_destroy": (_int, [_vp]),
+    "smcp_sym_reserve": (_int, [_vp, _i64]),
     "smcp_csp_alloc": (_int, [_vp, _i64, C.POINTER(_dp)]),
     "smcp_csp_free": (_int, [_vp, _dp]),
     "smcp_csp_copy": (_int, [_vp, _dp, _dp, _i64]),
@@ -203,6 +204,7 @@ def owned_column_blocks(m, rank, nranks, block):
 class DeviceBackend:
     """``BackendProtocol`` (see ``smcp_b200.chordal``) on the CUDA library."""
     name = "cuda-sm100a"
+    batched_probes = True        # line-search probes are evaluated as one device batch
 
     def __init__(self, symb, device=None, small_work=200000, comm=None):
         self.ctx = Context.get(device)
@@ -224,6 +226,9 @@ class DeviceBackend:
         h = C.c_void_p()
         _ck(lib, lib.smcp_sym_create(self.ctx.h, C.byref(d), C.byref(h)))
         self.sym = h
+        if symb.nblk * 255 * 8 <= (1 << 30):
+            # workspaces of the batched line-search probes (255 candidates) sized at setup time
+            _ck(lib, lib.smcp_sym_reserve(h, 255))
         self._pool = []
         self._op = None
         self._tok = None

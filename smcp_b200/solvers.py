@@ -285,6 +285,28 @@ def _frob(X):
     return math.sqrt(dot(X, X))
 
 
+_tree_cache = {}
+
+
+def _bisection_tree(minstep, depth=8):
+    """Step lengths of every node of the bisection on [minstep, 1] in heap order (node 1 = first
+    midpoint; child 2i after a failed probe, 2i+1 after a successful one), computed with the
+    same floating-point expression ``(gmin + gmax) / 2`` as the sequential loop."""
+    key = (float(minstep), depth)
+    if key not in _tree_cache:
+        gam = np.zeros(2 ** depth)
+        lo = np.zeros(2 ** depth)
+        hi = np.zeros(2 ** depth)
+        lo[1], hi[1] = minstep, 1.0
+        for i in range(1, 2 ** depth):
+            gam[i] = (lo[i] + hi[i]) / 2.0
+            if 2 * i + 1 < 2 ** depth:
+                lo[2 * i], hi[2 * i] = lo[i], gam[i]              # failure: gmax = gam
+                lo[2 * i + 1], hi[2 * i + 1] = gam[i], hi[i]      # success: gmin = gam
+        _tree_cache[key] = gam
+    return _tree_cache[key]
+
+
 def _in_cone(X, test):
     """True iff ``test`` (cholesky or completion) succeeds on a copy of X; returns the
     factor as well."""
@@ -356,7 +378,28 @@ def chordalsolver_feas(A, b, primalstart=None, dualstart=None, scaling="primal",
         return x, y
 
     def bisect(X, dX, test):
-        # 8 halvings on [MINSTEP, 1] (solvers.py:615-647)
+        # 8 halvings on [MINSTEP, 1] (solvers.py:615-647).  The verdict of a probe depends only on
+        # its step length, so on a backend with batched probes the whole decision tree of the
+        # bisection (255 candidate steps) is evaluated as ONE device batch and the reference's
+        # decisions are replayed on the verdicts; otherwise the probes run one after the other.
+        ops = prob.ops
+        if getattr(ops, "batched_probes", False):
+            tree = _bisection_tree(MINSTEP)
+            ok, _ = ops.probe("completion" if test is completion else "cholesky", X.buf, dX.buf, tree[1:])
+            gmin, gmax = MINSTEP, 1.0
+            g_ok = gmin
+            node = 1
+            for _ in range(8):
+                gam = tree[node]
+                if ok[node - 1]:
+                    gmin = gam
+                    g_ok = gam
+                    node = 2 * node + 1
+                else:
+                    gmax = gam
+                    g_ok = gmin
+                    node = 2 * node
+            return g_ok
         gmin, gmax = MINSTEP, 1.0
         g_ok = gmin
         for _ in range(8):

@@ -24,6 +24,10 @@ def _cases():
             # task partition that cuts the tree into many tasks (cross-warp hand-off)
             out.append(p + ("cta",))
             out.append(p + ("split",))
+        if p[1] == 0 and p[2] >= 1:
+            # band patterns: chain clique trees take the segment-parallel kernels by default;
+            # keep the warp-per-chain sweeps covered on them as well
+            out.append(p + ("nochain",))
     return out
 
 
@@ -36,10 +40,13 @@ def setup(request):
     symb = make_symbolic(n, ne, bw, seed)
     if mode == "cta":
         os.environ["SMCP_B200_NO_SMALL"] = "1"
+    if mode == "nochain":
+        os.environ["SMCP_B200_NO_CHAIN"] = "1"
     try:
         dev = DeviceBackend(symb, small_work=0 if mode == "split" else 2000)
     finally:
         os.environ.pop("SMCP_B200_NO_SMALL", None)
+        os.environ.pop("SMCP_B200_NO_CHAIN", None)
     s = random_pd(symb, seed)
     l = s.copy()
     sn.cholesky(symb, l)
