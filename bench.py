@@ -213,6 +213,7 @@ class IterTimer:
 
 
 def run_b200(args):
+    os.environ["NCCL_DEBUG"] = os.environ.get("SMCP_NCCL_DEBUG", "WARN")    # keep stdout to the one JSON line
     rank, world, local, pg = dist_setup(args)
     os.environ["LOCAL_RANK"] = str(local)
     from smcp_b200 import solvers, device
@@ -224,7 +225,9 @@ def run_b200(args):
         if rank == 0:
             idt = torch.frombuffer(bytearray(device.comm_unique_id()), dtype=torch.uint8).clone()
         pg.broadcast(idt, src=0)
-        device.init_comm(rank, world, bytes(idt.numpy().tobytes()), block=64, device=local)
+        # column blocks of H: 128 columns keep the DMMA tiles full; 64 when that would leave ranks idle
+        blk = 128 if WORKLOADS[args.workload][1] >= 256 * world else 64
+        device.init_comm(rank, world, bytes(idt.numpy().tobytes()), block=blk, device=local)
 
     W, K = args.warmup, args.steps
     solvers.options["show_progress"] = False

@@ -148,6 +148,8 @@ int smcp_op_aadj(smcp_op *op, const double *host_y, double *X);
 /* assemble the lower triangle of H (H_ij = A_i . Hess(A_j)); columns [j0, j1) only when
  * sharding across GPUs (pass 0, m for everything)                                          */
 int smcp_kkt_assemble(smcp_op *op, smcp_hess *h, int64_t j0, int64_t j1);
+/* multi-GPU: assemble the column blocks q = rank (mod nranks) of `block` columns as one batch */
+int smcp_kkt_assemble_cyclic(smcp_op *op, smcp_hess *h, int64_t block, int rank, int nranks);
 /* lapack.potrf(H): info_host = 0 ok, k > 0 if the leading minor of order k is not PD        */
 int smcp_kkt_factor(smcp_op *op, int32_t *info_host);
 /* lapack.potrs(H, y) in place on a host m-vector */

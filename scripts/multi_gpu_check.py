@@ -61,8 +61,7 @@ zref = sl.cho_solve(sl.cho_factor(Hs, lower=True), rhs)
 err_solve = np.linalg.norm(z - zref) / np.linalg.norm(zref)
 # exchange check: re-assemble sharded without factoring
 ops.lib.smcp_kkt_set_H(ops._op, np.zeros(m * m))
-for c0, c1 in owned_column_blocks(m, rank, world, 64):
-    ops.schur_assemble(tok, c0, c1)
+device._ck(ops.lib, ops.lib.smcp_kkt_assemble_cyclic(ops._op, tok, 64, rank, world))
 device._ck(ops.lib, ops.lib.smcp_kkt_allgather(ops._op, 64, rank, world))
 Hsh = np.tril(ops.get_H())
 err_H = np.linalg.norm(Hsh - Hfull) / np.linalg.norm(Hfull)

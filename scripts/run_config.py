@@ -1,0 +1,80 @@
+"""Run one BASELINE.json configuration through the public API on the CUDA backend for a few
+iterations and report seconds per iteration (device families included).
+
+    python scripts/run_config.py C4 [iters]      # mtxnorm p=q=200, r=500 (solve_esd)
+    python scripts/run_config.py C3 [iters] [n] [m]   # rand_SDP, sparse aggregate pattern
+    python scripts/run_config.py C5 [iters] [n]  # max-cut on a random sparse graph (solve_esd)
+    python scripts/run_config.py C2 [iters]      # band n=5000 m=1000 (solve_feas)
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import scipy.sparse as sp
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import smcp_b200 as S
+from smcp_b200 import solvers
+from smcp_b200.device import Context
+
+cfg = sys.argv[1]
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+t0 = time.time()
+kw = {}
+if cfg == "C2":
+    P = S.band_SDP(5000, 1000, 5, seed=0)
+    method, kw = "feas", {"primalstart": {"x": P._X0}}
+elif cfg == "C4":
+    P = S.mtxnorm_SDP(200, 200, 500, density=1.0, seed=0)
+    method = "esd"
+elif cfg == "C3":
+    n = int(sys.argv[3]) if len(sys.argv) > 3 else 2000
+    m = int(sys.argv[4]) if len(sys.argv) > 4 else 10000
+    rng = np.random.default_rng(0)
+    ne = 3 * n
+    e = rng.integers(0, n, size=(ne, 2))
+    I = np.concatenate([e[:, 0], np.arange(n), np.arange(1, n)])
+    J = np.concatenate([e[:, 1], np.arange(n), np.arange(0, n - 1)])
+    V = sp.coo_matrix((np.ones(len(I)), (I, J)), shape=(n, n))
+    P = S.rand_SDP(V, m, density=0.005, seed=0)
+    method, kw = "feas", ({"primalstart": {"x": P._X0}} if getattr(P, "_X0", None) is not None else {})
+elif cfg == "C5":
+    n = int(sys.argv[3]) if len(sys.argv) > 3 else 20000
+    rng = np.random.default_rng(0)
+    e = rng.integers(0, n, size=(3 * n // 2, 2))
+    P = S.maxcut_SDP(n, e)
+    method = "esd"
+else:
+    raise SystemExit("unknown config")
+print("%s: %s generated in %.1f s" % (cfg, P, time.time() - t0), flush=True)
+ctx = Context.get()
+solvers.options["maxiters"] = iters
+solvers.options["show_progress"] = False
+stamps = {}
+
+
+def hook(name, it):
+    ctx.sync()
+    stamps[it] = time.perf_counter()
+
+
+solvers._iteration_hook = hook
+ctx.prof_reset()
+ctx.prof_enable(True)
+t0 = time.time()
+sol = getattr(P, "solve_" + method)(kktsolver="chol", **kw)
+ctx.prof_enable(False)
+print("solve_%s: status %s, %d iterations, %.2f s total (incl. setup)" % (method, sol["status"], sol["iterations"], time.time() - t0))
+its = sorted(stamps)
+for a, b in zip(its[:-1], its[1:]):
+    print("  iteration %d: %.2f ms (with per-launch event timing on)" % (a, 1e3 * (stamps[b] - stamps[a])))
+rows = []
+for nm in ctx.prof_names():
+    ms, cnt = ctx.prof_get(nm)
+    if cnt:
+        rows.append((ms, nm, cnt))
+tot = sum(r[0] for r in rows)
+for ms, nm, cnt in sorted(rows, reverse=True)[:14]:
+    print("  %-28s %10.3f ms %7d launches %5.1f%%" % (nm, ms, cnt, 100 * ms / tot))
+print("  device total %.1f ms" % tot)

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <algorithm>
+#include <utility>
 #include <dlfcn.h>
 
 static thread_local char g_err[1024] = "";
@@ -642,37 +643,60 @@ __global__ void set_identity_kernel(double *Z, long long n) {
     if (i < n) Z[i + i * n] = 1.0;
 }
 
-extern "C" int smcp_kkt_assemble(smcp_op *op, smcp_hess *h, int64_t j0, int64_t j1) {
+// technique 1 on a set of column ranges: ONE batched Hessian over all of them (the chordal kernels
+// are latency/issue bound, small batches waste the machine), then one DMMA contraction per range
+static int assemble_dense_ranges(smcp_op *op, smcp_hess *h, const std::vector<std::pair<int64_t, int64_t>> &ranges) {
     smcp_sym *s = op->sym;
     smcp_ctx *ctx = s->ctx;
-    const int64_t m = op->m, md = op->md;
+    const int64_t m = op->m;
     const long long nblk = s->d.nblk;
-    if (j1 > m) j1 = m;
-    // technique 1: batched Hessian + DMMA contraction
-    int64_t d0 = std::max<int64_t>(j0, 0), d1 = std::min<int64_t>(j1, md);
-    if (d1 > d0) {
-        size_t per_col = ((size_t)nblk + (size_t)s->d.nupd) * sizeof(double);
-        int64_t chunk = (int64_t)std::max<size_t>(1, ((size_t)6 << 30) / per_col);
-        chunk = std::min<int64_t>(chunk, 2048);
-        chunk = std::min<int64_t>(chunk, d1 - d0);
-        if (grow((void **)&op->Ub, &op->Ub_cap, (size_t)chunk * nblk * sizeof(double))) return -1;
-        for (int64_t c0 = d0; c0 < d1; c0 += chunk) {
-            int64_t nc = std::min<int64_t>(chunk, d1 - c0);
-            CUDA_TRY(cudaMemsetAsync(op->Ub, 0, (size_t)nc * nblk * sizeof(double), ctx->stream));
-            {
-                LaunchScope ls(ctx, "scatter_cols");
-                scatter_cols_kernel<<<(unsigned)nc, 128, 0, ctx->stream>>>(op->colptr, op->rowblk, op->vals, op->Ub, nblk, c0, (int)nc);
-            }
-            if (k_hess_apply(h, op->Ub, nc, 0)) return -1;
-            // H[c0:m, c0:c0+nc] = (w.Av[:, c0:m])^T W
-            if (d_gemm_tn(ctx, op->AvW + (size_t)c0 * nblk, nblk, op->Ub, nblk, op->H + c0 + c0 * m, m, m - c0, nc, nblk, 0)) return -1;
+    if (ranges.empty()) return 0;
+    size_t per_col = ((size_t)nblk + (size_t)s->d.nupd) * sizeof(double);
+    int64_t cap = (int64_t)std::max<size_t>(1, ((size_t)6 << 30) / per_col);
+    cap = std::min<int64_t>(cap, 2048);
+    // split ranges that exceed the capacity, then group consecutive pieces up to `cap` columns
+    std::vector<std::pair<int64_t, int64_t>> pieces;
+    for (auto r : ranges)
+        for (int64_t c0 = r.first; c0 < r.second; c0 += cap) pieces.push_back({c0, std::min(r.second, c0 + cap)});
+    size_t gi = 0;
+    while (gi < pieces.size()) {
+        size_t ge = gi;
+        int64_t ncols = 0;
+        while (ge < pieces.size() && ncols + (pieces[ge].second - pieces[ge].first) <= cap) {
+            ncols += pieces[ge].second - pieces[ge].first;
+            ++ge;
         }
+        if (grow((void **)&op->Ub, &op->Ub_cap, (size_t)ncols * nblk * sizeof(double))) return -1;
+        CUDA_TRY(cudaMemsetAsync(op->Ub, 0, (size_t)ncols * nblk * sizeof(double), ctx->stream));
+        int64_t off = 0;
+        for (size_t q = gi; q < ge; ++q) {
+            const int64_t c0 = pieces[q].first, nc = pieces[q].second - c0;
+            LaunchScope ls(ctx, "scatter_cols");
+            scatter_cols_kernel<<<(unsigned)nc, 128, 0, ctx->stream>>>(op->colptr, op->rowblk, op->vals, op->Ub + (size_t)off * nblk, nblk, c0, (int)nc);
+            off += nc;
+        }
+        if (k_hess_apply(h, op->Ub, ncols, 0)) return -1;
+        off = 0;
+        for (size_t q = gi; q < ge; ++q) {
+            const int64_t c0 = pieces[q].first, nc = pieces[q].second - c0;
+            // H[c0:m, c0:c0+nc] = (w.Av[:, c0:m])^T W
+            if (d_gemm_tn(ctx, op->AvW + (size_t)c0 * nblk, nblk, op->Ub + (size_t)off * nblk, nblk, op->H + c0 + c0 * m, m, m - c0, nc, nblk, 0)) return -1;
+            off += nc;
+        }
+        gi = ge;
     }
-    // technique 2: sparse constraints through the dense inverse of S
-    int64_t s0 = std::max<int64_t>(j0, md), s1 = j1;
-    if (s1 > s0) {
-        if (!op->ent_r) { smcp_set_error("entry coordinates not set (smcp_op_set_entry_coords)"); return -2; }
-        const long long n = s->d.n;
+    return 0;
+}
+
+// technique 2: sparse constraints through the dense inverse of S (columns [s0, s1))
+static int assemble_sparse_range(smcp_op *op, smcp_hess *h, int64_t s0, int64_t s1, bool fresh_inverse) {
+    smcp_sym *s = op->sym;
+    smcp_ctx *ctx = s->ctx;
+    const int64_t m = op->m;
+    if (s1 <= s0) return 0;
+    if (!op->ent_r) { smcp_set_error("entry coordinates not set (smcp_op_set_entry_coords)"); return -2; }
+    const long long n = s->d.n;
+    if (fresh_inverse) {
         if (!op->Zinv) CUDA_TRY(cudaMalloc(&op->Zinv, (size_t)n * n * sizeof(double)));
         CUDA_TRY(cudaMemsetAsync(op->Zinv, 0, (size_t)n * n * sizeof(double), ctx->stream));
         {
@@ -681,9 +705,40 @@ extern "C" int smcp_kkt_assemble(smcp_op *op, smcp_hess *h, int64_t j0, int64_t 
         }
         if (k_trsm(s, h->L, op->Zinv, n, n, 0)) return -1;
         if (k_trsm(s, h->L, op->Zinv, n, n, 1)) return -1;
-        {
-            LaunchScope ls(ctx, "scm_sparse");
-            scm_sparse_kernel<<<(unsigned)(s1 - s0), 128, 0, ctx->stream>>>(op->colptr, op->vals, op->ent_r, op->ent_c, op->Zinv, n, op->H, m, s0);
+    }
+    {
+        LaunchScope ls(ctx, "scm_sparse");
+        scm_sparse_kernel<<<(unsigned)(s1 - s0), 128, 0, ctx->stream>>>(op->colptr, op->vals, op->ent_r, op->ent_c, op->Zinv, n, op->H, m, s0);
+    }
+    return 0;
+}
+
+extern "C" int smcp_kkt_assemble(smcp_op *op, smcp_hess *h, int64_t j0, int64_t j1) {
+    const int64_t m = op->m, md = op->md;
+    if (j1 > m) j1 = m;
+    int64_t d0 = std::max<int64_t>(j0, 0), d1 = std::min<int64_t>(j1, md);
+    if (d1 > d0 && assemble_dense_ranges(op, h, {{d0, d1}})) return -1;
+    if (assemble_sparse_range(op, h, std::max<int64_t>(j0, md), j1, true)) return -1;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// the column blocks q = rank (mod nranks) of `block` columns each, as ONE batch
+extern "C" int smcp_kkt_assemble_cyclic(smcp_op *op, smcp_hess *h, int64_t block, int rank, int nranks) {
+    const int64_t m = op->m, md = op->md;
+    if (block < 1 || nranks < 1 || rank < 0 || rank >= nranks) { smcp_set_error("smcp_kkt_assemble_cyclic: bad arguments"); return -2; }
+    std::vector<std::pair<int64_t, int64_t>> dense;
+    bool fresh = true;
+    for (int64_t c0 = (int64_t)rank * block; c0 < m; c0 += (int64_t)nranks * block) {
+        const int64_t c1 = std::min(m, c0 + block);
+        if (c0 < md) dense.push_back({c0, std::min(c1, md)});
+    }
+    if (assemble_dense_ranges(op, h, dense)) return -1;
+    for (int64_t c0 = (int64_t)rank * block; c0 < m; c0 += (int64_t)nranks * block) {
+        const int64_t c1 = std::min(m, c0 + block);
+        if (c1 > md) {
+            if (assemble_sparse_range(op, h, std::max(c0, md), c1, fresh)) return -1;
+            fresh = false;
         }
     }
     CUDA_TRY(cudaGetLastError());

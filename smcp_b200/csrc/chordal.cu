@@ -74,7 +74,7 @@ __global__ void tree_kernel(TreeArgs a) {
 // ---------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------
-static const size_t SMEM_WS_LIMIT = 96 * 1024;
+static const size_t SMEM_WS_LIMIT = 200 * 1024;     // fronts up to nj = 79 stay in shared memory (227 KB per CTA on sm_100)
 
 static size_t ws_doubles(const smcp_sym *s) {
     size_t nj = (size_t)s->max_nj;

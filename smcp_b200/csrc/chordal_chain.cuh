@@ -39,6 +39,7 @@ struct ChainArgs {
     const double *F;           // add kernel: B x nsq local fronts
     long long nsq;
     int root_off, root_nj, root_sq;
+    const double *Yaa;         // up-final: fused Hessian scaling (Y_aa per node, W x W)
     double *psi;               // two-level scan: G x D x (D+1) group propagators
     int G, gs;                 // groups of gs consecutive boundaries
 };
@@ -46,6 +47,8 @@ struct ChainArgs {
 enum { CH_PROBE = 0, CH_FINAL = 1, CH_BASIS = 2 };
 
 #define TRI(p, q) ((p) * ((p) + 1) / 2 + (q))
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // PF = how many nodes ahead the block / factor entries are fetched: 1 for large batches (occupancy
 // hides the latency, registers matter), 4 for a single matrix (nothing else hides it).
@@ -92,6 +95,13 @@ __global__ void __launch_bounds__(128) chain_up_kernel(ChainArgs a) {
                     for (int i = 0; i < NJ; ++i) xb[t][i] = (MODE != CH_BASIS) ? x[(long long)(k + PF) * NJ + i] : 0.0;
 #pragma unroll
                     for (int i = 0; i < W; ++i) lb[t][i] = l[(long long)(k + PF) * NJ + 1 + i];
+                    if (MODE == CH_FINAL && PF > 1 && a.Yaa) {      // single matrix: nothing else hides the Y_aa loads
+                        const double *yn = a.Yaa + (long long)(k + PF) * W * W;
+                        prefetch_l1(yn);
+                        if (W * W > 16) prefetch_l1(yn + 16);
+                        if (W * W > 32) prefetch_l1(yn + 32);
+                        if (W * W > 48) prefetch_l1(yn + W * W - 1);
+                    }
                 }
                 const double f0 = xv[0] + u[0][0];
                 double fa[W], ka[W];
@@ -110,9 +120,28 @@ __global__ void __launch_bounds__(128) chain_up_kernel(ChainArgs a) {
                     }
                 if (MODE == CH_FINAL) {
                     double *o = x + (long long)k * NJ;
-                    o[0] = f0;
+                    if (a.Yaa) {
+                        // fused scaling (App. A.4 step 2, single-column supernode):
+                        // M_nn = K_nn / l^4, M_an = Y_aa (K_an / l^2)
+                        const double l0 = l[(long long)k * NJ];
+                        const double *yp = a.Yaa + (long long)k * W * W;
+                        const double inv = 1.0 / (l0 * l0);
+                        double kv[W];
 #pragma unroll
-                    for (int i = 0; i < W; ++i) o[1 + i] = ka[i];
+                        for (int i = 0; i < W; ++i) kv[i] = ka[i] * inv;
+                        o[0] = f0 * inv * inv;
+#pragma unroll
+                        for (int r = 0; r < W; ++r) {
+                            double acc = 0.0;
+#pragma unroll
+                            for (int c = 0; c < W; ++c) acc = fma(yp[r + c * W], kv[c], acc);
+                            o[1 + r] = acc;
+                        }
+                    } else {
+                        o[0] = f0;
+#pragma unroll
+                        for (int i = 0; i < W; ++i) o[1 + i] = ka[i];
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < W; ++i)
@@ -562,8 +591,6 @@ __global__ void __launch_bounds__(64) chain_chol_kernel(ChainArgs a, int *fail) 
 // The Newton solves of an iteration apply the Hessian ~20 times to ONE matrix each (solvers.py:
 // 506-539 plus iterative refinement), so this latency is what an IPM iteration waits for.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
 #define CH1_THREADS 256
 #define CH1_MAXP (CH1_THREADS - 32)
 
@@ -836,6 +863,69 @@ __global__ void __launch_bounds__(CH1_THREADS) chain_hessian1_kernel(ChainArgs a
     }
 }
 
+// completion on a chain (chompack.completion, solvers.py:625, 874; App. A.3): every node is
+// independent — one THREAD per (matrix, node) with the W x W separator block in registers:
+// R = chol(X_aa), w = X_aa^{-1} X_an, delta = X_nn - X_an^T w, L_nn = delta^{-1/2}, L_an = -w L_nn.
+// Same operation order as the warp version (op_compl), which still handles the root supernode.
+template <int W>
+__global__ void __launch_bounds__(128) chain_compl_kernel(ChainArgs a, const double *__restrict__ Xin, const int *__restrict__ aaidx, int *fail) {
+    const long long total = (long long)a.N * a.B;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(idx / a.N), k = (int)(idx - (long long)b * a.N);
+        const double *xi = Xin + (long long)b * a.nblk;
+        const int *ai = aaidx + (long long)k * W * W;
+        double R[W][W], z[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) R[i][j] = xi[ai[i + j * W]];
+        const double *blk = xi + (long long)k * (W + 1);
+#pragma unroll
+        for (int i = 0; i < W; ++i) z[i] = blk[1 + i];
+        double dl = blk[0];
+        bool bad = false;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            const double d = R[j][j];
+            const bool bj = !(d > 0.0);
+            bad |= bj;
+            const double sq = bj ? 1.0 : sqrt(d);
+#pragma unroll
+            for (int i = j + 1; i < W; ++i) R[i][j] /= sq;
+            R[j][j] = sq;
+#pragma unroll
+            for (int c = j + 1; c < W; ++c)
+#pragma unroll
+                for (int i = c; i < W; ++i) R[i][c] = fma(-R[i][j], R[c][j], R[i][c]);
+        }
+#pragma unroll
+        for (int j = 0; j < W; ++j) {          // z <- R^{-1} z
+            z[j] /= R[j][j];
+#pragma unroll
+            for (int i = j + 1; i < W; ++i) z[i] = fma(-R[i][j], z[j], z[i]);
+        }
+        double ss = 0.0;
+#pragma unroll
+        for (int i = 0; i < W; ++i) ss = fma(z[i], z[i], ss);
+        dl = dl + (-1.0) * ss;
+#pragma unroll
+        for (int j = W - 1; j >= 0; --j) {     // z <- R^{-T} z
+            z[j] /= R[j][j];
+#pragma unroll
+            for (int i = 0; i < j; ++i) z[i] = fma(-R[j][i], z[j], z[i]);
+        }
+        const bool bd = !(dl > 0.0);
+        bad |= bd;
+        const double sq = bd ? 1.0 : sqrt(dl);
+        const double li = 1.0 / sq;
+        double *o = a.X + (long long)b * a.nblk + (long long)k * (W + 1);
+        o[0] = li;
+#pragma unroll
+        for (int i = 0; i < W; ++i) o[1 + i] = -fma(z[i], li, 0.0);
+        if (bad) fail[b] = 1;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
@@ -985,12 +1075,13 @@ static int chain_prepare(smcp_hess *h) {
 }
 
 // one linear sweep (probe, scan, final) on `batch` matrices
-static int chain_sweep(smcp_sym *s, bool up, double *X, const double *Lt, double *phi, double *psi, int64_t batch, const char *name) {
+static int chain_sweep(smcp_sym *s, bool up, double *X, const double *Lt, double *phi, double *psi, const double *Yaa, int64_t batch, const char *name) {
     smcp_ctx *ctx = s->ctx;
     ChainArgs a = {};
     if (chain_fill(s, a, X, Lt, batch)) return -1;
     a.phi = phi;
     a.psi = psi;
+    a.Yaa = Yaa;
     {
         LaunchScope ls(ctx, name, 3, (double)batch);
         chain_launch<CH_PROBE>(s->chW, up, a, ctx->stream);
@@ -1087,6 +1178,28 @@ static int chain_hessian1(smcp_hess *h, double *U) {
         }
     }
     if (rc) return rc;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int chain_completion(smcp_sym *s, double *X, const double *Xin, int64_t batch, const char *name) {
+    smcp_ctx *ctx = s->ctx;
+    ChainArgs a = {};
+    if (chain_fill(s, a, X, nullptr, batch)) return -1;
+    long long grid = ((long long)a.N * batch + 127) / 128;
+    if (grid > (long long)ctx->num_sms * 32) grid = (long long)ctx->num_sms * 32;
+    {
+        LaunchScope ls(ctx, name, 1, (double)batch);
+        switch (s->chW) {
+            case 1: chain_compl_kernel<1><<<(unsigned)grid, 128, 0, ctx->stream>>>(a, Xin, s->d.aaidx, s->fail); break;
+            case 2: chain_compl_kernel<2><<<(unsigned)grid, 128, 0, ctx->stream>>>(a, Xin, s->d.aaidx, s->fail); break;
+            case 3: chain_compl_kernel<3><<<(unsigned)grid, 128, 0, ctx->stream>>>(a, Xin, s->d.aaidx, s->fail); break;
+            case 4: chain_compl_kernel<4><<<(unsigned)grid, 128, 0, ctx->stream>>>(a, Xin, s->d.aaidx, s->fail); break;
+            case 5: chain_compl_kernel<5><<<(unsigned)grid, 128, 0, ctx->stream>>>(a, Xin, s->d.aaidx, s->fail); break;
+            case 6: chain_compl_kernel<6><<<(unsigned)grid, 128, 0, ctx->stream>>>(a, Xin, s->d.aaidx, s->fail); break;
+            default: chain_compl_kernel<7><<<(unsigned)grid, 128, 0, ctx->stream>>>(a, Xin, s->d.aaidx, s->fail); break;
+        }
+    }
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -1145,7 +1145,13 @@ int ks_completion(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
     SmallArgs a = {};
     a.t.X = x;
     a.t.Xin = s->tmp;
-    if (launch_flat<FL_COMPL>(s, a, batch, batch > 1 ? "completion_batch" : "completion")) return -1;
+    if (s->chain && batch >= 8) {
+        // chain nodes: one thread per (matrix, node); the root supernode keeps the warp kernel
+        if (chain_completion(s, x, s->tmp, batch, "completion_chain_batch")) return -1;
+        a.list = s->sm.wide_sn;
+        a.nlist = s->sm.nwide;
+        if (launch_flat<FL_COMPL>(s, a, batch, "completion_root_batch")) return -1;
+    } else if (launch_flat<FL_COMPL>(s, a, batch, batch > 1 ? "completion_batch" : "completion")) return -1;
     if (info_host) return fetch_fail(s, batch, info_host);
     return 0;
 }
@@ -1211,7 +1217,7 @@ int ks_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
         a.t.Yaa = h->Yaa;
         if (s->chain) {
             if (chain_prepare(h)) return -1;
-            if (chain_sweep(s, true, U, h->Lt, h->phi_up, h->psi_up, batch, big ? "hessian_up_chain_batch" : "hessian_up_chain")) return -1;
+            if (chain_sweep(s, true, U, h->Lt, h->phi_up, h->psi_up, h->Yaa, batch, big ? "hessian_up_chain_batch" : "hessian_up_chain")) return -1;
         } else if (launch_sweep(s, sweep_up_kernel<SW_HUP>, WS_HUP, a, s->up, batch, big ? "hessian_up_batch" : "hessian_up")) return -1;
         if (big || s->chain) {
             // one thread per (supernode, matrix) for the single-column supernodes, warps for the rest
@@ -1219,7 +1225,7 @@ int ks_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
             fill_common(s, a, s->flat, batch);
             long long items = (long long)s->d.nsn * batch;
             long long grid = std::min<long long>((items + 255) / 256, (long long)ctx->num_sms * 16);
-            {
+            if (!s->chain) {      // chain: fused into the final pass of the up sweep
                 LaunchScope ls(ctx, "hessian_scale_batch", 1, (double)batch);
                 hscale_nn1_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(a);
             }
@@ -1230,7 +1236,7 @@ int ks_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
             a.list = nullptr;
             a.nlist = 0;
         } else if (launch_flat<FL_HSCALE>(s, a, batch, "hessian_scale")) return -1;
-        if (s->chain) return chain_sweep(s, false, U, h->Lt, h->phi_dn, h->psi_dn, batch, big ? "hessian_down_chain_batch" : "hessian_down_chain");
+        if (s->chain) return chain_sweep(s, false, U, h->Lt, h->phi_dn, h->psi_dn, nullptr, batch, big ? "hessian_down_chain_batch" : "hessian_down_chain");
         return launch_sweep(s, sweep_down_kernel, WS_DOWN, a, s->down, batch, big ? "hessian_down_batch" : "hessian_down");
     }
     if (!h->have_Raa) {

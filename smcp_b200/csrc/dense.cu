@@ -5,7 +5,7 @@
 // FP64 has no tcgen05/UMMA kind on sm_100a; the FP64 tensor path is mma.sync.m8n8k4.f64
 // (SASS: DMMA.8x8x4).  The GEMM below stages K-major operand tiles in shared memory with a
 // 3-stage cp.async pipeline, pads the tile rows so the per-thread 8-byte fragment loads
-// are bank-conflict free, and keeps a 64x32 accumulator tile per warp in registers.
+// are bank-conflict free, and keeps a 32x32 accumulator tile per warp in registers (16 warps per CTA).
 #include "internal.cuh"
 #include <algorithm>
 
@@ -20,7 +20,7 @@
 #define BK 16
 #define LDK (BK + 4)       // 20 doubles: rows shifted by 4 banks -> conflict-free fragments
 #define STAGES 3
-#define GEMM_THREADS 256
+#define GEMM_THREADS 512       // 16 warps: 4 x 4 warp tiles of 32 x 32 (4 warps per scheduler keep the DMMA pipe fed)
 
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -70,13 +70,13 @@ gemm_dmma_kernel(const double *__restrict__ A, long long lda, const double *__re
     const long long j0 = (long long)blockIdx.y * BN;
     if (tri && (i0 + BM - 1 + tri_off < j0)) return;        // tile entirely above the diagonal
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = (warp & 1) * 64;       // 2 warps along M
-    const int wn = (warp >> 1) * 32;      // 4 warps along N
+    const int wm = (warp & 3) * 32;       // 4 warps along M
+    const int wn = (warp >> 2) * 32;      // 4 warps along N
     const int g = lane >> 2, t = lane & 3;
 
-    double acc[8][4][2];
+    double acc[4][4][2];
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
@@ -108,13 +108,13 @@ gemm_dmma_kernel(const double *__restrict__ A, long long lda, const double *__re
         const double *bs = Bs + (kt % STAGES) * 128 * LDK;
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 4) {
-            double af[8], bf[4];
+            double af[4], bf[4];
 #pragma unroll
-            for (int a = 0; a < 8; ++a) af[a] = as[(wm + a * 8 + g) * LDK + kk + t];
+            for (int a = 0; a < 4; ++a) af[a] = as[(wm + a * 8 + g) * LDK + kk + t];
 #pragma unroll
             for (int b = 0; b < 4; ++b) bf[b] = bs[(wn + b * 8 + g) * LDK + kk + t];
 #pragma unroll
-            for (int a = 0; a < 8; ++a)
+            for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
         }
@@ -122,7 +122,7 @@ gemm_dmma_kernel(const double *__restrict__ A, long long lda, const double *__re
     cp_async_wait<0>();
     // epilogue: C(i, j), i = i0 + wm + a*8 + g, j = j0 + wn + b*8 + 2t + {0,1}
 #pragma unroll
-    for (int a = 0; a < 8; ++a) {
+    for (int a = 0; a < 4; ++a) {
         long long i = i0 + wm + a * 8 + g;
         if (i >= M) continue;
 #pragma unroll

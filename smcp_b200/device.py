@@ -74,6 +74,7 @@ API = {
     "smcp_op_amap": (_int, [_vp, _dp, _i64, _f64p]),
     "smcp_op_aadj": (_int, [_vp, _f64p, _dp]),
     "smcp_kkt_assemble": (_int, [_vp, _vp, _i64, _i64]),
+    "smcp_kkt_assemble_cyclic": (_int, [_vp, _vp, _i64, _int, _int]),
     "smcp_kkt_factor": (_int, [_vp, _i32p]),
     "smcp_kkt_solve": (_int, [_vp, _f64p]),
     "smcp_kkt_get_H": (_int, [_vp, _f64p]),
@@ -438,8 +439,7 @@ class DeviceBackend:
             self.schur_assemble(tok)
         else:
             rank, nranks, block = self.comm
-            for c0, c1 in owned_column_blocks(self.m, rank, nranks, block):
-                self.schur_assemble(tok, c0, c1)
+            _ck(self.lib, self.lib.smcp_kkt_assemble_cyclic(self._op, tok, block, rank, nranks))
             _ck(self.lib, self.lib.smcp_kkt_allgather(self._op, block, rank, nranks))
         info = np.zeros(1, dtype=np.int32)
         _ck(self.lib, self.lib.smcp_kkt_factor(self._op, info))
