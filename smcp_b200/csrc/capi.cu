@@ -253,6 +253,8 @@ extern "C" int smcp_sym_create(smcp_ctx *ctx, const smcp_sym_desc *D, smcp_sym *
     for (int i = 0; i <= nsn; ++i) tp3[i] = i;
     for (int i = 0; i < nsn; ++i) ts3[i] = i;
     if (upload_sched(s, nsn, tp3, ts3, dp3, di3, &s->flat)) return -1;
+    s->h_root_boff = (long long)D->blkptr[nsn > 0 ? nsn - 1 : 0];
+    if (s->max_nj > 8 && root_setup(s, D)) return -1;
     // tiny cliques: warp-per-chain kernels (SMCP_B200_NO_SMALL=1 forces the CTA kernels)
     if (s->max_nj <= 8 && !getenv("SMCP_B200_NO_SMALL") && small_setup(s, D, tp, ts, tp2, ts2)) return -1;
 

@@ -53,6 +53,7 @@ __global__ void tree_kernel(TreeArgs a) {
         __syncthreads();
         __threadfence();
         for (int p = a.T.task_ptr[t]; p < a.T.task_ptr[t + 1]; ++p) {
+            if (a.T.task_sn[p] + 1 == a.skip_sn1) continue;      // dense root path (front.cu)
             Node q = node_of(a.S, a.T.task_sn[p]);
             if (OP == OP_CHOL) op_chol<false>(a, q, b);
             else if (OP == OP_LLT) op_llt<false>(a, q, b, ws);
@@ -152,6 +153,9 @@ int fetch_fail(smcp_sym *s, int64_t batch, int32_t *info_host) {
     return 0;
 }
 
+// single matrices (or a handful): the large root supernode goes to the dense kernels of front.cu
+static bool use_root(const smcp_sym *s, int64_t batch) { return s->big_root >= 0 && batch <= 4; }
+
 int k_cholesky(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
     if (s->small) return ks_cholesky(s, x, batch, info_host);
     if (sym_ensure(s, batch, false)) return -1;
@@ -159,7 +163,11 @@ int k_cholesky(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
     TreeArgs a = {};
     a.X = x;
     a.upd = s->upd;
+    if (use_root(s, batch)) a.skip_sn1 = s->big_root + 1;
     if (launch_tree<OP_CHOL>(s, a, s->up, batch, pick_threads(s), batch > 1 ? "cholesky_batch" : "cholesky")) return -1;
+    if (use_root(s, batch))
+        for (int64_t b = 0; b < batch; ++b)
+            if (root_cholesky(s, x, b)) return -1;
     if (info_host) return fetch_fail(s, batch, info_host);
     return 0;
 }
@@ -170,7 +178,12 @@ int k_llt(smcp_sym *s, double *x, int64_t batch) {
     TreeArgs a = {};
     a.X = x;
     a.upd = s->upd;
-    return launch_tree<OP_LLT>(s, a, s->up, batch, pick_threads(s), "llt");
+    if (use_root(s, batch)) a.skip_sn1 = s->big_root + 1;
+    if (launch_tree<OP_LLT>(s, a, s->up, batch, pick_threads(s), "llt")) return -1;
+    if (use_root(s, batch))
+        for (int64_t b = 0; b < batch; ++b)
+            if (root_llt(s, x, b)) return -1;
+    return 0;
 }
 
 int k_projinv(smcp_sym *s, double *x, int64_t batch) {
@@ -178,6 +191,11 @@ int k_projinv(smcp_sym *s, double *x, int64_t batch) {
     if (sym_ensure(s, batch, false)) return -1;
     TreeArgs a = {};
     a.X = x;
+    if (use_root(s, batch)) {
+        a.skip_sn1 = s->big_root + 1;
+        for (int64_t b = 0; b < batch; ++b)
+            if (root_projinv(s, x, b)) return -1;
+    }
     return launch_tree<OP_PROJINV>(s, a, s->down, batch, pick_threads(s), "projected_inverse");
 }
 
@@ -192,7 +210,11 @@ int k_completion(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
     TreeArgs a = {};
     a.X = x;
     a.Xin = s->tmp;
+    if (use_root(s, batch)) a.skip_sn1 = s->big_root + 1;
     if (launch_tree<OP_COMPL>(s, a, flat_sched(s), batch, pick_threads(s), batch > 1 ? "completion_batch" : "completion")) return -1;
+    if (use_root(s, batch))
+        for (int64_t b = 0; b < batch; ++b)
+            if (root_completion(s, x, s->tmp, b)) return -1;
     if (info_host) return fetch_fail(s, batch, info_host);
     return 0;
 }
@@ -231,16 +253,24 @@ int k_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
     a.Yaa = h->Yaa;
     a.Raa = h->Raa;
     int threads = pick_threads(s);
+    if (use_root(s, batch)) a.skip_sn1 = s->big_root + 1;
     if (!inv) {
         const bool big = batch >= 32;
         if (launch_tree<OP_HFWD_UP>(s, a, s->up, batch, threads, big ? "hessian_up_batch" : "hessian_up")) return -1;
+        if (use_root(s, batch))
+            for (int64_t b = 0; b < batch; ++b)
+                if (root_hess_up(s, h->Lt, U, b)) return -1;
         return launch_tree<OP_HFWD_DOWN>(s, a, s->down, batch, threads, big ? "hessian_down_batch" : "hessian_down");
     }
     if (!h->have_Raa) {
         if (k_hess_prep_inv(h)) return -1;
         h->have_Raa = true;
     }
-    return launch_tree<OP_HINV>(s, a, s->up, batch, threads, batch >= 32 ? "hessian_inv_batch" : "hessian_inv");
+    if (launch_tree<OP_HINV>(s, a, s->up, batch, threads, batch >= 32 ? "hessian_inv_batch" : "hessian_inv")) return -1;
+    if (use_root(s, batch))
+        for (int64_t b = 0; b < batch; ++b)
+            if (root_hess_inv(s, h->Lt, U, b)) return -1;
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -30,6 +30,7 @@ struct TreeArgs {
     double *cta_ws;
     long long ws_stride;
     int use_smem;
+    int skip_sn1;        // supernode (index + 1) left to the dense root path, 0 = none
 };
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {

@@ -10,9 +10,11 @@
 #include <algorithm>
 
 // ---------------------------------------------------------------------------------------
-// DMMA GEMM:  C(MxN) = beta*C + alpha * op(A)^T op(B)
-//   TN = true : A is K x M (column-major, K contiguous), B is K x N       (Schur assembly)
-//   TN = false: A is M x K (column-major, M contiguous), B is N x K       (SYRK-like update)
+// DMMA GEMM:  C(i, j) = [C(i, j) +] alpha * sum_k A'(i, k) B'(j, k)
+//   TA = true : A'(i, k) = A[k + i*lda] (K contiguous)     TA = false: A'(i, k) = A[i + k*lda]
+//   TB = true : B'(j, k) = B[k + j*ldb] (K contiguous)     TB = false: B'(j, k) = B[j + k*ldb]
+//   (true, true) = A^T B: Schur assembly; (false, false) = A B^T: SYRK-like updates;
+//   (false, true) = A B and (true, false) = A^T B^T: frontal updates of large supernodes
 // tri: only tiles that intersect {i + tri_off >= j} are computed (lower triangle).
 // ---------------------------------------------------------------------------------------
 #define BM 128
@@ -58,7 +60,7 @@ __device__ __forceinline__ void load_tile(double *sm, const double *G, long long
     }
 }
 
-template <bool TN>
+template <bool TA, bool TB>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_dmma_kernel(const double *__restrict__ A, long long lda, const double *__restrict__ B, long long ldb,
                  double *__restrict__ C, long long ldc, long long M, long long N, long long K, double alpha,
@@ -87,8 +89,8 @@ gemm_dmma_kernel(const double *__restrict__ A, long long lda, const double *__re
     const long long nk = (kend - kbeg + BK - 1) / BK;
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < nk) {
-            load_tile<TN>(As + s * 128 * LDK, A, lda, i0, M, kbeg + (long long)s * BK, kend, tid);
-            load_tile<TN>(Bs + s * 128 * LDK, B, ldb, j0, N, kbeg + (long long)s * BK, kend, tid);
+            load_tile<TA>(As + s * 128 * LDK, A, lda, i0, M, kbeg + (long long)s * BK, kend, tid);
+            load_tile<TB>(Bs + s * 128 * LDK, B, ldb, j0, N, kbeg + (long long)s * BK, kend, tid);
         }
         cp_async_commit();
     }
@@ -99,8 +101,8 @@ gemm_dmma_kernel(const double *__restrict__ A, long long lda, const double *__re
             long long nx = kt + STAGES - 1;
             if (nx < nk) {
                 int s = (int)(nx % STAGES);
-                load_tile<TN>(As + s * 128 * LDK, A, lda, i0, M, kbeg + nx * BK, kend, tid);
-                load_tile<TN>(Bs + s * 128 * LDK, B, ldb, j0, N, kbeg + nx * BK, kend, tid);
+                load_tile<TA>(As + s * 128 * LDK, A, lda, i0, M, kbeg + nx * BK, kend, tid);
+                load_tile<TB>(Bs + s * 128 * LDK, B, ldb, j0, N, kbeg + nx * BK, kend, tid);
             }
             cp_async_commit();
         }
@@ -153,7 +155,7 @@ __global__ void splitk_reduce_kernel(const double *__restrict__ P, long long spl
     }
 }
 
-static int launch_gemm(smcp_ctx *ctx, bool tn, const double *A, int64_t lda, const double *B, int64_t ldb,
+int launch_gemm(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, const double *B, int64_t ldb,
                        double *C, int64_t ldc, int64_t M, int64_t N, int64_t K, double alpha, int accumulate,
                        int tri, int64_t tri_off, const char *name) {
     if (M <= 0 || N <= 0) return 0;
@@ -185,8 +187,10 @@ static int launch_gemm(smcp_ctx *ctx, bool tn, const double *A, int64_t lda, con
     size_t smem = (size_t)2 * STAGES * 128 * LDK * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     // algorithmic flops: 2*K per computed entry of the (lower-triangular) result
@@ -200,10 +204,12 @@ static int launch_gemm(smcp_ctx *ctx, bool tn, const double *A, int64_t lda, con
         }
     {
         LaunchScope ls(ctx, name, 1, 2.0 * (double)K * pairs);
-        if (tn)
-            gemm_dmma_kernel<true><<<grid, GEMM_THREADS, smem, ctx->stream>>>(A, lda, B, ldb, Cout, ldout, M, N, K, alpha, accumulate, tri, tri_off, kchunk, split_stride);
-        else
-            gemm_dmma_kernel<false><<<grid, GEMM_THREADS, smem, ctx->stream>>>(A, lda, B, ldb, Cout, ldout, M, N, K, alpha, accumulate, tri, tri_off, kchunk, split_stride);
+#define GEMM_LAUNCH(TA_, TB_) gemm_dmma_kernel<TA_, TB_><<<grid, GEMM_THREADS, smem, ctx->stream>>>(A, lda, B, ldb, Cout, ldout, M, N, K, alpha, accumulate, tri, tri_off, kchunk, split_stride)
+        if (ta && tb) GEMM_LAUNCH(true, true);
+        else if (!ta && !tb) GEMM_LAUNCH(false, false);
+        else if (ta) GEMM_LAUNCH(true, false);
+        else GEMM_LAUNCH(false, true);
+#undef GEMM_LAUNCH
         if (splits > 1) {
             ctx->launches += 1;
             long long g = (M * N + 255) / 256;
@@ -218,7 +224,7 @@ static int launch_gemm(smcp_ctx *ctx, bool tn, const double *A, int64_t lda, con
 // C(i, j) = sum_k A(k, i) B(k, j) for i + row_lo_of_col0 >= j  (lower part of a column block of H)
 int d_gemm_tn(smcp_ctx *ctx, const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
               int64_t ldc, int64_t M, int64_t N, int64_t K, int64_t row_lo_of_col0) {
-    return launch_gemm(ctx, true, A, lda, B, ldb, C, ldc, M, N, K, 1.0, 0, 1, row_lo_of_col0, "schur_gemm_dmma");
+    return launch_gemm(ctx, true, true, A, lda, B, ldb, C, ldc, M, N, K, 1.0, 0, 1, row_lo_of_col0, "schur_gemm_dmma");
 }
 
 // ---------------------------------------------------------------------------------------
@@ -370,7 +376,7 @@ int d_potrf(smcp_ctx *ctx, double *H, int64_t m, int32_t *info_dev, double *Dinv
         if (rem > 0) {
             const double *P = H + (k0 + kb) + k0 * m;
             double *Ct = H + (k0 + kb) + (k0 + kb) * m;
-            if (launch_gemm(ctx, false, P, m, P, m, Ct, m, rem, rem, kb, -1.0, 1, 1, 0, "potrf_syrk_dmma")) return -1;
+            if (launch_gemm(ctx, false, false, P, m, P, m, Ct, m, rem, rem, kb, -1.0, 1, 1, 0, "potrf_syrk_dmma")) return -1;
         }
     }
     (void)Dinv;

@@ -121,6 +121,12 @@ struct smcp_sym {
     int chW = 0, chN = 0, chP = 0, ch_root_off = 0, ch_root_nj = 0;
     double *ch_state = nullptr;      // batch x P x D boundary states
     size_t ch_state_cap = 0;
+    // large root supernode processed by dense multi-CTA kernels for single matrices (front.cu)
+    int big_root = -1, root_nn = 0, root_nch = 0;
+    const int *root_ch = nullptr, *root_inv = nullptr;
+    double *root_ws = nullptr;       // 3 x nn x nn
+    int *root_info = nullptr;
+    long long h_root_boff = 0;
     // host copies used by the operator setup
     std::vector<int> h_vec2blk;
     std::vector<int64_t> h_snptr;
@@ -169,9 +175,22 @@ int k_scatter_vec(smcp_sym *s, double *dst, const double *dev_vec);
 int k_gather_vec(smcp_sym *s, const double *src, double *dev_vec);
 int k_axpy_batch(smcp_sym *s, const double *x, const double *dx, const double *gam_dev, double *out, int64_t count);
 
+// dense root supernode (front.cu)
+int root_setup(smcp_sym *s, const smcp_sym_desc *D);
+int root_cholesky(smcp_sym *s, double *X, int64_t b);
+int root_llt(smcp_sym *s, double *X, int64_t b);
+int root_hess_up(smcp_sym *s, const double *Lt, double *X, int64_t b);
+int root_hess_inv(smcp_sym *s, const double *Lt, double *X, int64_t b);
+int root_projinv(smcp_sym *s, double *X, int64_t b);
+int root_completion(smcp_sym *s, double *X, const double *Xin, int64_t b);
+int d_trsm_left_lower(smcp_ctx *ctx, bool trans, const double *L, int64_t ldl, int64_t n, double *B, int64_t ldb, int64_t nrhs);
+
 // dense kernels (dense.cu)
 int d_potrf(smcp_ctx *ctx, double *H, int64_t m, int32_t *info_dev, double *Dinv);
 int d_potrs(smcp_ctx *ctx, const double *H, int64_t m, const double *Dinv, double *y_dev);
+int launch_gemm(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
+                int64_t ldc, int64_t M, int64_t N, int64_t K, double alpha, int accumulate, int tri, int64_t tri_off,
+                const char *name);
 // C(lower blocks, rows i0.. ) = A^T * B : A is K x M (col-major, ld K), B is K x N
 int d_gemm_tn(smcp_ctx *ctx, const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
               int64_t ldc, int64_t M, int64_t N, int64_t K, int64_t row_lo_of_col0);

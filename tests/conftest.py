@@ -111,4 +111,5 @@ PATTERNS = [
     (250, 0, -6, 11),    # random tree, cliques of 7
     (120, -3, 6, 12),    # clique chain: 3-column supernodes with 3-row separators
     (100, -2, 8, 13),    # clique chain: 2-column supernodes with 6-row separators
+    (180, 2500, 1, 14),  # heavy fill: a dense root supernode of ~170 columns (dense root path, front.cu)
 ]
