@@ -166,6 +166,19 @@ int smcp_comm_destroy(smcp_ctx *ctx);
 /* all-gather the block-cyclic column blocks of H assembled by each rank */
 int smcp_kkt_allgather(smcp_op *op, int64_t block, int rank, int nranks);
 
+/* ---- host-side symbolic analysis in native code (no CUDA) ---------
+ * Native twins of smcp_b200/symbolic.py with identical tie-breaking (bit-identical results).
+ * Patterns are lower-triangular CCS, int64 indices. */
+/* cvxopt.amd.order stand-in (solvers.py:192-198, 278-279): exact minimum degree, ties by index */
+int smcp_host_min_degree(int64_t n, const int64_t *colptr, const int64_t *rowind, int64_t *perm);
+/* chompack.maxcardsearch (solvers.py:301, 1542): reverse maximum-cardinality-search order */
+int smcp_host_maxcardsearch(int64_t n, const int64_t *colptr, const int64_t *rowind, int64_t *order);
+/* embedding step of chompack.symbolic (solvers.py:305-308) for a pattern already in elimination
+ * order: call with frowind = NULL to get fcolptr (sizes), then again to fill frowind; parent
+ * (elimination tree) may be NULL */
+int smcp_host_embed(int64_t n, const int64_t *colptr, const int64_t *rowind, int64_t *fcolptr,
+                    int64_t *frowind, int64_t *parent);
+
 #ifdef __cplusplus
 }
 #endif

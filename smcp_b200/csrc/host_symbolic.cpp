@@ -1,0 +1,199 @@
+// Host-side symbolic analysis in native code: the once-per-solve step
+// immediately before the GPU hot path (reference call sites src/python/solvers.py:278-319,
+// 1542-1560: cvxopt.amd.order / chompack.maxcardsearch / chompack.symbolic — not vendored).
+//
+// These are the native twins of smcp_b200/symbolic.py (min_degree, maxcardsearch, embed): the
+// SAME tie-breaking rules, so both produce bit-identical orderings and filled patterns (tested
+// in tests/test_host_symbolic.py).  The Python versions stay as the readable specification; the
+// drivers call the native ones (n = 20 000 max-cut: minimum degree 553 s in Python).
+//
+// Input everywhere: lower-triangular CCS pattern (colptr[n+1], rowind[nnz]) with int64 indices
+// like CVXOPT's int_t (src/C/cvxopt.h:46).  No CUDA in this file.
+#include "../../include/smcp_b200.h"
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <queue>
+#include <utility>
+#include <vector>
+
+namespace {
+
+// symmetric adjacency without the diagonal, neighbours sorted increasingly
+void build_adjacency(int64_t n, const int64_t *colptr, const int64_t *rowind, std::vector<int64_t> &ptr,
+                     std::vector<int32_t> &idx) {
+    ptr.assign(n + 1, 0);
+    for (int64_t j = 0; j < n; ++j)
+        for (int64_t q = colptr[j]; q < colptr[j + 1]; ++q) {
+            const int64_t i = rowind[q];
+            if (i == j) continue;
+            ++ptr[i + 1];
+            ++ptr[j + 1];
+        }
+    for (int64_t v = 0; v < n; ++v) ptr[v + 1] += ptr[v];
+    idx.resize((size_t)ptr[n]);
+    std::vector<int64_t> fill(ptr.begin(), ptr.end() - 1);
+    for (int64_t j = 0; j < n; ++j)
+        for (int64_t q = colptr[j]; q < colptr[j + 1]; ++q) {
+            const int64_t i = rowind[q];
+            if (i == j) continue;
+            idx[(size_t)fill[i]++] = (int32_t)j;
+            idx[(size_t)fill[j]++] = (int32_t)i;
+        }
+    for (int64_t v = 0; v < n; ++v) {
+        std::sort(idx.begin() + ptr[v], idx.begin() + ptr[v + 1]);
+        // duplicates cannot occur for a valid CCS pattern, but be safe
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// Exact minimum (external) degree on the elimination graph, ties by smallest vertex index:
+// at every step the not-yet-eliminated vertex with the smallest (degree, index) goes next and its
+// neighbourhood becomes a clique.  (smcp_b200/symbolic.py:min_degree; stand-in for
+// cvxopt.amd.order, solvers.py:192-198, 278-279.)
+int smcp_host_min_degree(int64_t n, const int64_t *colptr, const int64_t *rowind, int64_t *perm) {
+    if (n < 0 || !colptr || !perm) return -1;
+    if (n > INT32_MAX) return -1;
+    std::vector<int64_t> ptr;
+    std::vector<int32_t> idx;
+    build_adjacency(n, colptr, rowind, ptr, idx);
+    std::vector<std::vector<int32_t>> adj((size_t)n);
+    for (int64_t v = 0; v < n; ++v) adj[(size_t)v].assign(idx.begin() + ptr[v], idx.begin() + ptr[v + 1]);
+    idx.clear();
+    idx.shrink_to_fit();
+    std::vector<int32_t> deg((size_t)n);
+    std::vector<char> done((size_t)n, 0);
+    typedef std::pair<int32_t, int32_t> Key;      // (degree, vertex)
+    std::priority_queue<Key, std::vector<Key>, std::greater<Key>> heap;
+    for (int64_t v = 0; v < n; ++v) {
+        deg[(size_t)v] = (int32_t)adj[(size_t)v].size();
+        heap.push(Key(deg[(size_t)v], (int32_t)v));
+    }
+    std::vector<int32_t> merged;
+    int64_t k = 0, remaining = n;
+    while (!heap.empty()) {
+        const Key top = heap.top();
+        heap.pop();
+        const int32_t v = top.second;
+        if (done[(size_t)v] || top.first != deg[(size_t)v]) continue;
+        if ((int64_t)top.first == remaining - 1) {
+            // the rest of the graph is one clique: every remaining vertex keeps the same degree
+            // after each elimination, so the order is by index from here on
+            for (int64_t u = 0; u < n; ++u)
+                if (!done[(size_t)u]) perm[k++] = u;
+            break;
+        }
+        done[(size_t)v] = 1;
+        perm[k++] = v;
+        --remaining;
+        std::vector<int32_t> nb;
+        nb.swap(adj[(size_t)v]);
+        for (size_t a = 0; a < nb.size(); ++a) {
+            const int32_t u = nb[a];
+            std::vector<int32_t> &au = adj[(size_t)u];
+            // au <- (au ∪ nb) \ {u, v}
+            merged.clear();
+            merged.reserve(au.size() + nb.size());
+            size_t i = 0, j = 0;
+            while (i < au.size() || j < nb.size()) {
+                int32_t w;
+                if (j >= nb.size() || (i < au.size() && au[i] < nb[j])) w = au[i++];
+                else if (i >= au.size() || nb[j] < au[i]) w = nb[j++];
+                else { w = au[i]; ++i; ++j; }
+                if (w != u && w != v) merged.push_back(w);
+            }
+            au.assign(merged.begin(), merged.end());
+        }
+        for (size_t a = 0; a < nb.size(); ++a) {
+            const int32_t u = nb[a];
+            deg[(size_t)u] = (int32_t)adj[(size_t)u].size();
+            heap.push(Key(deg[(size_t)u], u));
+        }
+    }
+    return k == n ? 0 : -2;
+}
+
+// Maximum cardinality search; returns the REVERSE visiting order (a perfect elimination ordering
+// iff the pattern is chordal).  Ties towards the largest vertex index.
+// (smcp_b200/symbolic.py:maxcardsearch; chompack.maxcardsearch, solvers.py:301, 1542.)
+int smcp_host_maxcardsearch(int64_t n, const int64_t *colptr, const int64_t *rowind, int64_t *order) {
+    if (n < 0 || !colptr || !order) return -1;
+    if (n > INT32_MAX) return -1;
+    std::vector<int64_t> ptr;
+    std::vector<int32_t> idx;
+    build_adjacency(n, colptr, rowind, ptr, idx);
+    std::vector<int32_t> weight((size_t)n, 0);
+    std::vector<char> visited((size_t)n, 0);
+    typedef std::pair<int32_t, int32_t> Key;      // (weight, vertex): max-heap on both
+    std::priority_queue<Key> heap;
+    for (int64_t v = 0; v < n; ++v) heap.push(Key(0, (int32_t)v));
+    int64_t k = n - 1;
+    while (!heap.empty()) {
+        const Key top = heap.top();
+        heap.pop();
+        const int32_t v = top.second;
+        if (visited[(size_t)v] || top.first != weight[(size_t)v]) continue;
+        visited[(size_t)v] = 1;
+        order[k--] = v;
+        for (int64_t q = ptr[v]; q < ptr[v + 1]; ++q) {
+            const int32_t u = idx[(size_t)q];
+            if (!visited[(size_t)u]) {
+                ++weight[(size_t)u];
+                heap.push(Key(weight[(size_t)u], u));
+            }
+        }
+    }
+    return 0;
+}
+
+// Symbolic Cholesky of a lower-triangular pattern that is ALREADY in elimination order:
+// elimination tree and column structures of the filled (chordal) pattern.  Two calls:
+// frowind == NULL returns the column counts in fcolptr (so the caller can allocate), the second
+// call fills frowind (sorted rows, diagonal first).  parent may be NULL.
+// (smcp_b200/symbolic.py:embed; the embedding step of chompack.symbolic, solvers.py:305-308.)
+int smcp_host_embed(int64_t n, const int64_t *colptr, const int64_t *rowind, int64_t *fcolptr, int64_t *frowind,
+                    int64_t *parent) {
+    if (n < 0 || !colptr || !fcolptr) return -1;
+    // struct(j) = rows > j of column j  ∪  ⋃_{children c} struct(c) \ {j}; children's structures
+    // are released as soon as they are merged into the parent when only counting.
+    std::vector<std::vector<int64_t>> st((size_t)n);
+    std::vector<std::vector<int64_t>> children((size_t)n);
+    std::vector<int64_t> mark((size_t)n, -1);
+    fcolptr[0] = 0;
+    for (int64_t j = 0; j < n; ++j) {
+        std::vector<int64_t> &s = st[(size_t)j];
+        mark[(size_t)j] = j;
+        for (int64_t q = colptr[j]; q < colptr[j + 1]; ++q) {
+            const int64_t i = rowind[q];
+            if (i > j && mark[(size_t)i] != j) { mark[(size_t)i] = j; s.push_back(i); }
+        }
+        for (size_t c = 0; c < children[(size_t)j].size(); ++c) {
+            std::vector<int64_t> &sc = st[(size_t)children[(size_t)j][c]];
+            for (size_t a = 0; a < sc.size(); ++a) {
+                const int64_t i = sc[a];
+                if (i > j && mark[(size_t)i] != j) { mark[(size_t)i] = j; s.push_back(i); }
+            }
+            if (!frowind) std::vector<int64_t>().swap(sc);
+        }
+        std::sort(s.begin(), s.end());
+        if (!s.empty()) {
+            if (parent) parent[j] = s[0];
+            children[(size_t)s[0]].push_back(j);
+        } else if (parent) parent[j] = -1;
+        fcolptr[j + 1] = fcolptr[j] + 1 + (int64_t)s.size();
+        if (frowind) {
+            int64_t *out = frowind + fcolptr[j];
+            out[0] = j;
+            std::copy(s.begin(), s.end(), out + 1);
+            // children of j are final; free them
+            for (size_t c = 0; c < children[(size_t)j].size(); ++c) std::vector<int64_t>().swap(st[(size_t)children[(size_t)j][c]]);
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"

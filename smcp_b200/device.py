@@ -84,6 +84,9 @@ API = {
     "smcp_comm_init": (_int, [_vp, _int, _int, C.c_char_p]),
     "smcp_comm_destroy": (_int, [_vp]),
     "smcp_kkt_allgather": (_int, [_vp, _i64, _int, _int]),
+    "smcp_host_min_degree": (_int, [_i64, _i64p, _i64p, _i64p]),
+    "smcp_host_maxcardsearch": (_int, [_i64, _i64p, _i64p, _i64p]),
+    "smcp_host_embed": (_int, [_i64, _i64p, _i64p, _i64p, C.c_void_p, C.c_void_p]),
 }
 
 

@@ -68,7 +68,7 @@ def _adjacency(n, colptr, rowind):
     return ptr, b
 
 
-def maxcardsearch(n, colptr, rowind):
+def _py_maxcardsearch(n, colptr, rowind):
     """Maximum cardinality search on a lower-triangular pattern.
 
     Returns an ordering ``p`` (``p[k]`` = vertex eliminated k-th) that is a perfect
@@ -109,7 +109,7 @@ def _perm_lower(n, colptr, rowind, p):
     return lower_pattern(n, ip[rows], ip[cols])
 
 
-def embed(n, colptr, rowind, p=None):
+def _py_embed(n, colptr, rowind, p=None):
     """Symbolic Cholesky of the pattern under ordering ``p``.
 
     Returns ``(fcolptr, frowind, parent)``: the filled (chordal) lower pattern in the
@@ -153,7 +153,8 @@ def peo(n, colptr, rowind, p):
     return int(fc[-1]) == int(pc[-1])
 
 
-def min_degree(n, colptr, rowind):
+
+def _py_min_degree(n, colptr, rowind):
     """Minimum (external) degree ordering on the elimination graph with lazy heap updates.
 
     Stand-in for ``cvxopt.amd.order`` (``solvers.py:192-198, 278-279``).  Exact-degree
@@ -185,6 +186,63 @@ def min_degree(n, colptr, rowind):
             heapq.heappush(heap, (deg[u], u))
         adj[v] = set()
     return np.asarray(order, dtype=np.int64)
+
+
+# --------------------------------------------------------------------------------------
+# native twins (smcp_b200/csrc/host_symbolic.cpp): same tie-breaking, bit-identical results.
+# The Python functions above are the specification; the drivers go through these dispatchers.
+# --------------------------------------------------------------------------------------
+def _native():
+    """The shared library if it is built (host symbolic code needs no GPU), else None."""
+    try:
+        from . import device
+        return device.load_library()
+    except (RuntimeError, OSError, AttributeError):
+        return None
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def min_degree(n, colptr, rowind):
+    """Minimum-degree ordering (native ``smcp_host_min_degree``; see ``_py_min_degree``)."""
+    lib = _native()
+    if lib is None:
+        return _py_min_degree(n, colptr, rowind)
+    perm = np.empty(n, dtype=np.int64)
+    if lib.smcp_host_min_degree(int(n), _i64(colptr), _i64(rowind), perm) != 0:
+        raise RuntimeError("smcp_host_min_degree failed")
+    return perm
+
+
+def maxcardsearch(n, colptr, rowind):
+    """Reverse MCS order (native ``smcp_host_maxcardsearch``; see ``_py_maxcardsearch``)."""
+    lib = _native()
+    if lib is None:
+        return _py_maxcardsearch(n, colptr, rowind)
+    order = np.empty(n, dtype=np.int64)
+    if lib.smcp_host_maxcardsearch(int(n), _i64(colptr), _i64(rowind), order) != 0:
+        raise RuntimeError("smcp_host_maxcardsearch failed")
+    return order
+
+
+def embed(n, colptr, rowind, p=None):
+    """Chordal embedding under ordering ``p`` (native ``smcp_host_embed``; see ``_py_embed``)."""
+    lib = _native()
+    if lib is None:
+        return _py_embed(n, colptr, rowind, p)
+    if p is not None:
+        colptr, rowind = _perm_lower(n, colptr, rowind, p)
+    colptr, rowind = _i64(colptr), _i64(rowind)
+    fcolptr = np.empty(n + 1, dtype=np.int64)
+    parent = np.empty(n, dtype=np.int64)
+    if lib.smcp_host_embed(int(n), colptr, rowind, fcolptr, None, None) != 0:
+        raise RuntimeError("smcp_host_embed failed")
+    frowind = np.empty(int(fcolptr[-1]), dtype=np.int64)
+    if lib.smcp_host_embed(int(n), colptr, rowind, fcolptr, frowind.ctypes.data, parent.ctypes.data) != 0:
+        raise RuntimeError("smcp_host_embed failed")
+    return fcolptr, frowind, parent
 
 
 # --------------------------------------------------------------------------------------
