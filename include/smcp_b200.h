@@ -163,6 +163,10 @@ int smcp_kkt_H_devptr(smcp_op *op, double **dev_out);
 int smcp_comm_unique_id(char *id_out_128);
 int smcp_comm_init(smcp_ctx *ctx, int rank, int nranks, const char *id_128);
 int smcp_comm_destroy(smcp_ctx *ctx);
+/* distributed lapack.potrf (solvers.py:501, 1931) on the block-cyclic column blocks of 128 columns
+ * assembled by smcp_kkt_assemble_cyclic(block = 128): owners factor and ncclBroadcast their panels,
+ * every rank updates its own column tiles; on return every rank holds the complete factor */
+int smcp_kkt_factor_dist(smcp_op *op, int rank, int nranks, int32_t *info_host);
 /* all-gather the block-cyclic column blocks of H assembled by each rank */
 int smcp_kkt_allgather(smcp_op *op, int64_t block, int rank, int nranks);
 

@@ -31,7 +31,8 @@ idt = torch.zeros(128, dtype=torch.uint8)
 if rank == 0:
     idt = torch.frombuffer(bytearray(device.comm_unique_id()), dtype=torch.uint8).clone()
 dist.broadcast(idt, src=0)
-device.init_comm(rank, world, bytes(idt.numpy().tobytes()), block=64, device=local)
+BLOCK = int(os.environ.get("SMCP_BLOCK", "128"))
+device.init_comm(rank, world, bytes(idt.numpy().tobytes()), block=BLOCK, device=local)
 
 solvers.options["show_progress"] = False
 n, m, bw = (int(a) for a in (sys.argv[1:4] if len(sys.argv) > 3 else (600, 300, 5)))
@@ -50,9 +51,20 @@ tok = ops.hessian_factor(L, Y)
 # (a) full assembly on this rank alone
 ops.schur_assemble(tok)
 Hfull = np.tril(ops.get_H())
-# (b) sharded assembly + exchange + factorisation (what the drivers call)
+# single-rank factor of the full H (reference for the distributed factorisation)
+info = np.zeros(1, dtype=np.int32)
+device._ck(ops.lib, ops.lib.smcp_kkt_factor(ops._op, info))
+Lsingle = np.tril(ops.get_H())
+# (b) sharded assembly + block-cyclic Cholesky with NCCL panel broadcasts (what the drivers call)
 ops.lib.smcp_kkt_set_H(ops._op, np.zeros(m * m))
+ops.ctx.sync()
+import time
+t0 = time.perf_counter()
 ops.schur_factor(tok)
+ops.ctx.sync()
+t_dist = time.perf_counter() - t0
+Ldist = np.tril(ops.get_H())
+err_L = float(np.abs(Ldist - Lsingle).max())
 rhs = rng.standard_normal(m)
 z = ops.schur_solve(rhs)
 import scipy.linalg as sl
@@ -61,8 +73,8 @@ zref = sl.cho_solve(sl.cho_factor(Hs, lower=True), rhs)
 err_solve = np.linalg.norm(z - zref) / np.linalg.norm(zref)
 # exchange check: re-assemble sharded without factoring
 ops.lib.smcp_kkt_set_H(ops._op, np.zeros(m * m))
-device._ck(ops.lib, ops.lib.smcp_kkt_assemble_cyclic(ops._op, tok, 64, rank, world))
-device._ck(ops.lib, ops.lib.smcp_kkt_allgather(ops._op, 64, rank, world))
+device._ck(ops.lib, ops.lib.smcp_kkt_assemble_cyclic(ops._op, tok, BLOCK, rank, world))
+device._ck(ops.lib, ops.lib.smcp_kkt_allgather(ops._op, BLOCK, rank, world))
 Hsh = np.tril(ops.get_H())
 err_H = np.linalg.norm(Hsh - Hfull) / np.linalg.norm(Hfull)
 zt = torch.from_numpy(z.copy())
@@ -74,10 +86,10 @@ sol = P.solve_feas(kktsolver="chol", primalstart={"x": P._X0})
 v = torch.tensor([sol["primal objective"], float(sol["iterations"])], dtype=torch.float64)
 v0 = v.clone()
 dist.broadcast(v0, src=0)
-print("rank %d/%d: |H_sharded - H_full|/|H| = %.2e, solve err vs scipy = %.2e, |z - z_rank0|max = %.2e, "
-      "driver pobj %.12e iters %d (rank0: %.12e %d)" % (rank, world, err_H, err_solve, same, v[0], int(v[1]), v0[0], int(v0[1])),
-      flush=True)
-assert err_H < 1e-12 and err_solve < 1e-8 and same == 0.0 and torch.equal(v, v0)
+print("rank %d/%d: |H_sharded - H_full|/|H| = %.2e, |L_dist - L_single|max = %.2e (assemble+factor %.2f ms), "
+      "solve err vs scipy = %.2e, |z - z_rank0|max = %.2e, driver pobj %.12e iters %d (rank0: %.12e %d)"
+      % (rank, world, err_H, err_L, 1e3 * t_dist, err_solve, same, v[0], int(v[1]), v0[0], int(v0[1])), flush=True)
+assert err_H < 1e-12 and err_L == 0.0 and err_solve < 1e-8 and same == 0.0 and torch.equal(v, v0)
 dist.barrier()
 if rank == 0:
     print("MULTI_GPU_CHECK OK")

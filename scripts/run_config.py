@@ -32,10 +32,10 @@ elif cfg == "C3":
     n = int(sys.argv[3]) if len(sys.argv) > 3 else 2000
     m = int(sys.argv[4]) if len(sys.argv) > 4 else 10000
     rng = np.random.default_rng(0)
-    ne = 3 * n
+    ne = 6 * n                 # |V| (lower triangle) ~ 8 n must exceed m: the A_i live on V
     e = rng.integers(0, n, size=(ne, 2))
-    I = np.concatenate([e[:, 0], np.arange(n), np.arange(1, n)])
-    J = np.concatenate([e[:, 1], np.arange(n), np.arange(0, n - 1)])
+    I = np.concatenate([np.maximum(e[:, 0], e[:, 1]), np.arange(n), np.arange(1, n)])
+    J = np.concatenate([np.minimum(e[:, 0], e[:, 1]), np.arange(n), np.arange(0, n - 1)])
     V = sp.coo_matrix((np.ones(len(I)), (I, J)), shape=(n, n))
     P = S.rand_SDP(V, m, density=0.005, seed=0)
     method, kw = "feas", ({"primalstart": {"x": P._X0}} if getattr(P, "_X0", None) is not None else {})

@@ -358,19 +358,27 @@ class rand_SDP(SDP):
         y0 /= np.linalg.norm(y0)
         S0 = mk_rand(n, cp, ri, "posdef", seed)
         X0 = mk_rand(n, cp, ri, "completable", seed)
-        nz = min(max(1, int(round(density * N))), N)
-        pos = np.empty((m, nz), dtype=np.int64)
-        for j in range(m):
-            pos[j] = np.arange(N) if nz == N else rng.choice(N, size=nz, replace=False)
-        vals = rng.standard_normal((m, nz))
-        a0 = S0.copy()
-        np.add.at(a0, pos.reshape(-1), (vals * y0[:, None]).reshape(-1))
+        # density: one float for all constraints or a list with one float per constraint
+        # (``base.py:903-931``)
+        if isinstance(density, float):
+            nzs = [min(max(1, int(round(density * N))), N)] * m
+        elif isinstance(density, (list, tuple)) and len(density) == m:
+            nzs = [min(max(1, int(round(float(v) * N))), N) for v in density]
+        else:
+            raise TypeError("density must be a float or a list of m floats")
+        pos = [np.arange(N) if nz == N else rng.choice(N, size=nz, replace=False) for nz in nzs]
+        vals = [rng.standard_normal(nz) for nz in nzs]
         x = X0.copy()
         x[diag] *= 0.5
-        self._b = 2.0 * np.einsum("ij,ij->i", vals, x[pos])
-        rows = np.concatenate([Il, Il[pos.reshape(-1)]])
-        cols = np.concatenate([np.zeros(N, dtype=np.int64), np.repeat(np.arange(1, m + 1, dtype=np.int64), nz)])
-        data = np.concatenate([a0, vals.reshape(-1)])
+        a0 = S0.copy()
+        self._b = np.empty(m)
+        for j in range(m):
+            np.add.at(a0, pos[j], vals[j] * y0[j])
+            self._b[j] = 2.0 * np.dot(vals[j], x[pos[j]])
+        pos_all = np.concatenate(pos) if m else np.zeros(0, dtype=np.int64)
+        rows = np.concatenate([Il, Il[pos_all]])
+        cols = np.concatenate([np.zeros(N, dtype=np.int64), np.repeat(np.arange(1, m + 1, dtype=np.int64), nzs)])
+        data = np.concatenate([a0] + vals)
         self._A = misc.as_csc(sp.csc_matrix((data, (rows, cols)), shape=(n * n, m + 1)))
         self._X0 = sp.csc_matrix((X0, (I1, J1)), shape=(n, n))
         self._S0 = sp.csc_matrix((S0, (I1, J1)), shape=(n, n))

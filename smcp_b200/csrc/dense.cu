@@ -8,6 +8,7 @@
 // are bank-conflict free, and keeps a 32x32 accumulator tile per warp in registers (16 warps per CTA).
 #include "internal.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 // ---------------------------------------------------------------------------------------
 // DMMA GEMM:  C(i, j) = [C(i, j) +] alpha * sum_k A'(i, k) B'(j, k)
@@ -64,12 +65,14 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_dmma_kernel(const double *__restrict__ A, long long lda, const double *__restrict__ B, long long ldb,
                  double *__restrict__ C, long long ldc, long long M, long long N, long long K, double alpha,
-                 int accumulate, int tri, long long tri_off, long long kchunk, long long split_stride) {
+                 int accumulate, int tri, long long tri_off, long long kchunk, long long split_stride,
+                 int jt0, int jtstride) {
     extern __shared__ double smem[];
     double *As = smem;                              // STAGES x 128 x LDK
     double *Bs = smem + STAGES * 128 * LDK;
     const long long i0 = (long long)blockIdx.x * BM;
-    const long long j0 = (long long)blockIdx.y * BN;
+    // column tiles jt0, jt0 + jtstride, ...: the block-cyclic owner of a column block updates only its own tiles
+    const long long j0 = ((long long)jt0 + (long long)blockIdx.y * jtstride) * BN;
     if (tri && (i0 + BM - 1 + tri_off < j0)) return;        // tile entirely above the diagonal
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp & 3) * 32;       // 4 warps along M
@@ -158,14 +161,23 @@ __global__ void splitk_reduce_kernel(const double *__restrict__ P, long long spl
 int launch_gemm(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, const double *B, int64_t ldb,
                        double *C, int64_t ldc, int64_t M, int64_t N, int64_t K, double alpha, int accumulate,
                        int tri, int64_t tri_off, const char *name) {
+    return launch_gemm_cyc(ctx, ta, tb, A, lda, B, ldb, C, ldc, M, N, K, alpha, accumulate, tri, tri_off, name, 0, 1);
+}
+
+// as launch_gemm, restricted to the column tiles jt0, jt0 + jtstride, ... (128 columns each)
+int launch_gemm_cyc(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, const double *B, int64_t ldb,
+                    double *C, int64_t ldc, int64_t M, int64_t N, int64_t K, double alpha, int accumulate,
+                    int tri, int64_t tri_off, const char *name, int jt0, int jtstride) {
     if (M <= 0 || N <= 0) return 0;
-    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
+    const long long ntile_n = (N + BN - 1) / BN;
+    if (jt0 >= ntile_n) return 0;
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((ntile_n - jt0 + jtstride - 1) / jtstride));
     // split-K when the (lower-triangular) tile grid cannot fill the GPU and K is long: the Schur
     // assembly contracts over |blkval| ~ 10^4..10^6 rows into an m x m block
     long long ntiles = 0;
     for (unsigned bj = 0; bj < grid.y; ++bj)
         for (unsigned bi = 0; bi < grid.x; ++bi)
-            if (!tri || (long long)bi * BM + BM - 1 + tri_off >= (long long)bj * BN) ++ntiles;
+            if (!tri || (long long)bi * BM + BM - 1 + tri_off >= ((long long)jt0 + (long long)bj * jtstride) * BN) ++ntiles;
     int splits = 1;
     if (!accumulate && alpha == 1.0 && K >= 2048 && ntiles > 0 && ntiles < ctx->num_sms) {
         splits = (int)(ctx->num_sms / ntiles);
@@ -195,16 +207,16 @@ int launch_gemm(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, c
     }
     // algorithmic flops: 2*K per computed entry of the (lower-triangular) result
     double pairs = 0.0;
-    if (!tri) pairs = (double)M * (double)N;
-    else
-        for (int64_t j = 0; j < N; ++j) {
-            int64_t lo = j - tri_off;            // rows i >= lo
-            if (lo < 0) lo = 0;
-            if (lo < M) pairs += (double)(M - lo);
-        }
+    for (int64_t j = 0; j < N; ++j) {
+        const int64_t jt = j / BN;
+        if (jt < jt0 || (jt - jt0) % jtstride) continue;
+        int64_t lo = tri ? j - tri_off : 0;            // rows i >= lo
+        if (lo < 0) lo = 0;
+        if (lo < M) pairs += (double)(M - lo);
+    }
     {
         LaunchScope ls(ctx, name, 1, 2.0 * (double)K * pairs);
-#define GEMM_LAUNCH(TA_, TB_) gemm_dmma_kernel<TA_, TB_><<<grid, GEMM_THREADS, smem, ctx->stream>>>(A, lda, B, ldb, Cout, ldout, M, N, K, alpha, accumulate, tri, tri_off, kchunk, split_stride)
+#define GEMM_LAUNCH(TA_, TB_) gemm_dmma_kernel<TA_, TB_><<<grid, GEMM_THREADS, smem, ctx->stream>>>(A, lda, B, ldb, Cout, ldout, M, N, K, alpha, accumulate, tri, tri_off, kchunk, split_stride, jt0, jtstride)
         if (ta && tb) GEMM_LAUNCH(true, true);
         else if (!ta && !tb) GEMM_LAUNCH(false, false);
         else if (ta) GEMM_LAUNCH(true, false);
@@ -230,99 +242,134 @@ int d_gemm_tn(smcp_ctx *ctx, const double *A, int64_t lda, const double *B, int6
 // ---------------------------------------------------------------------------------------
 // blocked right-looking Cholesky (lower), column-major, in place (lapack.potrf, solvers.py:501)
 //
-// Per 64-column panel: ONE kernel factors the diagonal block and solves the panel below it, then
-// the DMMA kernel applies the trailing update.  At m ~ 10^3 the factorisation is a chain of tiny
-// dependent steps, so the diagonal block is factored with one ROW PER THREAD IN REGISTERS (64
-// threads, two barriers per column, fully unrolled: ~8 us instead of ~65 us through shared
-// memory) and every CTA of the panel kernel redoes that factorisation itself instead of waiting
-// for another launch to publish it.  // ---------------------------------------------------------------------------------------
+// Two-level blocking: column blocks of OB = 128 (= one DMMA tile column, and the unit of the
+// block-cyclic distribution over GPUs), factored by two 64-column panels.
+//   panel kernel : every CTA factors the 64 x 64 diagonal block itself (one warp, rows in
+//                  registers, pivots and multipliers exchanged by shuffles: no barriers, ~10 us)
+//                  and solves X L^T = B for its 128 panel rows;
+//   DMMA kernel  : trailing updates, K = 64 inside a block, K = 128 for the rest of the matrix.
+// Look-ahead: block q+1 is updated, factored (and, with several GPUs, broadcast) on a second
+// stream while the main stream applies panel q to the blocks >= q+2.
+// Several GPUs (north star (3)): 1-D block-cyclic columns, owner(q) = q mod nranks;
+// the owner factors block q and broadcasts its columns (NCCL); every rank updates only the
+// column tiles it owns.  Every rank ends with the full factor (all panels arrive by broadcast),
+// and the arithmetic per entry is the same as on one GPU, so the result is bitwise independent
+// of the number of ranks.
+// `ncols` < m gives the partial factorisation of a frontal matrix: the leading ncols columns
+// hold L, the trailing (m - ncols)^2 block its Schur complement (the update matrix).
+// ---------------------------------------------------------------------------------------
 #define NB 64
-#define LDT 66          // row stride of the transposed factor in shared memory
+#define OB 128
+#define LDT 66          // column stride of the factor in shared memory
 
-#define PP_THREADS 256
+#define PP_THREADS 128
 #define PP_ROWS 128       // panel rows per CTA
 
-// Diagonal block: 16 x 16 threads, each owns a 4 x 4 register block of the 64 x 64 matrix; per
-// column one barrier to publish the pivot column, one after 64 threads scaled it, then 16
-// predicated FMAs per thread.  Loops stay rolled (the first version unrolled everything and was
-// bound by instruction fetch: ncu showed stall_no_inst on 150 us launches).
-// Panel: X L^T = B, one row per thread, the row lives in shared memory (column-major, conflict
-// free), left-looking over 8-column blocks held in registers; L is read as broadcast double2.
-__global__ void __launch_bounds__(PP_THREADS) potrf_panel_kernel(double *H, long long ld, int kb, long long k0, long long m, int *info) {
-    extern __shared__ __align__(16) double ppsm[];
-    double *LT = ppsm;                       // NB x LDT: LT[c*LDT + r] = L(r, c), zero elsewhere
-    double *colbuf = LT + NB * LDT;          // 2 x NB
-    double *pivot = colbuf + 2 * NB;         // 2 (+ pad)
-    double *xs = pivot + 2;                  // NB x PP_ROWS
-    const int tid = threadIdx.x;
-    double *D = H + k0 + k0 * ld;
-    const int br = tid >> 4, bc = tid & 15;
-    double a[4][4];
+// Cholesky of a 32 x 32 block held one row per lane (a[c] = A(lane, c), c <= lane significant).
+// Rows/columns >= nv are treated as identity.  On return a[] is the row of L (zeros above the
+// diagonal); the return value is 0 or the 1-based index of the first non-positive pivot
+// (dpotrf's info), after which the result is meaningless but finite work continues.
+__device__ __forceinline__ int warp_chol32(double (&a)[32], const int lane, const int nv) {
+    int bad = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int l2 = 0; l2 < 4; ++l2) {
-            const int r = 4 * br + k, c = 4 * bc + l2;
-            a[k][l2] = (r < kb && c <= r) ? D[r + (long long)c * ld] : 0.0;
+    for (int j = 0; j < 32; ++j) {
+        double d = __shfl_sync(0xffffffffu, a[j], j);
+        if (j >= nv) d = 1.0;
+        if (!(d > 0.0)) {
+            if (!bad) bad = j + 1;
+            d = 1.0;
         }
-    for (int idx = tid; idx < NB * LDT; idx += PP_THREADS) LT[idx] = 0.0;
-    for (int j = 0; j < kb; ++j) {
-        double *cb = colbuf + (j & 1) * NB;
-        const int jb = j >> 2, jj = j & 3;
-        if (bc == jb) {
+        const double sq = sqrt(d);
+        const double l = (lane == j) ? sq : ((lane > j && lane < nv && j < nv) ? a[j] / sq : 0.0);
+        a[j] = l;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const double v = (jj == 0) ? a[k][0] : (jj == 1) ? a[k][1] : (jj == 2) ? a[k][2] : a[k][3];
-                cb[4 * br + k] = v;
-                if (4 * br + k == j) pivot[j & 1] = v;
-            }
+        for (int c = j + 1; c < 32; ++c) {
+            const double lc = __shfl_sync(0xffffffffu, l, c);
+            a[c] = fma(-l, lc, a[c]);
         }
-        __syncthreads();
-        if (tid < NB) {
-            double d = pivot[j & 1];
-            const bool bad = !(d > 0.0);
-            if (bad) d = 1.0;
-            if (bad && tid == 0 && blockIdx.x == 0 && *info == 0) *info = (int)(k0 + j + 1);   // dpotrf's info
-            const double sq = sqrt(d);
-            const double v = cb[tid];
-            cb[tid] = (tid == j) ? sq : ((tid > j) ? v / sq : 0.0);
-        }
-        __syncthreads();
-        double lr[4], lc[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            lr[k] = cb[4 * br + k];
-            lc[k] = cb[4 * bc + k];
-        }
-        if (bc == jb) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (jj == 0) a[k][0] = lr[k];
-                else if (jj == 1) a[k][1] = lr[k];
-                else if (jj == 2) a[k][2] = lr[k];
-                else a[k][3] = lr[k];
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int l2 = 0; l2 < 4; ++l2)
-                if (4 * bc + l2 > j) a[k][l2] = fma(-lr[k], lc[l2], a[k][l2]);     // rows <= j have lr = 0 or are finished columns
     }
+    return bad;
+}
+
+// Diagonal block D = H[k0:k0+kb, k0:k0+kb] (kb <= 64) factored in place by ONE warp:
+// [L11 0; L21 L22] with 32 x 32 register blocks.  A separate launch (not fused into the panel
+// kernel) because the panel CTAs must all read the FACTORED block: an in-place write-back by one
+// CTA of a fused kernel races with CTAs that are scheduled late.
+__global__ void __launch_bounds__(32) potrf_diag_kernel(double *H, long long ld, int kb, long long k0, int *info) {
+    __shared__ __align__(16) double LT[32 * LDT];      // LT[c*LDT + r] = L(r, c) for c < 32 (first block column)
+    const int lane = threadIdx.x;
+    double *D = H + k0 + k0 * ld;
+    double a[32], b[32];
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+        const int nv = min(32, kb - 32 * h);
+        if (nv <= 0) break;
+        const int r = 32 * h + lane;
+        const bool live = lane < nv;
+        if (h == 1) {
+            // L21 = D21 L11^{-T}: right-looking substitution on this lane's row
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+            for (int c = 0; c < 32; ++c) b[c] = live ? D[r + (long long)c * ld] : 0.0;
 #pragma unroll
-        for (int l2 = 0; l2 < 4; ++l2) {
-            const int r = 4 * br + k, c = 4 * bc + l2;
-            if (r < kb && c <= r) {
-                LT[c * LDT + r] = a[k][l2];
-                if (blockIdx.x == 0) D[r + (long long)c * ld] = a[k][l2];
+            for (int c = 0; c < 32; ++c) {
+                const double x = b[c] / LT[c * LDT + c];
+                b[c] = x;
+#pragma unroll
+                for (int c2 = c + 1; c2 < 32; ++c2) b[c2] = fma(-x, LT[c * LDT + c2], b[c2]);
+            }
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                LT[c * LDT + r] = b[c];
+                if (live) D[r + (long long)c * ld] = b[c];
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) a[c] = (live && c <= lane) ? D[r + (long long)(32 * h + c) * ld] : 0.0;
+        if (h == 1) {
+            // D22 -= L21 L21^T
+#pragma unroll 4
+            for (int p = 0; p < 32; ++p) {
+                const double bp = LT[p * LDT + r];
+                const double2 *lp = reinterpret_cast<const double2 *>(LT + p * LDT + 32);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const double2 lv = lp[c];
+                    a[2 * c] = fma(-bp, lv.x, a[2 * c]);
+                    a[2 * c + 1] = fma(-bp, lv.y, a[2 * c + 1]);
+                }
             }
         }
+        const int bad = warp_chol32(a, lane, nv);
+        if (bad && lane == 0 && *info == 0) *info = (int)(k0 + 32 * h + bad);   // dpotrf's info
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+            if (c <= lane) {
+                if (h == 0) LT[c * LDT + r] = a[c];
+                if (live && c < nv) D[r + (long long)(32 * h + c) * ld] = a[c];
+            }
+        __syncwarp();
+    }
+}
+
+// Panel rows below a FACTORED diagonal block: X L^T = B, one row per thread, the row lives in
+// shared memory (column-major over threads, conflict free), left-looking over 8-column register
+// blocks; L is read as broadcast double2.  H has leading dimension ld and mrows rows.
+__global__ void __launch_bounds__(PP_THREADS) potrf_panel_kernel(double *H, long long ld, int kb, long long k0, long long mrows) {
+    extern __shared__ __align__(16) double ppsm[];
+    double *LT = ppsm;                       // NB x LDT: LT[c*LDT + r] = L(r, c)
+    double *xs = LT + NB * LDT;              // NB x PP_ROWS
+    const int tid = threadIdx.x;
+    const double *D = H + k0 + k0 * ld;
+    for (int idx = tid; idx < NB * LDT; idx += PP_THREADS) LT[idx] = 0.0;
     __syncthreads();
-    // ---- panel rows
+    for (int idx = tid; idx < kb * kb; idx += PP_THREADS) {
+        const int r = idx % kb, c = idx / kb;
+        if (r >= c) LT[c * LDT + r] = D[r + (long long)c * ld];
+    }
+    __syncthreads();
     const long long row = k0 + kb + (long long)blockIdx.x * PP_ROWS + tid;
-    if (tid >= PP_ROWS || row >= m) return;
+    if (row >= mrows) return;
     double *P = H + row + k0 * ld;
     for (int c = 0; c < kb; ++c) xs[c * PP_ROWS + tid] = P[(long long)c * ld];
     for (int cb8 = 0; cb8 < kb; cb8 += 8) {
@@ -357,60 +404,149 @@ __global__ void __launch_bounds__(PP_THREADS) potrf_panel_kernel(double *H, long
     }
 }
 
-int d_potrf(smcp_ctx *ctx, double *H, int64_t m, int32_t *info_dev, double *Dinv) {
-    CUDA_TRY(cudaMemsetAsync(info_dev, 0, sizeof(int), ctx->stream));
-    const size_t pp_smem = (size_t)(NB * LDT + 2 * NB + 2 + NB * PP_ROWS) * sizeof(double);
+namespace {
+struct StreamSwap {      // run the launch helpers (which use ctx->stream) on another stream
+    smcp_ctx *ctx;
+    cudaStream_t saved;
+    StreamSwap(smcp_ctx *c, cudaStream_t s) : ctx(c), saved(c->stream) { c->stream = s; }
+    ~StreamSwap() { ctx->stream = saved; }
+};
+}  // namespace
+
+// factor the column block [c0, c0+w) of H (rows c0..mrows): two 64-column panels
+static int potrf_block(smcp_ctx *ctx, double *H, int64_t ld, int64_t mrows, int64_t c0, int64_t w, int32_t *info_dev, size_t pp_smem) {
+    for (int64_t k0 = c0; k0 < c0 + w; k0 += NB) {
+        const int kb = (int)std::min<int64_t>(NB, c0 + w - k0);
+        const int64_t below = mrows - k0 - kb;
+        {
+            LaunchScope ls(ctx, "potrf_panel", below > 0 ? 2 : 1, 16.0 * (double)(mrows - k0) * kb);
+            potrf_diag_kernel<<<1, 32, 0, ctx->stream>>>(H, ld, kb, k0, info_dev);
+            if (below > 0)
+                potrf_panel_kernel<<<(unsigned)((below + PP_ROWS - 1) / PP_ROWS), PP_THREADS, pp_smem, ctx->stream>>>(H, ld, kb, k0, mrows);
+        }
+        const int64_t ncr = c0 + w - (k0 + kb);      // columns of the block still to be updated
+        if (ncr > 0 && below > 0) {
+            const double *P = H + (k0 + kb) + k0 * ld;
+            double *Ct = H + (k0 + kb) + (k0 + kb) * ld;
+            if (launch_gemm(ctx, false, false, P, ld, P, ld, Ct, ld, below, ncr, kb, -1.0, 1, 1, 0, "potrf_syrk_dmma")) return -1;
+        }
+    }
+    return 0;
+}
+
+int d_potrf(smcp_ctx *ctx, double *H, int64_t ld, int64_t m, int64_t ncols, int32_t *info_dev, int rank, int nranks) {
+    if (ncols > m) ncols = m;
+    if (nranks < 1) nranks = 1;
+    const size_t pp_smem = (size_t)(NB * LDT + NB * PP_ROWS) * sizeof(double);
     static bool pp_attr = false;
     if (!pp_attr) {
         CUDA_TRY(cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_smem));
         pp_attr = true;
     }
-    for (int64_t k0 = 0; k0 < m; k0 += NB) {
-        int kb = (int)((m - k0 < NB) ? (m - k0) : NB);
-        int64_t rem = m - k0 - kb;
-        {
-            LaunchScope ls(ctx, "potrf_panel", 1, 16.0 * (double)(m - k0) * kb);
-            unsigned grid = (unsigned)std::max<int64_t>(1, (rem + PP_ROWS - 1) / PP_ROWS);
-            potrf_panel_kernel<<<grid, PP_THREADS, pp_smem, ctx->stream>>>(H, m, kb, k0, m, info_dev);
-        }
-        if (rem > 0) {
-            const double *P = H + (k0 + kb) + k0 * m;
-            double *Ct = H + (k0 + kb) + (k0 + kb) * m;
-            if (launch_gemm(ctx, false, false, P, m, P, m, Ct, m, rem, rem, kb, -1.0, 1, 1, 0, "potrf_syrk_dmma")) return -1;
-        }
+    const int64_t nblocks = (ncols + OB - 1) / OB;
+    if (nranks > 1 && (ld != m || ncols != m)) { smcp_set_error("d_potrf: the distributed factorisation needs a full square matrix"); return -2; }
+    // one profiling scope for the whole factorisation (the two streams overlap)
+    LaunchScope outer(ctx, "potrf_dmma", 0, (double)ncols * ncols * ncols / 3.0 + (double)(m - ncols) * ncols * (double)m);
+    ctx->prof_mute++;
+    struct Unmute { smcp_ctx *c; ~Unmute() { c->prof_mute--; } } unmute{ctx};
+    cudaStream_t sB = ctx->stream, sA = ctx->stream2;
+    static const bool lookahead = !(getenv("SMCP_B200_LOOKAHEAD") && atoi(getenv("SMCP_B200_LOOKAHEAD")) == 0);
+    // the second stream pays off once the trailing updates are long enough to hide a panel (m >= 4096);
+    // below that the factorisation is a chain of short kernels and one stream is as fast
+    const bool two = lookahead && (sA != nullptr) && (nblocks > 1) && (m >= 4096);
+    if (!two) sA = sB;
+    while ((int64_t)ctx->potrf_ev.size() < 2 * nblocks + 2) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->potrf_ev.push_back(e);
     }
-    (void)Dinv;
+    cudaEvent_t *E = ctx->potrf_ev.data(), *F = ctx->potrf_ev.data() + nblocks;
+    cudaEvent_t fork = ctx->potrf_ev[2 * nblocks], join = ctx->potrf_ev[2 * nblocks + 1];
+    CUDA_TRY(cudaMemsetAsync(info_dev, 0, sizeof(int), sB));
+    if (two) {
+        CUDA_TRY(cudaEventRecord(fork, sB));
+        CUDA_TRY(cudaStreamWaitEvent(sA, fork, 0));
+    }
+    auto blk_c0 = [&](int64_t q) { return q * OB; };
+    auto blk_w = [&](int64_t q) { return std::min<int64_t>(OB, ncols - q * OB); };
+    // block 0
+    {
+        StreamSwap sw(ctx, sA);
+        if (rank == 0 % nranks && potrf_block(ctx, H, ld, m, 0, blk_w(0), info_dev, pp_smem)) return -1;
+        if (nranks > 1 && comm_bcast(ctx, H, (size_t)blk_w(0) * ld, 0, sA)) return -1;
+        if (two) CUDA_TRY(cudaEventRecord(E[0], sA));
+    }
+    for (int64_t q = 0; q < nblocks; ++q) {
+        const int64_t c0 = blk_c0(q), w = blk_w(q), c1 = c0 + w;
+        if (c1 >= m) break;
+        const double *P1 = H + c1 + c0 * ld;          // panel q, rows c1..
+        if (two) CUDA_TRY(cudaStreamWaitEvent(sB, E[q], 0));
+        int64_t c2 = c1;
+        if (q + 1 < nblocks) {
+            // look-ahead: block q+1 gets panel q, is factored and published on stream A
+            const int64_t w1 = blk_w(q + 1);
+            c2 = c1 + w1;
+            StreamSwap sw(ctx, sA);
+            if (two && q >= 1) CUDA_TRY(cudaStreamWaitEvent(sA, F[q - 1], 0));
+            if ((q + 1) % nranks == rank) {
+                if (launch_gemm(ctx, false, false, P1, ld, P1, ld, H + c1 + c1 * ld, ld, m - c1, w1, w, -1.0, 1, 1, 0, "potrf_syrk_dmma")) return -1;
+                if (potrf_block(ctx, H, ld, m, c1, w1, info_dev, pp_smem)) return -1;
+            }
+            if (nranks > 1 && comm_bcast(ctx, H + c1 * ld, (size_t)w1 * ld, (int)((q + 1) % nranks), sA)) return -1;
+            if (two) CUDA_TRY(cudaEventRecord(E[q + 1], sA));
+        }
+        // panel q applied to everything right of block q+1 (own column tiles only)
+        if (c2 < m) {
+            const double *P2 = H + c2 + c0 * ld;
+            const int64_t qb = c2 / OB;                              // block index of the first tile column
+            const int jt0 = (int)(((rank - qb) % nranks + nranks) % nranks);
+            if (launch_gemm_cyc(ctx, false, false, P2, ld, P2, ld, H + c2 + c2 * ld, ld, m - c2, m - c2, w, -1.0, 1, 1, 0,
+                                "potrf_syrk_dmma", jt0, nranks)) return -1;
+        }
+        if (two) CUDA_TRY(cudaEventRecord(F[q], sB));
+    }
+    if (two) {
+        CUDA_TRY(cudaEventRecord(join, sA));
+        CUDA_TRY(cudaStreamWaitEvent(sB, join, 0));
+    }
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
 // ---------------------------------------------------------------------------------------
 // potrs: y <- L^{-T} L^{-1} y (lapack.potrs, solvers.py:526), single right-hand side.
-// A triangular solve is m dependent steps whatever the hardware, so this is a latency kernel:
-// one CTA of 1024 threads, the right-hand side lives in shared memory for the whole solve, the
-// 64 x 64 diagonal block is staged in shared memory, substitution inside a block is done by one
-// warp (row values in registers, pivot broadcast by shuffle, multiplication by the reciprocal
-// pivots computed off the critical path), and the off-diagonal part of every block column is a
-// GEMV spread over all 32 warps with independent partial sums.  Plain substitution, no explicit
-// inverses: backward stable like the LAPACK routine it replaces.
+// A triangular solve is m dependent steps whatever the hardware, so this is a latency kernel.
+// potrs_kernel: one CTA of 1024 threads solves with the diagonal block [i0, i0+mm): the
+// right-hand side lives in shared memory, each 64 x 64 diagonal block is staged in shared memory,
+// substitution inside a block is done by one warp (row values in registers, pivot broadcast by
+// shuffle, multiplication by the reciprocal pivots computed off the critical path), and the
+// off-diagonal part of every block column is a GEMV spread over all 32 warps with independent
+// partial sums.  Plain substitution, no explicit inverses: backward stable like the LAPACK
+// routine it replaces.  m <= 1536: one launch does everything.  Larger m: blocks of 256 rows
+// go through potrs_kernel and the rest of the matrix is streamed by multi-CTA GEMV kernels
+// (fixed summation order, no atomics).
 // ---------------------------------------------------------------------------------------
 #define PS_THREADS 1024
-__global__ void __launch_bounds__(PS_THREADS) potrs_kernel(const double *__restrict__ H, long long m, double *__restrict__ y) {
+__global__ void __launch_bounds__(PS_THREADS) potrs_kernel(const double *__restrict__ Hfull, long long ld, long long i0, long long m,
+                                                           double *__restrict__ yfull, int do_fwd, int do_bwd) {
     extern __shared__ double psm[];
     double *Lk = psm;                    // NB x (NB+1)
     double *rinv = Lk + NB * (NB + 1);   // NB
     double *tb = rinv + NB;              // NB
     double *ys = tb + NB;                // m
+    const double *H = Hfull + i0 + i0 * ld;
+    double *y = yfull + i0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long nblkc = (m + NB - 1) / NB;
     for (long long i = tid; i < m; i += PS_THREADS) ys[i] = y[i];
     // forward: L x = y
+    if (do_fwd)
     for (long long bi = 0; bi < nblkc; ++bi) {
         const long long k0 = bi * NB;
         const int kb = (int)min((long long)NB, m - k0);
         for (int idx = tid; idx < kb * kb; idx += PS_THREADS) {
             const int i = idx % kb, j = idx / kb;
-            Lk[i * (NB + 1) + j] = H[(k0 + i) + (k0 + j) * m];
+            Lk[i * (NB + 1) + j] = H[(k0 + i) + (k0 + j) * ld];
         }
         __syncthreads();
         if (tid < kb) rinv[tid] = 1.0 / Lk[tid * (NB + 1) + tid];
@@ -429,31 +565,32 @@ __global__ void __launch_bounds__(PS_THREADS) potrs_kernel(const double *__restr
         }
         __syncthreads();
         for (long long i = k0 + kb + tid; i < m; i += PS_THREADS) {
-            const double *Lr = H + i + k0 * m;
+            const double *Lr = H + i + k0 * ld;
             const double *xk = ys + k0;
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll 4
             for (int j = 0; j < NB; j += 4) {       // here kb == NB (rows remain below the block)
-                s0 = fma(Lr[(long long)j * m], xk[j], s0);
-                s1 = fma(Lr[(long long)(j + 1) * m], xk[j + 1], s1);
-                s2 = fma(Lr[(long long)(j + 2) * m], xk[j + 2], s2);
-                s3 = fma(Lr[(long long)(j + 3) * m], xk[j + 3], s3);
+                s0 = fma(Lr[(long long)j * ld], xk[j], s0);
+                s1 = fma(Lr[(long long)(j + 1) * ld], xk[j + 1], s1);
+                s2 = fma(Lr[(long long)(j + 2) * ld], xk[j + 2], s2);
+                s3 = fma(Lr[(long long)(j + 3) * ld], xk[j + 3], s3);
             }
             ys[i] -= (s0 + s1) + (s2 + s3);
         }
         __syncthreads();
     }
     // backward: L^T x = y
+    if (do_bwd)
     for (long long bi = nblkc - 1; bi >= 0; --bi) {
         const long long k0 = bi * NB;
         const int kb = (int)min((long long)NB, m - k0);
         for (int idx = tid; idx < kb * kb; idx += PS_THREADS) {
             const int i = idx % kb, j = idx / kb;
-            Lk[i * (NB + 1) + j] = H[(k0 + i) + (k0 + j) * m];
+            Lk[i * (NB + 1) + j] = H[(k0 + i) + (k0 + j) * ld];
         }
         // t_c = y[k0+c] - sum_{i >= k0+kb} L(i, k0+c) y[i]: warp w takes columns w and w + 32
         for (int c = warp; c < kb; c += PS_THREADS / 32) {
-            const double *Lc = H + (k0 + c) * m;
+            const double *Lc = H + (k0 + c) * ld;
             double s0 = 0.0, s1 = 0.0;
             long long i = k0 + kb + lane;
             for (; i + 32 < m; i += 64) {
@@ -485,18 +622,83 @@ __global__ void __launch_bounds__(PS_THREADS) potrs_kernel(const double *__restr
     for (long long i = tid; i < m; i += PS_THREADS) y[i] = ys[i];
 }
 
-int d_potrs(smcp_ctx *ctx, const double *H, int64_t m, const double *Dinv, double *y_dev) {
-    (void)Dinv;
-    const size_t smem = (size_t)(NB * (NB + 1) + 2 * NB + m + 8) * sizeof(double);
-    if (smem > 200 * 1024) { smcp_set_error("potrs: m = %lld exceeds the single-CTA kernel (right-hand side in shared memory)", (long long)m); return -2; }
+#define PSB 256          // diagonal block of the multi-kernel solve
+// forward update: y[i] -= sum_{j < kb} L(i, i0+j) x[i0+j] for i >= i0+kb.  64 rows per CTA, four
+// column groups of threads, partial sums combined in a fixed order.
+__global__ void __launch_bounds__(256) potrs_fwd_update_kernel(const double *__restrict__ H, long long ld, long long m, long long i0, int kb,
+                                                               double *__restrict__ y) {
+    __shared__ double xs[PSB];
+    __shared__ double part[4][64];
+    const int tid = threadIdx.x, r = tid & 63, cg = tid >> 6;
+    for (int j = tid; j < kb; j += 256) xs[j] = y[i0 + j];
+    __syncthreads();
+    const long long row = i0 + kb + (long long)blockIdx.x * 64 + r;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (row < m) {
+        const int per = (kb + 3) / 4, j0 = cg * per, j1 = min(kb, j0 + per);
+        const double *Lr = H + row + (i0 + j0) * ld;
+        int j = j0;
+        for (; j + 3 < j1; j += 4, Lr += 4 * ld) {
+            s0 = fma(Lr[0], xs[j], s0);
+            s1 = fma(Lr[ld], xs[j + 1], s1);
+            s2 = fma(Lr[2 * ld], xs[j + 2], s2);
+            s3 = fma(Lr[3 * ld], xs[j + 3], s3);
+        }
+        for (; j < j1; ++j, Lr += ld) s0 = fma(Lr[0], xs[j], s0);
+    }
+    part[cg][r] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (cg == 0 && row < m) y[row] -= (part[0][r] + part[1][r]) + (part[2][r] + part[3][r]);
+}
+
+// backward update: y[c] -= sum_{i < kb} L(i0+i, c) x[i0+i] for c < i0: one warp per column
+__global__ void __launch_bounds__(256) potrs_bwd_update_kernel(const double *__restrict__ H, long long ld, long long i0, int kb,
+                                                               double *__restrict__ y) {
+    __shared__ double xs[PSB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int j = tid; j < kb; j += 256) xs[j] = y[i0 + j];
+    __syncthreads();
+    const long long c = (long long)blockIdx.x * 8 + warp;
+    if (c >= i0) return;
+    const double *Lc = H + i0 + c * ld;
+    double s = 0.0;
+    for (int i = lane; i < kb; i += 32) s = fma(Lc[i], xs[i], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) y[c] -= s;
+}
+
+int d_potrs(smcp_ctx *ctx, const double *H, int64_t m, double *y_dev) {
+    const int64_t single_max = 1536;
+    const int64_t mm = (m <= single_max) ? m : PSB;
+    const size_t smem = (size_t)(NB * (NB + 1) + 2 * NB + mm + 8) * sizeof(double);
     static size_t attr = 0;
     if (smem > attr) {
         CUDA_TRY(cudaFuncSetAttribute(potrs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    {
-        LaunchScope ls(ctx, "potrs", 1, 8.0 * (double)m * (double)m);
-        potrs_kernel<<<1, PS_THREADS, smem, ctx->stream>>>(H, m, y_dev);
+    LaunchScope ls(ctx, "potrs", 0, 8.0 * (double)m * (double)m);
+    ctx->prof_mute++;
+    struct Unmute { smcp_ctx *c; ~Unmute() { c->prof_mute--; } } unmute{ctx};
+    if (m <= single_max) {
+        ctx->launches += 1;
+        potrs_kernel<<<1, PS_THREADS, smem, ctx->stream>>>(H, m, 0, m, y_dev, 1, 1);
+    } else {
+        const int64_t nb = (m + PSB - 1) / PSB;
+        for (int64_t b = 0; b < nb; ++b) {
+            const int64_t i0 = b * PSB;
+            const int kb = (int)std::min<int64_t>(PSB, m - i0);
+            potrs_kernel<<<1, PS_THREADS, smem, ctx->stream>>>(H, m, i0, kb, y_dev, 1, 0);
+            const int64_t below = m - i0 - kb;
+            if (below > 0) potrs_fwd_update_kernel<<<(unsigned)((below + 63) / 64), 256, 0, ctx->stream>>>(H, m, m, i0, kb, y_dev);
+            ctx->launches += 2;
+        }
+        for (int64_t b = nb - 1; b >= 0; --b) {
+            const int64_t i0 = b * PSB;
+            const int kb = (int)std::min<int64_t>(PSB, m - i0);
+            potrs_kernel<<<1, PS_THREADS, smem, ctx->stream>>>(H, m, i0, kb, y_dev, 0, 1);
+            if (i0 > 0) potrs_bwd_update_kernel<<<(unsigned)((i0 + 7) / 8), 256, 0, ctx->stream>>>(H, m, i0, kb, y_dev);
+            ctx->launches += 2;
+        }
     }
     CUDA_TRY(cudaGetLastError());
     return 0;

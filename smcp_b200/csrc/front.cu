@@ -326,7 +326,7 @@ int root_cholesky(smcp_sym *s, double *X, int64_t b) {
         LaunchScope ls(ctx, "front_elem");
         root_elem_kernel<0><<<elem_grid(s), 256, 0, ctx->stream>>>(root_args(s, b), blk, nullptr);
     }
-    if (d_potrf(ctx, blk, nn, s->root_info, nullptr)) return -1;
+    if (d_potrf(ctx, blk, nn, nn, nn, s->root_info, 0, 1)) return -1;
     root_flag_kernel<<<1, 1, 0, ctx->stream>>>(s->root_info, s->fail + b);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -431,7 +431,7 @@ int root_completion(smcp_sym *s, double *X, const double *Xin, int64_t b) {
         LaunchScope ls(ctx, "front_elem", 3);
         root_reverse_kernel<<<elem_grid(s), 256, 0, ctx->stream>>>(bin, T0, nn, 0);
     }
-    if (d_potrf(ctx, T0, nn, s->root_info, nullptr)) return -1;
+    if (d_potrf(ctx, T0, nn, nn, nn, s->root_info, 0, 1)) return -1;
     root_flag_kernel<<<1, 1, 0, ctx->stream>>>(s->root_info, s->fail + b);
     {
         LaunchScope ls(ctx, "front_elem", 2);

@@ -29,6 +29,9 @@ struct smcp_ctx {
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;                 // look-ahead stream of the dense Cholesky (panels + broadcasts)
+    std::vector<cudaEvent_t> potrf_ev;              // fork/join events of the look-ahead pipeline
+    int prof_mute = 0;                              // > 0: nested LaunchScopes do not time (an outer scope does)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;       // user timer
     cudaEvent_t pev0 = nullptr, pev1 = nullptr;     // profiling events
     int64_t launches = 0;
@@ -50,6 +53,8 @@ struct LaunchScope {
     const char *name;
     int n;
     double work;
+    bool active;
+    int64_t launches0;       // ctx->launches after this scope's own n: nested launches are credited to it too
     LaunchScope(smcp_ctx *c, const char *nm, int nlaunch = 1, double work = 0.0);
     ~LaunchScope();
 };
@@ -186,8 +191,15 @@ int root_completion(smcp_sym *s, double *X, const double *Xin, int64_t b);
 int d_trsm_left_lower(smcp_ctx *ctx, bool trans, const double *L, int64_t ldl, int64_t n, double *B, int64_t ldb, int64_t nrhs);
 
 // dense kernels (dense.cu)
-int d_potrf(smcp_ctx *ctx, double *H, int64_t m, int32_t *info_dev, double *Dinv);
-int d_potrs(smcp_ctx *ctx, const double *H, int64_t m, const double *Dinv, double *y_dev);
+// factor the leading ncols columns of the m x m matrix H (leading dimension ld); ncols < m leaves the
+// Schur complement in the trailing block; nranks > 1: block-cyclic columns with NCCL panel broadcasts
+int d_potrf(smcp_ctx *ctx, double *H, int64_t ld, int64_t m, int64_t ncols, int32_t *info_dev, int rank, int nranks);
+int d_potrs(smcp_ctx *ctx, const double *H, int64_t m, double *y_dev);
+int launch_gemm_cyc(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
+                    int64_t ldc, int64_t M, int64_t N, int64_t K, double alpha, int accumulate, int tri, int64_t tri_off,
+                    const char *name, int jt0, int jtstride);
+// ncclBroadcast of `count` doubles in place on stream s (capi.cu)
+int comm_bcast(smcp_ctx *ctx, double *ptr, size_t count, int root, cudaStream_t s);
 int launch_gemm(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
                 int64_t ldc, int64_t M, int64_t N, int64_t K, double alpha, int accumulate, int tri, int64_t tri_off,
                 const char *name);

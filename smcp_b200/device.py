@@ -76,6 +76,7 @@ API = {
     "smcp_kkt_assemble": (_int, [_vp, _vp, _i64, _i64]),
     "smcp_kkt_assemble_cyclic": (_int, [_vp, _vp, _i64, _int, _int]),
     "smcp_kkt_factor": (_int, [_vp, _i32p]),
+    "smcp_kkt_factor_dist": (_int, [_vp, _int, _int, _i32p]),
     "smcp_kkt_solve": (_int, [_vp, _f64p]),
     "smcp_kkt_get_H": (_int, [_vp, _f64p]),
     "smcp_kkt_set_H": (_int, [_vp, _f64p]),
@@ -104,8 +105,32 @@ def load_library(path=None):
         fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    if os.environ.get("SMCP_B200_HOSTPROF"):
+        lib = _HostProf(lib)
     _LIB = lib
     return lib
+
+
+HOSTPROF = {}      # name -> [calls, seconds]: host wall time spent inside each C-ABI call
+
+
+class _HostProf:
+    """Debug aid (SMCP_B200_HOSTPROF=1): wraps every entry point with a host wall-clock counter so
+    that a blocking call shows up by name; results in ``device.HOSTPROF``."""
+
+    def __init__(self, lib):
+        import time
+        for name in API:
+            fn = getattr(lib, name)
+
+            def wrapped(*a, _fn=fn, _name=name, _t=time.perf_counter):
+                t0 = _t()
+                r = _fn(*a)
+                e = HOSTPROF.setdefault(_name, [0, 0.0])
+                e[0] += 1
+                e[1] += _t() - t0
+                return r
+            setattr(self, name, wrapped)
 
 
 class DeviceError(RuntimeError):
@@ -438,14 +463,20 @@ class DeviceBackend:
         _ck(self.lib, self.lib.smcp_kkt_assemble(self._op, tok, int(j0), int(self.m if j1 is None else j1)))
 
     def schur_factor(self, tok):
+        info = np.zeros(1, dtype=np.int32)
         if self.comm is None or self.comm[1] == 1:
             self.schur_assemble(tok)
+            _ck(self.lib, self.lib.smcp_kkt_factor(self._op, info))
         else:
             rank, nranks, block = self.comm
             _ck(self.lib, self.lib.smcp_kkt_assemble_cyclic(self._op, tok, block, rank, nranks))
-            _ck(self.lib, self.lib.smcp_kkt_allgather(self._op, block, rank, nranks))
-        info = np.zeros(1, dtype=np.int32)
-        _ck(self.lib, self.lib.smcp_kkt_factor(self._op, info))
+            if block == 128:
+                # block-cyclic Cholesky: owners factor their 128-column blocks and broadcast the
+                # panels (NCCL); no gather of the unfactored H is needed
+                _ck(self.lib, self.lib.smcp_kkt_factor_dist(self._op, rank, nranks, info))
+            else:
+                _ck(self.lib, self.lib.smcp_kkt_allgather(self._op, block, rank, nranks))
+                _ck(self.lib, self.lib.smcp_kkt_factor(self._op, info))
         if info[0]:
             raise ArithmeticError("Schur complement is not positive definite (info=%d)" % info[0])
 

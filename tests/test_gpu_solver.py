@@ -36,6 +36,15 @@ def _make(kind):
         V = sp.coo_matrix((np.ones(50 + n), (np.concatenate([e[:, 0], np.arange(n)]),
                                              np.concatenate([e[:, 1], np.arange(n)]))), shape=(n, n))
         return S.rand_SDP(V, 25, density=0.03, seed=4)     # few non-zeros -> "sparse" constraints
+    if kind == "rand_mixed":
+        # dense and sparse constraints together: technique 1 (batched Hessian + DMMA) for the first
+        # group, technique 2 (position-form kernel on the dense inverse) for the second
+        rng = np.random.default_rng(11)
+        n = 90
+        e = rng.integers(0, n, size=(160, 2))
+        V = sp.coo_matrix((np.ones(160 + n), (np.concatenate([e[:, 0], np.arange(n)]),
+                                              np.concatenate([e[:, 1], np.arange(n)]))), shape=(n, n))
+        return S.rand_SDP(V, 40, density=[0.7] * 12 + [0.02] * 28, seed=5)
     if kind == "maxcut":
         rng = np.random.default_rng(5)
         n = 40
@@ -44,7 +53,7 @@ def _make(kind):
     raise ValueError(kind)
 
 
-@pytest.mark.parametrize("kind", ["band", "mtxnorm", "rand_sparse", "maxcut"])
+@pytest.mark.parametrize("kind", ["band", "mtxnorm", "rand_sparse", "rand_mixed", "maxcut"])
 def test_operator_and_schur(kind):
     from smcp_b200.chordal import cspmatrix, cholesky, projected_inverse, schur_token
     fo, fd = _factories()
@@ -105,7 +114,7 @@ def test_schur_not_pd_raises():
     assert info[0] == 1
 
 
-@pytest.mark.parametrize("m", [1, 63, 64, 65, 200, 333])
+@pytest.mark.parametrize("m", [1, 31, 33, 63, 64, 65, 127, 129, 200, 333, 1000, 1537, 2500])
 def test_dense_potrf_potrs(m):
     """lapack.potrf / potrs replacement on its own, against numpy."""
     from smcp_b200.device import _ck
@@ -131,6 +140,31 @@ def test_dense_potrf_potrs(m):
     rhs = rng.standard_normal(m)
     z = ops.schur_solve(rhs)
     assert np.linalg.norm(H @ z - rhs) <= 1e-10 * np.linalg.norm(rhs)
+    # the block-cyclic entry point with one rank is the same factorisation, bit for bit
+    _ck(ops.lib, ops.lib.smcp_kkt_set_H(ops._op, np.asfortranarray(np.tril(H)).reshape(-1, order="F")))
+    _ck(ops.lib, ops.lib.smcp_kkt_factor_dist(ops._op, 0, 1, info))
+    assert info[0] == 0 and np.array_equal(np.tril(ops.get_H()), Lh)
+
+
+@pytest.mark.parametrize("m,bad", [(40, 7), (200, 150), (300, 1), (500, 333)])
+def test_dense_potrf_info(m, bad):
+    """dpotrf's info: 1-based index of the first non-positive pivot."""
+    from smcp_b200.device import _ck, DeviceBackend
+    fo, fd = _factories()
+    pd = _problem(_make("band"), fd)
+    ops = DeviceBackend(pd.symb)
+    ops.set_operator(sp.random(pd.symb.nvp, m, density=min(1.0, 3.0 / m), random_state=1, format="csc"), 0)
+    rng = np.random.default_rng(m)
+    G = rng.standard_normal((m, m))
+    H = G @ G.T + m * np.eye(m)
+    # pivot `bad` becomes -1, the earlier ones are untouched
+    L = np.linalg.cholesky(H)
+    H2 = H.copy()
+    H2[bad - 1, bad - 1] -= L[bad - 1, bad - 1] ** 2 + 1.0
+    _ck(ops.lib, ops.lib.smcp_kkt_set_H(ops._op, np.asfortranarray(np.tril(H2)).reshape(-1, order="F")))
+    info = np.zeros(1, dtype=np.int32)
+    _ck(ops.lib, ops.lib.smcp_kkt_factor(ops._op, info))
+    assert info[0] == bad
 
 
 def _solve(P, factory, method, scaling):
