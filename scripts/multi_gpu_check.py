@@ -64,7 +64,7 @@ ops.schur_factor(tok)
 ops.ctx.sync()
 t_dist = time.perf_counter() - t0
 Ldist = np.tril(ops.get_H())
-err_L = float(np.abs(Ldist - Lsingle).max())
+err_L = float(np.abs(Ldist - Lsingle).max() / np.abs(Lsingle).max())
 rhs = rng.standard_normal(m)
 z = ops.schur_solve(rhs)
 import scipy.linalg as sl
@@ -89,7 +89,9 @@ dist.broadcast(v0, src=0)
 print("rank %d/%d: |H_sharded - H_full|/|H| = %.2e, |L_dist - L_single|max = %.2e (assemble+factor %.2f ms), "
       "solve err vs scipy = %.2e, |z - z_rank0|max = %.2e, driver pobj %.12e iters %d (rank0: %.12e %d)"
       % (rank, world, err_H, err_L, 1e3 * t_dist, err_solve, same, v[0], int(v[1]), v0[0], int(v0[1])), flush=True)
-assert err_H < 1e-12 and err_L == 0.0 and err_solve < 1e-8 and same == 0.0 and torch.equal(v, v0)
+# the split-K chunking of the Schur contraction depends on the launch geometry, so N ranks and one
+# rank agree to rounding (not bitwise); ACROSS ranks everything is bitwise identical (same == 0)
+assert err_H < 1e-12 and err_L < 1e-12 and err_solve < 1e-8 and same == 0.0 and torch.equal(v, v0)
 dist.barrier()
 if rank == 0:
     print("MULTI_GPU_CHECK OK")

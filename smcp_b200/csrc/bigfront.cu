@@ -1,0 +1,530 @@
+// Large frontal matrices as dense multi-CTA kernels on the FP64 tensor cores (north star (1):
+// "large frontal updates run as FP64 tensor-core (DMMA) tiles").
+//
+// The persistent tree kernels (chordal.cu) give one supernode to ONE CTA and keep its frontal matrix
+// in shared memory (nj <= 79) or in a per-CTA global scratch.  On patterns with real fill (rand_SDP,
+// max-cut embeddings, mtxnorm) a handful of supernodes near the root carry > 99 % of the flops
+// (rand_SDP n = 2000: root 1186 x 1186; max-cut n = 5000: a 679-column supernode with a 1-row
+// separator under a chain of 600-row separators), and a single CTA needs 0.1 .. 1 s for them.
+// For single matrices (Newton solves, line-search factorisations, scaling points) those supernodes
+// are taken out of the tree kernel: the "top set" T = {supernodes with nj >= threshold} plus all
+// their ancestors is processed here, supernode by supernode in (reverse) post-order, with dense
+// building blocks that use the whole GPU:
+//   * DMMA GEMM (dense.cu) for every congruence / Schur-complement product,
+//   * blocked triangular solves (front.cu: 64 x 64 diagonal blocks + DMMA updates),
+//   * the blocked Cholesky of dense.cu, as a PARTIAL factorisation of the frontal matrix: the
+//     leading nn columns become L, the trailing na x na block the update matrix.
+// The block formulas are those of chordal_ops.cuh / oracle/supernodal.py; reference
+// call sites: src/python/solvers.py:884 (cholesky), 874 (completion), 891 (projected_inverse),
+// 904 (llt), 483/524/531 (hessian), 405 (inverse hessian).
+// Children's update matrices are added through a precomputed inverse relative-index map so that
+// every entry of a frontal matrix is summed by one thread in child order (deterministic).
+#include "internal.cuh"
+#include <algorithm>
+#include <cstdlib>
+
+// ---------------------------------------------------------------------------------------
+// elementwise kernels
+// ---------------------------------------------------------------------------------------
+struct BigArgs {
+    int nn, na, nj, nch;
+    const int *ch;           // children
+    const int *inv;          // nch x nj: position of row p of this supernode in the child's separator, or -1
+    const int *na_all;       // per supernode
+    const long long *updptr;
+    const double *ub;        // update matrices of this matrix
+};
+
+__device__ __forceinline__ double big_children(const BigArgs &r, int i, int j, bool lower_stored) {
+    double acc = 0.0;
+    for (int q = 0; q < r.nch; ++q) {
+        const int a = r.inv[(long long)q * r.nj + i], b = r.inv[(long long)q * r.nj + j];
+        if (a >= 0 && b >= 0) {
+            const int c = r.ch[q], nac = r.na_all[c];
+            const double *Uc = r.ub + r.updptr[c];
+            acc += lower_stored ? Uc[max(a, b) + (long long)min(a, b) * nac] : Uc[a + (long long)b * nac];
+        }
+    }
+    return acc;
+}
+
+#define BIG_LOOP(total) for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < (total); idx += (long long)gridDim.x * blockDim.x)
+
+// F (nj x nj, lower) = [blk_nn(lower) ; blk_an ; 0] + children (lower-stored); upper <- 0        (cholesky)
+__global__ void big_front_lower_kernel(BigArgs r, const double *__restrict__ blk, double *__restrict__ F) {
+    const int nj = r.nj, nn = r.nn;
+    BIG_LOOP((long long)nj * nj) {
+        const int i = (int)(idx % nj), j = (int)(idx / nj);
+        double v = 0.0;
+        if (i >= j) {
+            if (j < nn) v = blk[i + (long long)j * nj];
+            v += big_children(r, i, j, true);
+        }
+        F[idx] = v;
+    }
+}
+
+// F (nj x nj, full symmetric) = sym([blk_nn blk_an^T; blk_an 0]) + children (full)               (hessian pass 1)
+__global__ void big_front_full_kernel(BigArgs r, const double *__restrict__ blk, double *__restrict__ F) {
+    const int nj = r.nj, nn = r.nn;
+    BIG_LOOP((long long)nj * nj) {
+        const int i = (int)(idx % nj), j = (int)(idx / nj);
+        const int hi = max(i, j), lo = min(i, j);
+        double v = (lo < nn) ? blk[hi + (long long)lo * nj] : 0.0;
+        F[idx] = v + big_children(r, i, j, false);
+    }
+}
+
+// copy the leading nn columns of F (ld nj) to blk: lower part of the nn x nn block, zero above
+__global__ void big_store_cols_kernel(const double *__restrict__ F, double *__restrict__ blk, int nn, int nj) {
+    BIG_LOOP((long long)nj * nn) {
+        const int i = (int)(idx % nj), j = (int)(idx / nj);
+        blk[idx] = (i >= j) ? F[idx] : 0.0;
+    }
+}
+
+// U (na x na, ld na) = S (ld lds); lower: only i >= j is written, the rest is zeroed
+__global__ void big_copy_mat_kernel(const double *__restrict__ S, long long lds, double *__restrict__ U, long long ldu, int rows, int cols, int lower) {
+    BIG_LOOP((long long)rows * cols) {
+        const int i = (int)(idx % rows), j = (int)(idx / rows);
+        U[i + (long long)j * ldu] = (!lower || i >= j) ? S[i + (long long)j * lds] : 0.0;
+    }
+}
+
+// llt: blk(lower nn cols) = P + children(lower), U(lower) = P_aa + children
+__global__ void big_llt_store_kernel(BigArgs r, const double *__restrict__ P, double *__restrict__ blk, double *__restrict__ U) {
+    const int nj = r.nj, nn = r.nn, na = r.na;
+    BIG_LOOP((long long)nj * nj) {
+        const int i = (int)(idx % nj), j = (int)(idx / nj);
+        if (j < nn) {
+            blk[i + (long long)j * nj] = (i >= j) ? P[idx] + big_children(r, i, j, true) : 0.0;
+        } else if (i >= j) {
+            U[(i - nn) + (long long)(j - nn) * na] = P[idx] + big_children(r, i, j, true);
+        }
+    }
+}
+
+// T (n x n, ld ldt) <- full symmetric copy of the lower-stored n x n block S (ld lds)
+__global__ void big_sym_copy_kernel(const double *__restrict__ S, long long lds, double *__restrict__ T, long long ldt, int n) {
+    BIG_LOOP((long long)n * n) {
+        const int i = (int)(idx % n), j = (int)(idx / n);
+        T[i + (long long)j * ldt] = (i >= j) ? S[i + (long long)j * lds] : S[j + (long long)i * lds];
+    }
+}
+
+// blk_nn (lower, ld nj) = alpha * blk_nn + beta * 0.5 (T(i,j) + T(j,i)) ; upper <- 0
+__global__ void big_sym_store_kernel(const double *__restrict__ T, long long ldt, double *__restrict__ blk, long long ldb, int n, double alpha, double beta) {
+    BIG_LOOP((long long)n * n) {
+        const int i = (int)(idx % n), j = (int)(idx / n);
+        double *d = blk + i + (long long)j * ldb;
+        if (i >= j) {
+            const double t = 0.5 * (T[i + (long long)j * ldt] + T[j + (long long)i * ldt]);
+            *d = (alpha != 0.0 ? alpha * *d : 0.0) + beta * t;
+        } else *d = 0.0;
+    }
+}
+
+// B (cols x rows, ld ldb) = A^T, A rows x cols (ld lda)
+__global__ void big_transpose_kernel(const double *__restrict__ A, long long lda, int rows, int cols, double *__restrict__ Bt, long long ldb) {
+    __shared__ double tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = bx + threadIdx.x, j = by + r;
+        tile[r][threadIdx.x] = (i < rows && j < cols) ? A[i + (long long)j * lda] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = by + threadIdx.x, j = bx + r;      // Bt(i, j) = A(j, i)
+        if (i < cols && j < rows) Bt[i + (long long)j * ldb] = tile[threadIdx.x][r];
+    }
+}
+
+__global__ void big_identity_kernel(double *A, long long lda, int n) {
+    BIG_LOOP((long long)n * n) {
+        const int i = (int)(idx % n), j = (int)(idx / n);
+        A[i + (long long)j * lda] = (i == j) ? 1.0 : 0.0;
+    }
+}
+
+// dst (na x na, ld na) = X[aaidx]: the alpha x alpha entries of the ancestors, full symmetric
+__global__ void big_gather_aa_kernel(const int *__restrict__ aaidx, const double *__restrict__ Xb, double *__restrict__ dst, long long total) {
+    BIG_LOOP(total) dst[idx] = Xb[aaidx[idx]];
+}
+
+// reversed symmetric copy (mode 0) and M = (P Lc P)^T (mode 1) for the "reverse" Cholesky of completion
+__global__ void big_reverse_kernel(const double *__restrict__ S, long long lds, double *__restrict__ T, int n, int mode) {
+    BIG_LOOP((long long)n * n) {
+        const int i = (int)(idx % n), j = (int)(idx / n);
+        if (mode == 0) {
+            const int ri = n - 1 - i, rj = n - 1 - j;
+            T[idx] = (ri >= rj) ? S[ri + (long long)rj * lds] : S[rj + (long long)ri * lds];
+        } else {
+            T[idx] = (i >= j) ? S[(n - 1 - j) + (long long)(n - 1 - i) * lds] : 0.0;
+        }
+    }
+}
+
+// inverse Hessian, final assembly: children (full) are added to (K_nn, F_an, F_aa)
+__global__ void big_hinv_store_kernel(BigArgs r, const double *__restrict__ Knn, const double *__restrict__ Fan, const double *__restrict__ Faa,
+                                      double *__restrict__ blk, double *__restrict__ U) {
+    const int nj = r.nj, nn = r.nn, na = r.na;
+    BIG_LOOP((long long)nj * nj) {
+        const int i = (int)(idx % nj), j = (int)(idx / nj);
+        if (j < nn) {
+            if (i < nn) {
+                if (i >= j) {
+                    const double a = Knn[i + (long long)j * nn] + big_children(r, i, j, false);
+                    const double b = Knn[j + (long long)i * nn] + big_children(r, j, i, false);
+                    blk[i + (long long)j * nj] = 0.5 * (a + b);
+                } else blk[i + (long long)j * nj] = 0.0;
+            } else {
+                blk[i + (long long)j * nj] = Fan[(i - nn) + (long long)j * na] + big_children(r, i, j, false);
+            }
+        } else if (i >= nn) {
+            U[(i - nn) + (long long)(j - nn) * na] = Faa[(i - nn) + (long long)(j - nn) * na] + big_children(r, i, j, false);
+        }
+    }
+}
+
+__global__ void big_flag_kernel(const int *info, int *fail) {
+    if (*info) *fail = 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static unsigned egrid(smcp_sym *s, long long total) {
+    long long g = (total + 255) / 256;
+    return (unsigned)std::max<long long>(1, std::min<long long>(g, (long long)s->ctx->num_sms * 8));
+}
+
+int big_setup(smcp_sym *s, const smcp_sym_desc *D) {
+    s->big.clear();
+    s->big_flag = nullptr;
+    const int nsn = (int)D->nsn;
+    if (nsn < 1) return 0;
+    // a supernode goes to the dense path when its share of a Hessian evaluation
+    // (4 nn^3 + 6 na nn^2 + 6 na^2 nn flops) is too much for one CTA;
+    // SMCP_B200_BIG_FLOPS overrides the threshold (0 disables the path), SMCP_B200_BIG_NJ adds a
+    // criterion on the front size (tests force tiny fronts through the dense path with it)
+    const char *envf = getenv("SMCP_B200_BIG_FLOPS"), *envn = getenv("SMCP_B200_BIG_NJ");
+    const double thr_flops = envf ? atof(envf) : 2.0e6;
+    const int thr_nj = envn ? atoi(envn) : 0;
+    if (thr_flops <= 0.0 && thr_nj <= 0) return 0;
+    std::vector<int> flag(nsn, 0);
+    bool any = false;
+    for (int k = 0; k < nsn; ++k) {
+        const double nj = (double)(D->rowptr[k + 1] - D->rowptr[k]), nn = (double)(D->snptr[k + 1] - D->snptr[k]), na = nj - nn;
+        const double fl = 4.0 * nn * nn * nn + 6.0 * na * nn * nn + 6.0 * na * na * nn;
+        if ((thr_flops > 0.0 && fl >= thr_flops) || (thr_nj > 0 && nj >= thr_nj)) { flag[k] = 1; any = true; }
+    }
+    if (!any) return 0;
+    // ancestor closure: post-order => parents have larger indices
+    for (int k = 0; k < nsn; ++k)
+        if (flag[k] && D->snpar[k] >= 0) flag[D->snpar[k]] = 1;
+    int max_nj_small = 1, max_nj_big = 1;
+    size_t inv_total = 0, ch_total = 0;
+    for (int k = 0; k < nsn; ++k) {
+        const int nj = (int)(D->rowptr[k + 1] - D->rowptr[k]);
+        if (flag[k]) {
+            max_nj_big = std::max(max_nj_big, nj);
+            const size_t nch = (size_t)(D->chptr[k + 1] - D->chptr[k]);
+            inv_total += nch * (size_t)nj;
+            ch_total += nch;
+        } else max_nj_small = std::max(max_nj_small, nj);
+    }
+    std::vector<int> inv(std::max<size_t>(1, inv_total), -1), ch(std::max<size_t>(1, ch_total), 0);
+    size_t io = 0, co = 0;
+    for (int k = 0; k < nsn; ++k) {
+        if (!flag[k]) continue;
+        BigNode b;
+        b.k = k;
+        b.nn = (int)(D->snptr[k + 1] - D->snptr[k]);
+        b.nj = (int)(D->rowptr[k + 1] - D->rowptr[k]);
+        b.na = b.nj - b.nn;
+        b.nch = (int)(D->chptr[k + 1] - D->chptr[k]);
+        b.boff = D->blkptr[k];
+        b.uoff = D->updptr[k];
+        b.inv_off = (long long)io;
+        b.ch_off = (long long)co;
+        for (int q = 0; q < b.nch; ++q) {
+            const int c = (int)D->chidx[D->chptr[k] + q];
+            ch[co + q] = c;
+            const int nac = (int)(D->relptr[c + 1] - D->relptr[c]);
+            for (int a = 0; a < nac; ++a) inv[io + (size_t)q * b.nj + D->relidx[D->relptr[c] + a]] = a;
+        }
+        io += (size_t)b.nch * b.nj;
+        co += b.nch;
+        s->big.push_back(b);
+    }
+    void *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, inv.size() * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(d, inv.data(), inv.size() * sizeof(int), cudaMemcpyHostToDevice));
+    s->allocs.push_back(d);
+    s->big_inv = (const int *)d;
+    CUDA_TRY(cudaMalloc(&d, ch.size() * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(d, ch.data(), ch.size() * sizeof(int), cudaMemcpyHostToDevice));
+    s->allocs.push_back(d);
+    s->big_ch = (const int *)d;
+    CUDA_TRY(cudaMalloc(&d, (size_t)nsn * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(d, flag.data(), (size_t)nsn * sizeof(int), cudaMemcpyHostToDevice));
+    s->allocs.push_back(d);
+    s->big_flag = (const int *)d;
+    CUDA_TRY(cudaMalloc(&d, (size_t)BIG_NWS * max_nj_big * max_nj_big * sizeof(double) + 64));
+    s->allocs.push_back(d);
+    s->big_ws = (double *)d;
+    s->big_ws_stride = (size_t)max_nj_big * max_nj_big;
+    CUDA_TRY(cudaMalloc(&d, 64));
+    s->allocs.push_back(d);
+    s->big_info = (int *)d;
+    s->max_nj_small = max_nj_small;
+    return 0;
+}
+
+static BigArgs big_args(smcp_sym *s, const BigNode &q, int64_t b) {
+    BigArgs r;
+    r.nn = q.nn; r.na = q.na; r.nj = q.nj; r.nch = q.nch;
+    r.ch = s->big_ch + q.ch_off;
+    r.inv = s->big_inv + q.inv_off;
+    r.na_all = s->d.na;
+    r.updptr = s->d.updptr;
+    r.ub = s->upd + (size_t)b * s->d.nupd;
+    return r;
+}
+
+#define WS(i) (s->big_ws + (size_t)(i) * s->big_ws_stride)
+#define ELEM(name, total, ...)                                                      \
+    do {                                                                            \
+        LaunchScope ls_(ctx, "front_elem");                                         \
+        name<<<egrid(s, (total)), 256, 0, ctx->stream>>>(__VA_ARGS__);              \
+    } while (0)
+
+static int big_transpose(smcp_sym *s, const double *A, int64_t lda, int rows, int cols, double *Bt, int64_t ldb) {
+    if (rows <= 0 || cols <= 0) return 0;
+    smcp_ctx *ctx = s->ctx;
+    dim3 grid((rows + 31) / 32, (cols + 31) / 32), block(32, 8);
+    LaunchScope ls(ctx, "front_elem");
+    big_transpose_kernel<<<grid, block, 0, ctx->stream>>>(A, lda, rows, cols, Bt, ldb);
+    return 0;
+}
+
+// C = [C +] alpha op(A) op(B)^T in launch_gemm's convention, family "front_gemm_dmma"
+static int G(smcp_sym *s, bool ta, bool tb, const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc,
+             int64_t M, int64_t N, int64_t K, double alpha, int acc, int tri = 0) {
+    if (M <= 0 || N <= 0) return 0;
+    if (K <= 0) {
+        if (acc) return 0;
+        smcp_ctx *ctx = s->ctx;
+        CUDA_TRY(cudaMemset2DAsync(C, (size_t)ldc * sizeof(double), 0, (size_t)M * sizeof(double), (size_t)N, ctx->stream));
+        return 0;
+    }
+    return launch_gemm(s->ctx, ta, tb, A, lda, B, ldb, C, ldc, M, N, K, alpha, acc, tri, 0, "front_gemm_dmma");
+}
+
+// ---- cholesky --------------------------------------------------------------------------
+int big_cholesky(smcp_sym *s, const BigNode &q, double *X, int64_t b) {
+    smcp_ctx *ctx = s->ctx;
+    const int nn = q.nn, na = q.na, nj = q.nj;
+    double *blk = X + (size_t)b * s->d.nblk + q.boff;
+    double *Uk = s->upd + (size_t)b * s->d.nupd + q.uoff;
+    double *F = WS(0);
+    ELEM(big_front_lower_kernel, (long long)nj * nj, big_args(s, q, b), blk, F);
+    if (d_potrf(ctx, F, nj, nj, nn, s->big_info, 0, 1)) return -1;
+    big_flag_kernel<<<1, 1, 0, ctx->stream>>>(s->big_info, s->fail + b);
+    ELEM(big_store_cols_kernel, (long long)nj * nn, F, blk, nn, nj);
+    if (na) ELEM(big_copy_mat_kernel, (long long)na * na, F + nn + (size_t)nn * nj, nj, Uk, na, na, na, 1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ---- llt -------------------------------------------------------------------------------
+int big_llt(smcp_sym *s, const BigNode &q, double *X, int64_t b) {
+    smcp_ctx *ctx = s->ctx;
+    const int nn = q.nn, nj = q.nj;
+    double *blk = X + (size_t)b * s->d.nblk + q.boff;
+    double *Uk = s->upd + (size_t)b * s->d.nupd + q.uoff;
+    double *P = WS(0);
+    if (G(s, false, false, blk, nj, blk, nj, P, nj, nj, nj, nn, 1.0, 0, 1)) return -1;      // P = L L^T (lower)
+    ELEM(big_llt_store_kernel, (long long)nj * nj, big_args(s, q, b), P, blk, Uk);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ---- forward Hessian, pass 1 + scaling ---------------------------------------------------
+int big_hess_up(smcp_sym *s, const BigNode &q, const double *Lt, const double *Yaa_all, double *X, int64_t b) {
+    smcp_ctx *ctx = s->ctx;
+    const int nn = q.nn, na = q.na, nj = q.nj;
+    double *blk = X + (size_t)b * s->d.nblk + q.boff;
+    double *Uk = s->upd + (size_t)b * s->d.nupd + q.uoff;
+    const double *Lb = Lt + q.boff, *Ltan = Lb + nn, *Yaa = Yaa_all + q.uoff;
+    double *F = WS(0), *T1 = WS(1), *T2 = WS(2);
+    double *Fan = F + nn, *Faa = F + nn + (size_t)nn * nj, *Fna = F + (size_t)nn * nj;
+    ELEM(big_front_full_kernel, (long long)nj * nj, big_args(s, q, b), blk, F);
+    if (na) {
+        // K_an = F_an - Lt F_nn
+        if (G(s, false, true, Ltan, nj, F, nj, Fan, nj, na, nn, nn, -1.0, 1)) return -1;
+        // U' = F_aa - Lt F_an(old)^T - K_an Lt^T ; F_na still holds F_an(old)^T
+        if (G(s, false, true, Ltan, nj, Fna, nj, Faa, nj, na, na, nn, -1.0, 1)) return -1;
+        if (G(s, false, false, Fan, nj, Ltan, nj, Faa, nj, na, na, nn, -1.0, 1)) return -1;
+        ELEM(big_copy_mat_kernel, (long long)na * na, Faa, nj, Uk, na, na, na, 0);
+    }
+    // M_nn = D^{-1} F_nn D^{-1}
+    if (d_trsm_left_lower(ctx, false, Lb, nj, nn, F, nj, nn)) return -1;          // L^-1 F
+    big_transpose(s, F, nj, nn, nn, T1, nn);
+    if (d_trsm_left_lower(ctx, false, Lb, nj, nn, T1, nn, nn)) return -1;         // L^-1 F L^-T
+    if (d_trsm_left_lower(ctx, true, Lb, nj, nn, T1, nn, nn)) return -1;          // L^-T (.)
+    big_transpose(s, T1, nn, nn, nn, T2, nn);
+    if (d_trsm_left_lower(ctx, true, Lb, nj, nn, T2, nn, nn)) return -1;          // D^-1 F D^-1
+    if (na) {
+        // M_an = Y_aa K_an D^{-1}: W = D^{-1} K_an^T, M_an = Y_aa W^T
+        double *W = T1;
+        big_transpose(s, Fan, nj, na, nn, W, nn);
+        if (d_trsm_left_lower(ctx, false, Lb, nj, nn, W, nn, na)) return -1;
+        if (d_trsm_left_lower(ctx, true, Lb, nj, nn, W, nn, na)) return -1;
+        if (G(s, false, false, Yaa, na, W, nn, blk + nn, nj, na, nn, na, 1.0, 0)) return -1;
+    }
+    ELEM(big_sym_store_kernel, (long long)nn * nn, T2, nn, blk, nj, nn, 0.0, 1.0);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ---- forward Hessian, pass 3 (root to leaves) --------------------------------------------
+int big_hess_down(smcp_sym *s, const BigNode &q, const double *Lt, double *X, int64_t b) {
+    smcp_ctx *ctx = s->ctx;
+    const int nn = q.nn, na = q.na, nj = q.nj;
+    if (!na) return 0;
+    double *Xb = X + (size_t)b * s->d.nblk;
+    double *blk = Xb + q.boff;
+    const double *Ltan = Lt + q.boff + nn;
+    double *Zaa = WS(0), *Mold = WS(1), *S = WS(2);
+    ELEM(big_gather_aa_kernel, (long long)na * na, s->d.aaidx + q.uoff, Xb, Zaa, (long long)na * na);
+    ELEM(big_copy_mat_kernel, (long long)na * nn, blk + nn, nj, Mold, na, na, nn, 0);
+    // Z_an = M_an - Z_aa Lt
+    if (G(s, false, true, Zaa, na, Ltan, nj, blk + nn, nj, na, nn, na, -1.0, 1)) return -1;
+    // S = Lt^T M_an(old) + Z_an^T Lt ; Z_nn = M_nn - sym(S)
+    if (G(s, true, true, Ltan, nj, Mold, na, S, nn, nn, nn, na, 1.0, 0)) return -1;
+    if (G(s, true, true, blk + nn, nj, Ltan, nj, S, nn, nn, nn, na, 1.0, 1)) return -1;
+    ELEM(big_sym_store_kernel, (long long)nn * nn, S, nn, blk, nj, nn, 1.0, -1.0);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ---- inverse Hessian ----------------------------------------------------------------------
+int big_hess_inv(smcp_sym *s, const BigNode &q, const double *Lt, const double *Raa_all, double *X, int64_t b) {
+    smcp_ctx *ctx = s->ctx;
+    const int nn = q.nn, na = q.na, nj = q.nj;
+    double *Xb = X + (size_t)b * s->d.nblk;
+    double *blk = Xb + q.boff;
+    double *Uk = s->upd + (size_t)b * s->d.nupd + q.uoff;
+    const double *Lb = Lt + q.boff, *Ltan = Lb + nn, *R = Raa_all + q.uoff;
+    double *D = WS(0), *Zaa = WS(1), *Man = WS(2), *Mnn = WS(3), *T = WS(4), *Kan = WS(5);
+    if (G(s, false, false, Lb, nj, Lb, nj, D, nn, nn, nn, nn, 1.0, 0)) return -1;                 // D = L L^T (full)
+    ELEM(big_sym_copy_kernel, (long long)nn * nn, blk, nj, Mnn, nn, nn);                          // Z_nn (full)
+    if (na) {
+        ELEM(big_gather_aa_kernel, (long long)na * na, s->d.aaidx + q.uoff, Xb, Zaa, (long long)na * na);
+        ELEM(big_copy_mat_kernel, (long long)na * nn, blk + nn, nj, Man, na, na, nn, 0);
+        if (G(s, false, true, Zaa, na, Ltan, nj, Man, na, na, nn, na, 1.0, 1)) return -1;          // M_an = Z_an + Z_aa Lt
+        if (G(s, true, true, Ltan, nj, blk + nn, nj, Mnn, nn, nn, nn, na, 1.0, 1)) return -1;      // += Lt^T Z_an
+        if (G(s, true, true, Man, na, Ltan, nj, Mnn, nn, nn, nn, na, 1.0, 1)) return -1;           // += M_an^T Lt
+    }
+    if (G(s, false, true, D, nn, Mnn, nn, T, nn, nn, nn, nn, 1.0, 0)) return -1;                   // D M
+    if (G(s, false, true, T, nn, D, nn, Mnn, nn, nn, nn, nn, 1.0, 0)) return -1;                   // K_nn = D M D
+    if (na) {
+        if (G(s, false, true, Man, na, D, nn, Kan, na, na, nn, nn, 1.0, 0)) return -1;             // M_an D
+        if (d_trsm_left_lower(ctx, false, R, na, na, Kan, na, nn)) return -1;                      // K_an = Y_aa^-1 M_an D
+        if (d_trsm_left_lower(ctx, true, R, na, na, Kan, na, nn)) return -1;
+        ELEM(big_copy_mat_kernel, (long long)na * nn, Kan, na, Man, na, na, nn, 0);
+        if (G(s, false, true, Ltan, nj, Mnn, nn, Man, na, na, nn, nn, 1.0, 1)) return -1;          // F_an = K_an + Lt K_nn
+        if (G(s, false, false, Ltan, nj, Kan, na, Zaa, na, na, na, nn, 1.0, 0)) return -1;         // F_aa = Lt K_an^T
+        if (G(s, false, false, Man, na, Ltan, nj, Zaa, na, na, na, nn, 1.0, 1)) return -1;         //      + F_an Lt^T
+    }
+    ELEM(big_hinv_store_kernel, (long long)nj * nj, big_args(s, q, b), Mnn, Man, Zaa, blk, Uk);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ---- projected inverse (root to leaves) ------------------------------------------------------
+int big_projinv(smcp_sym *s, const BigNode &q, double *X, int64_t b) {
+    smcp_ctx *ctx = s->ctx;
+    const int nn = q.nn, na = q.na, nj = q.nj;
+    double *Xb = X + (size_t)b * s->d.nblk;
+    double *blk = Xb + q.boff;
+    double *LtT = WS(0), *Li = WS(1), *Di = WS(2), *Yaa = WS(3), *S = WS(4);
+    if (na) {
+        big_transpose(s, blk + nn, nj, na, nn, LtT, nn);                                          // L_an^T
+        if (d_trsm_left_lower(ctx, true, blk, nj, nn, LtT, nn, na)) return -1;                      // Lt^T = L_nn^-T L_an^T
+    }
+    ELEM(big_identity_kernel, (long long)nn * nn, Li, nn, nn);
+    if (d_trsm_left_lower(ctx, false, blk, nj, nn, Li, nn, nn)) return -1;                          // L^-1
+    if (G(s, true, true, Li, nn, Li, nn, Di, nn, nn, nn, nn, 1.0, 0)) return -1;                    // D^-1 = L^-T L^-1 (full)
+    if (na) {
+        ELEM(big_gather_aa_kernel, (long long)na * na, s->d.aaidx + q.uoff, Xb, Yaa, (long long)na * na);
+        if (G(s, false, false, Yaa, na, LtT, nn, blk + nn, nj, na, nn, na, -1.0, 0)) return -1;     // Y_an = -Y_aa Lt
+        if (G(s, false, true, LtT, nn, blk + nn, nj, S, nn, nn, nn, na, 1.0, 0)) return -1;          // S = Lt^T Y_an
+        ELEM(big_copy_mat_kernel, (long long)nn * nn, Di, nn, blk, nj, nn, nn, 1);
+        ELEM(big_sym_store_kernel, (long long)nn * nn, S, nn, blk, nj, nn, 1.0, -1.0);              // Y_nn = D^-1 - sym(S)
+    } else {
+        ELEM(big_copy_mat_kernel, (long long)nn * nn, Di, nn, blk, nj, nn, nn, 1);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ---- completion (independent per supernode, out of place) ---------------------------------------
+int big_completion(smcp_sym *s, const BigNode &q, double *X, const double *Xin, int64_t b) {
+    smcp_ctx *ctx = s->ctx;
+    const int nn = q.nn, na = q.na, nj = q.nj;
+    const double *Xi = Xin + (size_t)b * s->d.nblk;
+    const double *bin = Xi + q.boff;
+    double *bout = X + (size_t)b * s->d.nblk + q.boff;
+    double *R = WS(0), *Z = WS(1), *Dl = WS(2), *T0 = WS(3), *M = WS(4), *Li = WS(5);
+    ELEM(big_sym_copy_kernel, (long long)nn * nn, bin, nj, Dl, nn, nn);
+    if (na) {
+        ELEM(big_gather_aa_kernel, (long long)na * na, s->d.aaidx + q.uoff, Xi, R, (long long)na * na);
+        if (d_potrf(ctx, R, na, na, na, s->big_info, 0, 1)) return -1;
+        big_flag_kernel<<<1, 1, 0, ctx->stream>>>(s->big_info, s->fail + b);
+        ELEM(big_copy_mat_kernel, (long long)na * nn, bin + nn, nj, Z, na, na, nn, 0);
+        if (d_trsm_left_lower(ctx, false, R, na, na, Z, na, nn)) return -1;                         // Z = R^-1 X_an
+        if (G(s, true, true, Z, na, Z, na, Dl, nn, nn, nn, na, -1.0, 1)) return -1;                 // Delta = X_nn - Z^T Z
+        if (d_trsm_left_lower(ctx, true, R, na, na, Z, na, nn)) return -1;                          // W = X_aa^-1 X_an
+    }
+    ELEM(big_reverse_kernel, (long long)nn * nn, Dl, nn, T0, nn, 0);
+    if (d_potrf(ctx, T0, nn, nn, nn, s->big_info, 0, 1)) return -1;
+    big_flag_kernel<<<1, 1, 0, ctx->stream>>>(s->big_info, s->fail + b);
+    ELEM(big_reverse_kernel, (long long)nn * nn, T0, nn, M, nn, 1);                                 // Delta = M^T M
+    ELEM(big_identity_kernel, (long long)nn * nn, Li, nn, nn);
+    if (d_trsm_left_lower(ctx, false, M, nn, nn, Li, nn, nn)) return -1;                            // L_nn = M^-1
+    ELEM(big_copy_mat_kernel, (long long)nn * nn, Li, nn, bout, nj, nn, nn, 1);
+    if (na && G(s, false, true, Z, na, Li, nn, bout + nn, nj, na, nn, nn, -1.0, 0)) return -1;      // L_an = -W L_nn
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ---- Hessian factor: Lt block and Y_aa ----------------------------------------------------------
+int big_hess_prep(smcp_sym *s, const BigNode &q, const double *L0, const double *Y0, double *Lt_out, double *Yaa_out) {
+    smcp_ctx *ctx = s->ctx;
+    const int nn = q.nn, na = q.na, nj = q.nj;
+    const double *Lb = L0 + q.boff;
+    double *Ob = Lt_out + q.boff;
+    ELEM(big_store_cols_kernel, (long long)nj * nn, Lb, Ob, nn, nj);
+    if (na) {
+        double *T = WS(0);
+        ELEM(big_gather_aa_kernel, (long long)na * na, s->d.aaidx + q.uoff, Y0, Yaa_out + q.uoff, (long long)na * na);
+        big_transpose(s, Lb + nn, nj, na, nn, T, nn);
+        if (d_trsm_left_lower(ctx, true, Ob, nj, nn, T, nn, na)) return -1;                          // (L_an L_nn^-1)^T
+        big_transpose(s, T, nn, nn, na, Ob + nn, nj);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int big_hess_prep_inv(smcp_sym *s, const BigNode &q, const double *Yaa_all, double *Raa_all) {
+    smcp_ctx *ctx = s->ctx;
+    const int na = q.na;
+    if (!na) return 0;
+    ELEM(big_copy_mat_kernel, (long long)na * na, Yaa_all + q.uoff, na, Raa_all + q.uoff, na, na, na, 0);
+    if (d_potrf(ctx, Raa_all + q.uoff, na, na, na, s->big_info, 0, 1)) return -1;
+    big_flag_kernel<<<1, 1, 0, ctx->stream>>>(s->big_info, s->fail);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}

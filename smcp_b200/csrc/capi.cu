@@ -259,9 +259,12 @@ extern "C" int smcp_sym_create(smcp_ctx *ctx, const smcp_sym_desc *D, smcp_sym *
     for (int i = 0; i < nsn; ++i) ts3[i] = i;
     if (upload_sched(s, nsn, tp3, ts3, dp3, di3, &s->flat)) return -1;
     s->h_root_boff = (long long)D->blkptr[nsn > 0 ? nsn - 1 : 0];
-    if (s->max_nj > 8 && root_setup(s, D)) return -1;
+    s->max_nj_small = s->max_nj;
+    // large frontal matrices: dense multi-CTA path; an explicit SMCP_B200_BIG_NJ also applies to
+    // tiny-clique patterns (tests), which then stay on the CTA-per-supernode kernels
+    if ((s->max_nj > 8 || getenv("SMCP_B200_BIG_NJ")) && big_setup(s, D)) return -1;
     // tiny cliques: warp-per-chain kernels (SMCP_B200_NO_SMALL=1 forces the CTA kernels)
-    if (s->max_nj <= 8 && !getenv("SMCP_B200_NO_SMALL") && small_setup(s, D, tp, ts, tp2, ts2)) return -1;
+    if (s->max_nj <= 8 && s->big.empty() && !getenv("SMCP_B200_NO_SMALL") && small_setup(s, D, tp, ts, tp2, ts2)) return -1;
 
     CUDA_TRY(cudaMalloc(&s->counter, 64));
     CUDA_TRY(cudaMemset(s->counter, 0, 64));

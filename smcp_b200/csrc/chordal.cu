@@ -54,6 +54,7 @@ __global__ void tree_kernel(TreeArgs a) {
         __threadfence();
         for (int p = a.T.task_ptr[t]; p < a.T.task_ptr[t + 1]; ++p) {
             if (a.T.task_sn[p] + 1 == a.skip_sn1) continue;      // dense root path (front.cu)
+            if (a.skipflag && a.skipflag[a.T.task_sn[p]]) continue;   // dense top-set path (bigfront.cu)
             Node q = node_of(a.S, a.T.task_sn[p]);
             if (OP == OP_CHOL) op_chol<false>(a, q, b);
             else if (OP == OP_LLT) op_llt<false>(a, q, b, ws);
@@ -77,8 +78,8 @@ __global__ void tree_kernel(TreeArgs a) {
 // ---------------------------------------------------------------------------------------
 static const size_t SMEM_WS_LIMIT = 200 * 1024;     // fronts up to nj = 79 stay in shared memory (227 KB per CTA on sm_100)
 
-static size_t ws_doubles(const smcp_sym *s) {
-    size_t nj = (size_t)s->max_nj;
+static size_t ws_doubles(const smcp_sym *s, bool skip_big) {
+    size_t nj = (size_t)(skip_big ? s->max_nj_small : s->max_nj);
     return 4 * nj * nj + 8;
 }
 
@@ -108,7 +109,7 @@ static int launch_tree(smcp_sym *s, TreeArgs &a, const TaskSched &T, int64_t bat
     a.done = s->done;
     a.epoch = ++s->epoch;
     a.fail = s->fail;
-    size_t wsd = ws_doubles(s);
+    size_t wsd = ws_doubles(s, a.skipflag != nullptr);
     size_t smem = wsd * sizeof(double);
     a.use_smem = smem <= SMEM_WS_LIMIT;
     auto kern = tree_kernel<OP>;
@@ -138,13 +139,13 @@ static int launch_tree(smcp_sym *s, TreeArgs &a, const TaskSched &T, int64_t bat
     return 0;
 }
 
-static int pick_threads(const smcp_sym *s) {
-    int nj = s->max_nj;
+static int pick_threads_nj(int nj) {
     if (nj <= 8) return 32;
     if (nj <= 16) return 64;
     if (nj <= 48) return 128;
     return 256;
 }
+static int pick_threads(const smcp_sym *s, bool skip_big = false) { return pick_threads_nj(skip_big ? s->max_nj_small : s->max_nj); }
 
 int fetch_fail(smcp_sym *s, int64_t batch, int32_t *info_host) {
     smcp_ctx *ctx = s->ctx;
@@ -153,8 +154,9 @@ int fetch_fail(smcp_sym *s, int64_t batch, int32_t *info_host) {
     return 0;
 }
 
-// single matrices (or a handful): the large root supernode goes to the dense kernels of front.cu
-static bool use_root(const smcp_sym *s, int64_t batch) { return s->big_root >= 0 && batch <= 4; }
+// single matrices (or a handful): the top set of large supernodes goes to the dense kernels of
+// bigfront.cu (after the tree kernel in leaves-to-root sweeps, before it in root-to-leaves sweeps)
+static bool use_big(const smcp_sym *s, int64_t batch) { return !s->big.empty() && batch <= 4; }
 
 int k_cholesky(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
     if (s->small) return ks_cholesky(s, x, batch, info_host);
@@ -163,11 +165,13 @@ int k_cholesky(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
     TreeArgs a = {};
     a.X = x;
     a.upd = s->upd;
-    if (use_root(s, batch)) a.skip_sn1 = s->big_root + 1;
-    if (launch_tree<OP_CHOL>(s, a, s->up, batch, pick_threads(s), batch > 1 ? "cholesky_batch" : "cholesky")) return -1;
-    if (use_root(s, batch))
+    const bool big = use_big(s, batch);
+    if (big) a.skipflag = s->big_flag;
+    if (launch_tree<OP_CHOL>(s, a, s->up, batch, pick_threads(s, big), batch > 1 ? "cholesky_batch" : "cholesky")) return -1;
+    if (big)
         for (int64_t b = 0; b < batch; ++b)
-            if (root_cholesky(s, x, b)) return -1;
+            for (const BigNode &q : s->big)
+                if (big_cholesky(s, q, x, b)) return -1;
     if (info_host) return fetch_fail(s, batch, info_host);
     return 0;
 }
@@ -178,11 +182,13 @@ int k_llt(smcp_sym *s, double *x, int64_t batch) {
     TreeArgs a = {};
     a.X = x;
     a.upd = s->upd;
-    if (use_root(s, batch)) a.skip_sn1 = s->big_root + 1;
-    if (launch_tree<OP_LLT>(s, a, s->up, batch, pick_threads(s), "llt")) return -1;
-    if (use_root(s, batch))
+    const bool big = use_big(s, batch);
+    if (big) a.skipflag = s->big_flag;
+    if (launch_tree<OP_LLT>(s, a, s->up, batch, pick_threads(s, big), "llt")) return -1;
+    if (big)
         for (int64_t b = 0; b < batch; ++b)
-            if (root_llt(s, x, b)) return -1;
+            for (const BigNode &q : s->big)
+                if (big_llt(s, q, x, b)) return -1;
     return 0;
 }
 
@@ -191,12 +197,14 @@ int k_projinv(smcp_sym *s, double *x, int64_t batch) {
     if (sym_ensure(s, batch, false)) return -1;
     TreeArgs a = {};
     a.X = x;
-    if (use_root(s, batch)) {
-        a.skip_sn1 = s->big_root + 1;
+    const bool big = use_big(s, batch);
+    if (big) {
+        a.skipflag = s->big_flag;
         for (int64_t b = 0; b < batch; ++b)
-            if (root_projinv(s, x, b)) return -1;
+            for (auto it = s->big.rbegin(); it != s->big.rend(); ++it)
+                if (big_projinv(s, *it, x, b)) return -1;
     }
-    return launch_tree<OP_PROJINV>(s, a, s->down, batch, pick_threads(s), "projected_inverse");
+    return launch_tree<OP_PROJINV>(s, a, s->down, batch, pick_threads(s, big), "projected_inverse");
 }
 
 static TaskSched flat_sched(const smcp_sym *s) { return s->flat; }
@@ -210,11 +218,13 @@ int k_completion(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
     TreeArgs a = {};
     a.X = x;
     a.Xin = s->tmp;
-    if (use_root(s, batch)) a.skip_sn1 = s->big_root + 1;
-    if (launch_tree<OP_COMPL>(s, a, flat_sched(s), batch, pick_threads(s), batch > 1 ? "completion_batch" : "completion")) return -1;
-    if (use_root(s, batch))
+    const bool big = use_big(s, batch);
+    if (big) a.skipflag = s->big_flag;
+    if (launch_tree<OP_COMPL>(s, a, flat_sched(s), batch, pick_threads(s, big), batch > 1 ? "completion_batch" : "completion")) return -1;
+    if (big)
         for (int64_t b = 0; b < batch; ++b)
-            if (root_completion(s, x, s->tmp, b)) return -1;
+            for (const BigNode &q : s->big)
+                if (big_completion(s, q, x, s->tmp, b)) return -1;
     if (info_host) return fetch_fail(s, batch, info_host);
     return 0;
 }
@@ -228,7 +238,13 @@ int k_hess_prep(smcp_hess *h, const double *L, const double *Y) {
     a.Y0 = Y;
     a.Lt_out = h->Lt;
     a.Yaa_out = h->Yaa;
-    return launch_tree<OP_HPREP>(s, a, flat_sched(s), 1, pick_threads(s), "hessian_prep");
+    const bool big = use_big(s, 1);
+    if (big) a.skipflag = s->big_flag;
+    if (launch_tree<OP_HPREP>(s, a, flat_sched(s), 1, pick_threads(s, big), "hessian_prep")) return -1;
+    if (big)
+        for (const BigNode &q : s->big)
+            if (big_hess_prep(s, q, L, Y, h->Lt, h->Yaa)) return -1;
+    return 0;
 }
 
 int k_hess_prep_inv(smcp_hess *h) {
@@ -239,7 +255,13 @@ int k_hess_prep_inv(smcp_hess *h) {
     TreeArgs a = {};
     a.Yaa = h->Yaa;
     a.Raa = h->Raa;
-    return launch_tree<OP_HPREP_INV>(s, a, flat_sched(s), 1, pick_threads(s), "hessian_prep_inv");
+    const bool big = use_big(s, 1);
+    if (big) a.skipflag = s->big_flag;
+    if (launch_tree<OP_HPREP_INV>(s, a, flat_sched(s), 1, pick_threads(s, big), "hessian_prep_inv")) return -1;
+    if (big)
+        for (const BigNode &q : s->big)
+            if (big_hess_prep_inv(s, q, h->Yaa, h->Raa)) return -1;
+    return 0;
 }
 
 int k_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
@@ -252,24 +274,30 @@ int k_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
     a.Lt = h->Lt;
     a.Yaa = h->Yaa;
     a.Raa = h->Raa;
-    int threads = pick_threads(s);
-    if (use_root(s, batch)) a.skip_sn1 = s->big_root + 1;
+    const bool big = use_big(s, batch);
+    if (big) a.skipflag = s->big_flag;
+    int threads = pick_threads(s, big);
     if (!inv) {
-        const bool big = batch >= 32;
-        if (launch_tree<OP_HFWD_UP>(s, a, s->up, batch, threads, big ? "hessian_up_batch" : "hessian_up")) return -1;
-        if (use_root(s, batch))
-            for (int64_t b = 0; b < batch; ++b)
-                if (root_hess_up(s, h->Lt, U, b)) return -1;
-        return launch_tree<OP_HFWD_DOWN>(s, a, s->down, batch, threads, big ? "hessian_down_batch" : "hessian_down");
+        const bool many = batch >= 32;
+        if (launch_tree<OP_HFWD_UP>(s, a, s->up, batch, threads, many ? "hessian_up_batch" : "hessian_up")) return -1;
+        if (big)
+            for (int64_t b = 0; b < batch; ++b) {
+                for (const BigNode &q : s->big)
+                    if (big_hess_up(s, q, h->Lt, h->Yaa, U, b)) return -1;
+                for (auto it = s->big.rbegin(); it != s->big.rend(); ++it)
+                    if (big_hess_down(s, *it, h->Lt, U, b)) return -1;
+            }
+        return launch_tree<OP_HFWD_DOWN>(s, a, s->down, batch, threads, many ? "hessian_down_batch" : "hessian_down");
     }
     if (!h->have_Raa) {
         if (k_hess_prep_inv(h)) return -1;
         h->have_Raa = true;
     }
     if (launch_tree<OP_HINV>(s, a, s->up, batch, threads, batch >= 32 ? "hessian_inv_batch" : "hessian_inv")) return -1;
-    if (use_root(s, batch))
+    if (big)
         for (int64_t b = 0; b < batch; ++b)
-            if (root_hess_inv(s, h->Lt, U, b)) return -1;
+            for (const BigNode &q : s->big)
+                if (big_hess_inv(s, q, h->Lt, h->Raa, U, b)) return -1;
     return 0;
 }
 

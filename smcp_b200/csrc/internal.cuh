@@ -94,6 +94,14 @@ struct SmallDev {
     int nwide;
 };
 
+// A supernode of the "top set" processed by the dense multi-CTA path (bigfront.cu)
+struct BigNode {
+    int k, nn, na, nj, nch;
+    long long boff, uoff;        // offsets of its block in blkval and of its update matrix
+    long long inv_off, ch_off;   // offsets into big_inv (nch x nj) and big_ch (nch)
+};
+#define BIG_NWS 6                // nj x nj workspaces of the dense path
+
 struct smcp_sym {
     smcp_ctx *ctx;
     SymDev d;
@@ -132,6 +140,13 @@ struct smcp_sym {
     double *root_ws = nullptr;       // 3 x nn x nn
     int *root_info = nullptr;
     long long h_root_boff = 0;
+    // top set of large supernodes (and their ancestors) processed by dense kernels for single matrices (bigfront.cu)
+    std::vector<BigNode> big;    // ascending supernode index = post-order
+    const int *big_flag = nullptr, *big_inv = nullptr, *big_ch = nullptr;
+    double *big_ws = nullptr;
+    size_t big_ws_stride = 0;
+    int *big_info = nullptr;
+    int max_nj_small = 0;        // largest frontal matrix left to the tree kernels when the top set is skipped
     // host copies used by the operator setup
     std::vector<int> h_vec2blk;
     std::vector<int64_t> h_snptr;
@@ -179,6 +194,18 @@ int k_sumlogdiag(smcp_sym *s, const double *x, int64_t batch, double *out_host);
 int k_scatter_vec(smcp_sym *s, double *dst, const double *dev_vec);
 int k_gather_vec(smcp_sym *s, const double *src, double *dev_vec);
 int k_axpy_batch(smcp_sym *s, const double *x, const double *dx, const double *gam_dev, double *out, int64_t count);
+
+// dense path for the top set of large supernodes (bigfront.cu)
+int big_setup(smcp_sym *s, const smcp_sym_desc *D);
+int big_cholesky(smcp_sym *s, const BigNode &q, double *X, int64_t b);
+int big_llt(smcp_sym *s, const BigNode &q, double *X, int64_t b);
+int big_hess_up(smcp_sym *s, const BigNode &q, const double *Lt, const double *Yaa_all, double *X, int64_t b);
+int big_hess_down(smcp_sym *s, const BigNode &q, const double *Lt, double *X, int64_t b);
+int big_hess_inv(smcp_sym *s, const BigNode &q, const double *Lt, const double *Raa_all, double *X, int64_t b);
+int big_projinv(smcp_sym *s, const BigNode &q, double *X, int64_t b);
+int big_completion(smcp_sym *s, const BigNode &q, double *X, const double *Xin, int64_t b);
+int big_hess_prep(smcp_sym *s, const BigNode &q, const double *L0, const double *Y0, double *Lt_out, double *Yaa_out);
+int big_hess_prep_inv(smcp_sym *s, const BigNode &q, const double *Yaa_all, double *Raa_all);
 
 // dense root supernode (front.cu)
 int root_setup(smcp_sym *s, const smcp_sym_desc *D);

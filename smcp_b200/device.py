@@ -255,7 +255,19 @@ class DeviceBackend:
         h = C.c_void_p()
         _ck(lib, lib.smcp_sym_create(self.ctx.h, C.byref(d), C.byref(h)))
         self.sym = h
-        if symb.nblk * 255 * 8 <= (1 << 30):
+        # patterns with large frontal matrices: single-matrix operations go to the dense multi-CTA
+        # path (csrc/bigfront.cu), so the 8 probes of a bisection run one after the other through
+        # it instead of as one 255-candidate batch through the CTA-per-supernode kernels
+        # (same rule as big_setup in csrc/bigfront.cu)
+        nj = np.diff(symb.rowptr).astype(np.float64)
+        nn = np.diff(symb.snptr).astype(np.float64)
+        na = nj - nn
+        fl = 4.0 * nn ** 3 + 6.0 * na * nn ** 2 + 6.0 * na ** 2 * nn
+        thr_flops = float(os.environ.get("SMCP_B200_BIG_FLOPS", "2e6"))
+        thr_nj = int(os.environ.get("SMCP_B200_BIG_NJ", "0"))
+        has_big = symb.nsn > 0 and ((thr_flops > 0 and fl.max() >= thr_flops) or (thr_nj > 0 and nj.max() >= thr_nj))
+        self.batched_probes = not (has_big and (nj.max() > 8 or thr_nj > 0))
+        if self.batched_probes and symb.nblk * 255 * 8 <= (1 << 30):
             # workspaces of the batched line-search probes (255 candidates) sized at setup time
             _ck(lib, lib.smcp_sym_reserve(h, 255))
         self._pool = []

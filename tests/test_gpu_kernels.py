@@ -24,9 +24,13 @@ def _cases():
             # task partition that cuts the tree into many tasks (cross-warp hand-off)
             out.append(p + ("cta",))
             out.append(p + ("split",))
-        if p[3] in (0, 1, 3, 6):
-            # general trees: also with the dense multi-CTA root path forced on small roots
-            out.append(p + ("bigroot",))
+        if p[3] in (0, 1, 3, 6, 14):
+            # general trees: also with the dense multi-CTA path (bigfront.cu) forced on every
+            # supernode with >= 3 rows (and all their ancestors), separators included ...
+            out.append(p + ("bigtop3",))
+        if p[3] in (0, 1, 6, 14):
+            # ... and with a threshold that splits the tree between the two code paths
+            out.append(p + ("bigtop6",))
         if p[1] == 0 and p[2] >= 1:
             # band patterns: chain clique trees take the segment-parallel kernels by default;
             # keep the warp-per-chain sweeps covered on them as well
@@ -45,14 +49,14 @@ def setup(request):
         os.environ["SMCP_B200_NO_SMALL"] = "1"
     if mode == "nochain":
         os.environ["SMCP_B200_NO_CHAIN"] = "1"
-    if mode == "bigroot":
-        os.environ["SMCP_B200_BIG_NN"] = "3"
+    if mode.startswith("bigtop"):
+        os.environ["SMCP_B200_BIG_NJ"] = mode[6:]
     try:
         dev = DeviceBackend(symb, small_work=0 if mode == "split" else 2000)
     finally:
         os.environ.pop("SMCP_B200_NO_SMALL", None)
         os.environ.pop("SMCP_B200_NO_CHAIN", None)
-        os.environ.pop("SMCP_B200_BIG_NN", None)
+        os.environ.pop("SMCP_B200_BIG_NJ", None)
     s = random_pd(symb, seed)
     l = s.copy()
     sn.cholesky(symb, l)
