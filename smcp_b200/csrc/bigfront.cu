@@ -528,3 +528,191 @@ int big_hess_prep_inv(smcp_sym *s, const BigNode &q, const double *Yaa_all, doub
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------
+// Batched forward Hessian over the top set (Schur assembly with dense constraints: hundreds of
+// matrices at ONE scaling point).  L and Y are shared by the batch, so every triangular solve
+// runs on the concatenated right-hand sides (nn x nn*B) and every product is a strided batched
+// DMMA GEMM with a shared operand; the elementwise steps carry the matrix index in blockIdx.y.
+// ---------------------------------------------------------------------------------------
+__global__ void big_front_full_b_kernel(BigArgs r, long long nupd, const double *__restrict__ X, long long nblk, long long boff,
+                                        double *__restrict__ F, long long sF) {
+    const int nj = r.nj, nn = r.nn;
+    const long long b = blockIdx.y;
+    r.ub += b * nupd;
+    const double *blk = X + b * nblk + boff;
+    double *Fb = F + b * sF;
+    BIG_LOOP((long long)nj * nj) {
+        const int i = (int)(idx % nj), j = (int)(idx / nj);
+        const int hi = max(i, j), lo = min(i, j);
+        double v = (lo < nn) ? blk[hi + (long long)lo * nj] : 0.0;
+        Fb[idx] = v + big_children(r, i, j, false);
+    }
+}
+
+__global__ void big_copy_b_kernel(const double *__restrict__ S, long long lds, long long sS, double *__restrict__ U, long long ldu, long long sU,
+                                  int rows, int cols) {
+    const long long b = blockIdx.y;
+    S += b * sS;
+    U += b * sU;
+    BIG_LOOP((long long)rows * cols) {
+        const int i = (int)(idx % rows), j = (int)(idx / rows);
+        U[i + (long long)j * ldu] = S[i + (long long)j * lds];
+    }
+}
+
+__global__ void big_transpose_b_kernel(const double *__restrict__ A, long long lda, long long sA, int rows, int cols,
+                                       double *__restrict__ Bt, long long ldb, long long sB) {
+    __shared__ double tile[32][33];
+    A += (long long)blockIdx.z * sA;
+    Bt += (long long)blockIdx.z * sB;
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = bx + threadIdx.x, j = by + r;
+        tile[r][threadIdx.x] = (i < rows && j < cols) ? A[i + (long long)j * lda] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = by + threadIdx.x, j = bx + r;
+        if (i < cols && j < rows) Bt[i + (long long)j * ldb] = tile[threadIdx.x][r];
+    }
+}
+
+__global__ void big_sym_store_b_kernel(const double *__restrict__ T, long long ldt, long long sT, double *__restrict__ blk, long long ldb, long long sB,
+                                       int n, double alpha, double beta) {
+    const long long b = blockIdx.y;
+    T += b * sT;
+    blk += b * sB;
+    BIG_LOOP((long long)n * n) {
+        const int i = (int)(idx % n), j = (int)(idx / n);
+        double *d = blk + i + (long long)j * ldb;
+        if (i >= j) {
+            const double t = 0.5 * (T[i + (long long)j * ldt] + T[j + (long long)i * ldt]);
+            *d = (alpha != 0.0 ? alpha * *d : 0.0) + beta * t;
+        } else *d = 0.0;
+    }
+}
+
+__global__ void big_gather_aa_b_kernel(const int *__restrict__ aaidx, const double *__restrict__ X, long long nblk, double *__restrict__ dst,
+                                       long long sD, long long total) {
+    const long long b = blockIdx.y;
+    const double *Xb = X + b * nblk;
+    double *d = dst + b * sD;
+    BIG_LOOP(total) d[idx] = Xb[aaidx[idx]];
+}
+
+static dim3 egrid_b(smcp_sym *s, long long total, int64_t nb) {
+    long long g = (total + 255) / 256;
+    g = std::max<long long>(1, std::min<long long>(g, (long long)s->ctx->num_sms * 4));
+    return dim3((unsigned)g, (unsigned)nb);
+}
+#define ELEMB(name, total, nb, ...)                                                  \
+    do {                                                                             \
+        LaunchScope ls_(ctx, "front_elem_batch");                                    \
+        name<<<egrid_b(s, (total), (nb)), 256, 0, ctx->stream>>>(__VA_ARGS__);       \
+    } while (0)
+
+static int big_transpose_b(smcp_sym *s, const double *A, int64_t lda, int64_t sA, int rows, int cols, double *Bt, int64_t ldb, int64_t sB, int64_t nb) {
+    if (rows <= 0 || cols <= 0) return 0;
+    smcp_ctx *ctx = s->ctx;
+    for (int64_t z0 = 0; z0 < nb; z0 += 32768) {
+        const int64_t nz = std::min<int64_t>(32768, nb - z0);
+        dim3 grid((rows + 31) / 32, (cols + 31) / 32, (unsigned)nz), block(32, 8);
+        LaunchScope ls(ctx, "front_elem_batch");
+        big_transpose_b_kernel<<<grid, block, 0, ctx->stream>>>(A + z0 * sA, lda, sA, rows, cols, Bt + z0 * sB, ldb, sB);
+    }
+    return 0;
+}
+
+static int GB(smcp_sym *s, bool ta, bool tb, const double *A, int64_t lda, int64_t sA, const double *B, int64_t ldb, int64_t sB,
+              double *C, int64_t ldc, int64_t sC, int64_t M, int64_t N, int64_t K, double alpha, int acc, int64_t nb) {
+    return launch_gemm_batched(s->ctx, ta, tb, A, lda, sA, B, ldb, sB, C, ldc, sC, M, N, K, alpha, acc, nb, "front_gemm_dmma_batch");
+}
+
+// the elementwise kernels take the matrix index from blockIdx.y (<= 65535)
+static const int64_t BIG_BATCH_MAX = 32768;
+
+static int big_hess_up_batched(smcp_sym *s, const BigNode &q, const double *Lt, const double *Yaa_all, double *X, int64_t nb,
+                               double *W, size_t sW) {
+    smcp_ctx *ctx = s->ctx;
+    const int nn = q.nn, na = q.na, nj = q.nj;
+    const long long nblk = s->d.nblk, nupd = s->d.nupd;
+    const double *Lb = Lt + q.boff, *Ltan = Lb + nn, *Yaa = Yaa_all + q.uoff;
+    // per matrix: F (nj^2) | T1 (nn * max(nn, na)) | T2 (nn^2), stride sW
+    double *F = W, *T1 = W + (size_t)nj * nj, *T2 = T1 + (size_t)nn * std::max(nn, na);
+    double *Fan = F + nn, *Faa = F + nn + (size_t)nn * nj, *Fna = F + (size_t)nn * nj;
+    ELEMB(big_front_full_b_kernel, (long long)nj * nj, nb, big_args(s, q, 0), nupd, X, nblk, q.boff, F, (long long)sW);
+    if (na) {
+        if (GB(s, false, true, Ltan, nj, 0, F, nj, sW, Fan, nj, sW, na, nn, nn, -1.0, 1, nb)) return -1;       // K_an = F_an - Lt F_nn
+        if (GB(s, false, true, Ltan, nj, 0, Fna, nj, sW, Faa, nj, sW, na, na, nn, -1.0, 1, nb)) return -1;     // U' = F_aa - Lt F_an(old)^T
+        if (GB(s, false, false, Fan, nj, sW, Ltan, nj, 0, Faa, nj, sW, na, na, nn, -1.0, 1, nb)) return -1;    //      - K_an Lt^T
+        ELEMB(big_copy_b_kernel, (long long)na * na, nb, Faa, nj, (long long)sW, s->upd + q.uoff, na, nupd, na, na);
+    }
+    // M_nn = D^{-1} F_nn D^{-1} on the concatenated nn x (nn * nb) right-hand sides: compact copies first
+    // (T2 blocks are contiguous only when sW == nn*nn, so the concatenation lives in its own buffer)
+    double *C1 = s->big_cat, *C2 = s->big_cat + (size_t)nn * std::max(nn, na) * nb;
+    ELEMB(big_copy_b_kernel, (long long)nn * nn, nb, F, nj, (long long)sW, C2, nn, (long long)nn * nn, nn, nn);
+    if (d_trsm_left_lower(ctx, false, Lb, nj, nn, C2, nn, (int64_t)nn * nb)) return -1;          // L^-1 F
+    big_transpose_b(s, C2, nn, (int64_t)nn * nn, nn, nn, C1, nn, (int64_t)nn * nn, nb);
+    if (d_trsm_left_lower(ctx, false, Lb, nj, nn, C1, nn, (int64_t)nn * nb)) return -1;          // L^-1 F L^-T
+    if (d_trsm_left_lower(ctx, true, Lb, nj, nn, C1, nn, (int64_t)nn * nb)) return -1;           // L^-T (.)
+    big_transpose_b(s, C1, nn, (int64_t)nn * nn, nn, nn, C2, nn, (int64_t)nn * nn, nb);
+    if (d_trsm_left_lower(ctx, true, Lb, nj, nn, C2, nn, (int64_t)nn * nb)) return -1;           // D^-1 F D^-1
+    if (na) {
+        // M_an = Y_aa K_an D^{-1}: W = D^{-1} K_an^T (nn x na per matrix, concatenated), M_an = Y_aa W^T
+        big_transpose_b(s, Fan, nj, (int64_t)sW, na, nn, C1, nn, (int64_t)nn * na, nb);
+        if (d_trsm_left_lower(ctx, false, Lb, nj, nn, C1, nn, (int64_t)na * nb)) return -1;
+        if (d_trsm_left_lower(ctx, true, Lb, nj, nn, C1, nn, (int64_t)na * nb)) return -1;
+        if (GB(s, false, false, Yaa, na, 0, C1, nn, (int64_t)nn * na, X + q.boff + nn, nj, nblk, na, nn, na, 1.0, 0, nb)) return -1;
+    }
+    ELEMB(big_sym_store_b_kernel, (long long)nn * nn, nb, C2, nn, (long long)nn * nn, X + q.boff, nj, nblk, nn, 0.0, 1.0);
+    (void)T1; (void)T2;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int big_hess_down_batched(smcp_sym *s, const BigNode &q, const double *Lt, double *X, int64_t nb, double *W, size_t sW) {
+    smcp_ctx *ctx = s->ctx;
+    const int nn = q.nn, na = q.na, nj = q.nj;
+    if (!na) return 0;
+    const long long nblk = s->d.nblk;
+    const double *Ltan = Lt + q.boff + nn;
+    // per matrix (stride sW): Zaa (na^2) | Mold (na*nn) | S (nn^2)  -- all within 3 nj^2
+    double *Zaa = W, *Mold = W + (size_t)na * na, *S = Mold + (size_t)na * nn;
+    double *blk = X + q.boff;
+    ELEMB(big_gather_aa_b_kernel, (long long)na * na, nb, s->d.aaidx + q.uoff, X, nblk, Zaa, (long long)sW, (long long)na * na);
+    ELEMB(big_copy_b_kernel, (long long)na * nn, nb, blk + nn, nj, nblk, Mold, na, (long long)sW, na, nn);
+    if (GB(s, false, true, Zaa, na, sW, Ltan, nj, 0, blk + nn, nj, nblk, na, nn, na, -1.0, 1, nb)) return -1;        // Z_an = M_an - Z_aa Lt
+    if (GB(s, true, true, Ltan, nj, 0, Mold, na, sW, S, nn, sW, nn, nn, na, 1.0, 0, nb)) return -1;                  // S = Lt^T M_an(old)
+    if (GB(s, true, true, blk + nn, nj, nblk, Ltan, nj, 0, S, nn, sW, nn, nn, na, 1.0, 1, nb)) return -1;            //   + Z_an^T Lt
+    ELEMB(big_sym_store_b_kernel, (long long)nn * nn, nb, S, nn, (long long)sW, blk, nj, nblk, nn, 1.0, -1.0);        // Z_nn = M_nn - sym(S)
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// top-set part of a batched forward Hessian: called between the two tree-kernel sweeps
+int big_hess_fwd_batched(smcp_sym *s, const double *Lt, const double *Yaa_all, double *U, int64_t batch) {
+    int max_nj = 1;
+    for (const BigNode &q : s->big) max_nj = std::max(max_nj, q.nj);
+    const size_t sW = (size_t)3 * max_nj * max_nj;
+    int64_t chunk = (int64_t)std::max<size_t>(1, ((size_t)3 << 30) / (sW * sizeof(double)));
+    chunk = std::min<int64_t>(std::min<int64_t>(chunk, batch), BIG_BATCH_MAX);
+    if (grow((void **)&s->big_bws, &s->big_bws_cap, (size_t)chunk * sW * sizeof(double))) return -1;
+    if (grow((void **)&s->big_cat, &s->big_cat_cap, (size_t)chunk * 2 * (size_t)max_nj * max_nj * sizeof(double))) return -1;
+    for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
+        const int64_t nb = std::min(chunk, batch - b0);
+        double *Ub = U + (size_t)b0 * s->d.nblk;
+        // the children's update matrices of matrix b0 + b start at upd + (b0 + b) * nupd
+        double *upd_saved = s->upd;
+        s->upd = upd_saved + (size_t)b0 * s->d.nupd;
+        int rc = 0;
+        for (const BigNode &q : s->big)
+            if ((rc = big_hess_up_batched(s, q, Lt, Yaa_all, Ub, nb, s->big_bws, sW))) break;
+        if (!rc)
+            for (auto it = s->big.rbegin(); it != s->big.rend(); ++it)
+                if ((rc = big_hess_down_batched(s, *it, Lt, Ub, nb, s->big_bws, sW))) break;
+        s->upd = upd_saved;
+        if (rc) return rc;
+    }
+    return 0;
+}

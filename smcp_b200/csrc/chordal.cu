@@ -22,6 +22,7 @@
 //    order (bitwise reproducible; no floating-point atomics anywhere).
 #include "internal.cuh"
 #include <cstdio>
+#include <cstdlib>
 
 #include "chordal_ops.cuh"
 
@@ -274,12 +275,16 @@ int k_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
     a.Lt = h->Lt;
     a.Yaa = h->Yaa;
     a.Raa = h->Raa;
+    // forward map on a batch (Schur assembly): the top set goes to the batched dense path
+    static const bool allow_bb = !(getenv("SMCP_B200_NO_BIG_BATCH") && atoi(getenv("SMCP_B200_NO_BIG_BATCH")) != 0);
+    const bool bigb = !inv && !s->big.empty() && batch > 4 && allow_bb;
     const bool big = use_big(s, batch);
-    if (big) a.skipflag = s->big_flag;
-    int threads = pick_threads(s, big);
+    if (big || bigb) a.skipflag = s->big_flag;
+    int threads = pick_threads(s, big || bigb);
     if (!inv) {
         const bool many = batch >= 32;
         if (launch_tree<OP_HFWD_UP>(s, a, s->up, batch, threads, many ? "hessian_up_batch" : "hessian_up")) return -1;
+        if (bigb && big_hess_fwd_batched(s, h->Lt, h->Yaa, U, batch)) return -1;
         if (big)
             for (int64_t b = 0; b < batch; ++b) {
                 for (const BigNode &q : s->big)

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_dmma_kernel(const double *__restrict__ A, long long lda, const double *__restrict__ B, long long ldb,
                  double *__restrict__ C, long long ldc, long long M, long long N, long long K, double alpha,
                  int accumulate, int tri, long long tri_off, long long kchunk, long long split_stride,
-                 int jt0, int jtstride) {
+                 int jt0, int jtstride, long long bsA, long long bsB, int batched) {
     extern __shared__ double smem[];
     double *As = smem;                              // STAGES x 128 x LDK
     double *Bs = smem + STAGES * 128 * LDK;
@@ -85,10 +85,15 @@ gemm_dmma_kernel(const double *__restrict__ A, long long lda, const double *__re
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-    // split-K: slice blockIdx.z works on k in [kbeg, kend) and writes its own partial result
-    const long long kbeg = (long long)blockIdx.z * kchunk;
+    // split-K: slice blockIdx.z works on k in [kbeg, kend) and writes its own partial result;
+    // batched: blockIdx.z is the matrix index and split_stride the stride of C
+    const long long kbeg = batched ? 0 : (long long)blockIdx.z * kchunk;
     const long long kend = (kbeg + kchunk < K) ? kbeg + kchunk : K;
     C += (long long)blockIdx.z * split_stride;
+    if (batched) {
+        A += (long long)blockIdx.z * bsA;
+        B += (long long)blockIdx.z * bsB;
+    }
     const long long nk = (kend - kbeg + BK - 1) / BK;
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < nk) {
@@ -216,7 +221,7 @@ int launch_gemm_cyc(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t ld
     }
     {
         LaunchScope ls(ctx, name, 1, 2.0 * (double)K * pairs);
-#define GEMM_LAUNCH(TA_, TB_) gemm_dmma_kernel<TA_, TB_><<<grid, GEMM_THREADS, smem, ctx->stream>>>(A, lda, B, ldb, Cout, ldout, M, N, K, alpha, accumulate, tri, tri_off, kchunk, split_stride, jt0, jtstride)
+#define GEMM_LAUNCH(TA_, TB_) gemm_dmma_kernel<TA_, TB_><<<grid, GEMM_THREADS, smem, ctx->stream>>>(A, lda, B, ldb, Cout, ldout, M, N, K, alpha, accumulate, tri, tri_off, kchunk, split_stride, jt0, jtstride, 0LL, 0LL, 0)
         if (ta && tb) GEMM_LAUNCH(true, true);
         else if (!ta && !tb) GEMM_LAUNCH(false, false);
         else if (ta) GEMM_LAUNCH(true, false);
@@ -228,6 +233,42 @@ int launch_gemm_cyc(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t ld
             if (g > (long long)ctx->num_sms * 8) g = (long long)ctx->num_sms * 8;
             splitk_reduce_kernel<<<(unsigned)g, 256, 0, ctx->stream>>>(ctx->gemm_ws, split_stride, splits, C, ldc, M, N, tri, tri_off);
         }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// `batch` independent products with strides between consecutive A / B / C (0 = shared operand)
+int launch_gemm_batched(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, int64_t sA, const double *B, int64_t ldb,
+                        int64_t sB, double *C, int64_t ldc, int64_t sC, int64_t M, int64_t N, int64_t K, double alpha,
+                        int accumulate, int64_t batch, const char *name) {
+    if (M <= 0 || N <= 0 || batch <= 0) return 0;
+    if (K <= 0) {
+        if (accumulate) return 0;
+        smcp_set_error("launch_gemm_batched: K = 0 without accumulation");
+        return -2;
+    }
+    size_t smem = (size_t)2 * STAGES * 128 * LDK * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    for (int64_t z0 = 0; z0 < batch; z0 += 32768) {
+        const int64_t nz = std::min<int64_t>(32768, batch - z0);
+        dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)nz);
+        const double *Az = A + z0 * sA, *Bz = B + z0 * sB;
+        double *Cz = C + z0 * sC;
+        LaunchScope ls(ctx, name, 1, 2.0 * (double)K * (double)M * (double)N * (double)nz);
+#define GEMM_LAUNCH(TA_, TB_) gemm_dmma_kernel<TA_, TB_><<<grid, GEMM_THREADS, smem, ctx->stream>>>(Az, lda, Bz, ldb, Cz, ldc, M, N, K, alpha, accumulate, 0, 0, K, sC, 0, 1, sA, sB, 1)
+        if (ta && tb) GEMM_LAUNCH(true, true);
+        else if (!ta && !tb) GEMM_LAUNCH(false, false);
+        else if (ta) GEMM_LAUNCH(true, false);
+        else GEMM_LAUNCH(false, true);
+#undef GEMM_LAUNCH
     }
     CUDA_TRY(cudaGetLastError());
     return 0;

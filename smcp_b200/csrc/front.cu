@@ -124,28 +124,35 @@ int d_trsm_left_lower(smcp_ctx *ctx, bool trans, const double *L, int64_t ldl, i
     }
     const unsigned grid = (unsigned)((nrhs + 127) / 128);
     const int64_t nb = (n + FNB - 1) / FNB;
+    // right-looking: after a 64-row block is solved the whole remainder is updated by ONE GEMM
+    // with K = 64 and (rows left) x nrhs outputs, which fills the GPU; the left-looking form
+    // (K growing, 64 output rows) runs on nrhs/128 CTAs and was 10x slower at n = 1186
     if (!trans) {
         for (int64_t bi = 0; bi < nb; ++bi) {
             const int64_t i0 = bi * FNB;
             const int kb = (int)std::min<int64_t>(FNB, n - i0);
-            if (i0 > 0) {
-                // B_i -= L(i0:i0+kb, 0:i0) X(0:i0, :)
-                if (launch_gemm(ctx, false, true, L + i0, ldl, B, ldb, B + i0, ldb, kb, nrhs, i0, -1.0, 1, 0, 0, "front_gemm_dmma")) return -1;
+            {
+                LaunchScope ls(ctx, "front_trsm_diag");
+                trsm_diag_kernel<false><<<grid, 128, smem, ctx->stream>>>(L + i0 + i0 * ldl, ldl, kb, B + i0, ldb, nrhs);
             }
-            LaunchScope ls(ctx, "front_trsm_diag");
-            trsm_diag_kernel<false><<<grid, 128, smem, ctx->stream>>>(L + i0 + i0 * ldl, ldl, kb, B + i0, ldb, nrhs);
+            const int64_t below = n - i0 - kb;
+            if (below > 0) {
+                // B(i0+kb:n, :) -= L(i0+kb:n, i0:i0+kb) X(i0:i0+kb, :)
+                if (launch_gemm(ctx, false, true, L + (i0 + kb) + i0 * ldl, ldl, B + i0, ldb, B + i0 + kb, ldb, below, nrhs, kb, -1.0, 1, 0, 0, "front_gemm_dmma")) return -1;
+            }
         }
     } else {
         for (int64_t bi = nb - 1; bi >= 0; --bi) {
             const int64_t i0 = bi * FNB;
             const int kb = (int)std::min<int64_t>(FNB, n - i0);
-            const int64_t below = n - i0 - kb;
-            if (below > 0) {
-                // B_i -= L(i0+kb:n, i0:i0+kb)^T X(i0+kb:n, :)
-                if (launch_gemm(ctx, true, true, L + (i0 + kb) + i0 * ldl, ldl, B + i0 + kb, ldb, B + i0, ldb, kb, nrhs, below, -1.0, 1, 0, 0, "front_gemm_dmma")) return -1;
+            {
+                LaunchScope ls(ctx, "front_trsm_diag");
+                trsm_diag_kernel<true><<<grid, 128, smem, ctx->stream>>>(L + i0 + i0 * ldl, ldl, kb, B + i0, ldb, nrhs);
             }
-            LaunchScope ls(ctx, "front_trsm_diag");
-            trsm_diag_kernel<true><<<grid, 128, smem, ctx->stream>>>(L + i0 + i0 * ldl, ldl, kb, B + i0, ldb, nrhs);
+            if (i0 > 0) {
+                // B(0:i0, :) -= L(i0:i0+kb, 0:i0)^T X(i0:i0+kb, :)
+                if (launch_gemm(ctx, true, true, L + i0, ldl, B + i0, ldb, B, ldb, i0, nrhs, kb, -1.0, 1, 0, 0, "front_gemm_dmma")) return -1;
+            }
         }
     }
     CUDA_TRY(cudaGetLastError());

@@ -147,6 +147,8 @@ struct smcp_sym {
     size_t big_ws_stride = 0;
     int *big_info = nullptr;
     int max_nj_small = 0;        // largest frontal matrix left to the tree kernels when the top set is skipped
+    double *big_bws = nullptr, *big_cat = nullptr;      // batched top-set workspaces (grown on demand)
+    size_t big_bws_cap = 0, big_cat_cap = 0;
     // host copies used by the operator setup
     std::vector<int> h_vec2blk;
     std::vector<int64_t> h_snptr;
@@ -206,6 +208,7 @@ int big_projinv(smcp_sym *s, const BigNode &q, double *X, int64_t b);
 int big_completion(smcp_sym *s, const BigNode &q, double *X, const double *Xin, int64_t b);
 int big_hess_prep(smcp_sym *s, const BigNode &q, const double *L0, const double *Y0, double *Lt_out, double *Yaa_out);
 int big_hess_prep_inv(smcp_sym *s, const BigNode &q, const double *Yaa_all, double *Raa_all);
+int big_hess_fwd_batched(smcp_sym *s, const double *Lt, const double *Yaa_all, double *U, int64_t batch);
 
 // dense root supernode (front.cu)
 int root_setup(smcp_sym *s, const smcp_sym_desc *D);
@@ -225,6 +228,9 @@ int d_potrs(smcp_ctx *ctx, const double *H, int64_t m, double *y_dev);
 int launch_gemm_cyc(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
                     int64_t ldc, int64_t M, int64_t N, int64_t K, double alpha, int accumulate, int tri, int64_t tri_off,
                     const char *name, int jt0, int jtstride);
+int launch_gemm_batched(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, int64_t sA, const double *B, int64_t ldb,
+                        int64_t sB, double *C, int64_t ldc, int64_t sC, int64_t M, int64_t N, int64_t K, double alpha,
+                        int accumulate, int64_t batch, const char *name);
 // ncclBroadcast of `count` doubles in place on stream s (capi.cu)
 int comm_bcast(smcp_ctx *ctx, double *ptr, size_t count, int root, cudaStream_t s);
 int launch_gemm(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
