@@ -246,9 +246,14 @@ def run_b200(args):
     launches = {}
     timer.marks[W] = lambda: (traffic0.update(TRAFFIC), launches.update(a=ctx.launch_count()), barrier())
     solvers._iteration_hook = timer
+    # nvidia-smi needs ~1 s to attach to the driver and perturbs CUDA calls while it does: wait for
+    # its first sample before the solve starts so that only steady-state polling overlaps the timed region
     sampler = ClockSampler(local)
-    barrier()
     sampler.start()
+    t_wait = time.perf_counter()
+    while not sampler.rows and time.perf_counter() - t_wait < 10.0 and sampler.proc is not None:
+        time.sleep(0.05)
+    barrier()
     sol = P.solve_feas(kktsolver="chol", primalstart=start)
     ctx.sync()
     clocks = sampler.stop()

@@ -286,6 +286,12 @@ extern "C" int smcp_sym_destroy(smcp_sym *s) {
     if (s->red) cudaFree(s->red);
     if (s->fbuf) cudaFree(s->fbuf);
     if (s->ch_state) cudaFree(s->ch_state);
+    if (s->big_bws) cudaFree(s->big_bws);
+    if (s->big_cat) cudaFree(s->big_cat);
+    for (auto &b : s->hess_pool) {
+        cudaFree(b.Lt); cudaFree(b.Yaa); cudaFree(b.Raa);
+        if (b.phi) cudaFree(b.phi);
+    }
     delete s;
     return 0;
 }
@@ -387,20 +393,32 @@ extern "C" int smcp_hess_create(smcp_sym *s, const double *L, const double *Y, s
     smcp_hess *h = new smcp_hess();
     h->sym = s;
     h->L = L;
-    CUDA_TRY(cudaMalloc(&h->Lt, (size_t)(s->d.nblk + 1) * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&h->Yaa, (size_t)(s->d.nupd + 1) * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&h->Raa, (size_t)(s->d.nupd + 1) * sizeof(double)));
+    if (!s->hess_pool.empty()) {
+        const smcp_sym::HessBufs b = s->hess_pool.back();
+        s->hess_pool.pop_back();
+        h->Lt = b.Lt; h->Yaa = b.Yaa; h->Raa = b.Raa; h->phi_up = b.phi;      // phi is refilled by chain_prepare
+    } else {
+        CUDA_TRY(cudaMalloc(&h->Lt, (size_t)(s->d.nblk + 1) * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&h->Yaa, (size_t)(s->d.nupd + 1) * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&h->Raa, (size_t)(s->d.nupd + 1) * sizeof(double)));
+    }
     if (k_hess_prep(h, L, Y)) return -1;
     *out = h;
     return 0;
 }
 extern "C" int smcp_hess_destroy(smcp_hess *h) {
     if (!h) return 0;
-    cudaStreamSynchronize(h->sym->ctx->stream);
-    cudaFree(h->Lt);
-    cudaFree(h->Yaa);
-    cudaFree(h->Raa);
-    if (h->phi_up) cudaFree(h->phi_up);      // one allocation: phi_up | phi_dn | psi_up | psi_dn
+    smcp_sym *s = h->sym;
+    if (s->hess_pool.size() < 4) {
+        // work still queued on the stream may read these buffers; the next owner writes them in stream order
+        s->hess_pool.push_back({h->Lt, h->Yaa, h->Raa, h->phi_up});
+    } else {
+        cudaStreamSynchronize(s->ctx->stream);
+        cudaFree(h->Lt);
+        cudaFree(h->Yaa);
+        cudaFree(h->Raa);
+        if (h->phi_up) cudaFree(h->phi_up);      // one allocation: phi_up | phi_dn | psi_up | psi_dn
+    }
     delete h;
     return 0;
 }

@@ -49,16 +49,18 @@ enum { CH_PROBE = 0, CH_FINAL = 1, CH_BASIS = 2 };
 #define TRI(p, q) ((p) * ((p) + 1) / 2 + (q))
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void chain_cp_async8(void *smem, const void *gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem));
+}
 
 // PF = how many nodes ahead the block / factor entries are fetched: 1 for large batches (occupancy
 // hides the latency, registers matter), 4 for a single matrix (nothing else hides it).
+// One segment of the up sweep for matrix / basis vector b.  x, l and yaa are indexed by the ABSOLUTE
+// node number: global arrays, or shared-memory copies of the segment shifted by its first node.
 template <int W, int MODE, int PF>
-__global__ void __launch_bounds__(128) chain_up_kernel(ChainArgs a) {
+__device__ __forceinline__ void chain_up_body(const ChainArgs &a, const int s, const int b, double *x, const double *l, const double *yaa) {
     constexpr int D = W * (W + 1) / 2, NJ = W + 1;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int nb = (MODE == CH_BASIS) ? D : a.B;
-    const int s = (int)(idx / nb), b = (int)(idx - (long long)s * nb);
-    if (s >= a.P) return;
     double u[W][W];
 #pragma unroll
     for (int p = 0; p < W; ++p)
@@ -69,8 +71,6 @@ __global__ void __launch_bounds__(128) chain_up_kernel(ChainArgs a) {
             else u[p][q] = (TRI(p, q) == b) ? 1.0 : 0.0;
         }
     const int k0 = s * a.SEG, k1 = min(a.N, k0 + a.SEG);
-    double *x = a.X + (long long)b * a.nblk;
-    const double *l = a.Lt;
     double xb[PF][NJ], lb[PF][W];
 #pragma unroll
     for (int t = 0; t < PF; ++t) {
@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(128) chain_up_kernel(ChainArgs a) {
                     for (int i = 0; i < NJ; ++i) xb[t][i] = (MODE != CH_BASIS) ? x[(long long)(k + PF) * NJ + i] : 0.0;
 #pragma unroll
                     for (int i = 0; i < W; ++i) lb[t][i] = l[(long long)(k + PF) * NJ + 1 + i];
-                    if (MODE == CH_FINAL && PF > 1 && a.Yaa) {      // single matrix: nothing else hides the Y_aa loads
-                        const double *yn = a.Yaa + (long long)(k + PF) * W * W;
+                    if (MODE == CH_FINAL && PF > 1 && yaa) {      // single matrix: nothing else hides the Y_aa loads
+                        const double *yn = yaa + (long long)(k + PF) * W * W;
                         prefetch_l1(yn);
                         if (W * W > 16) prefetch_l1(yn + 16);
                         if (W * W > 32) prefetch_l1(yn + 32);
@@ -120,11 +120,11 @@ __global__ void __launch_bounds__(128) chain_up_kernel(ChainArgs a) {
                     }
                 if (MODE == CH_FINAL) {
                     double *o = x + (long long)k * NJ;
-                    if (a.Yaa) {
+                    if (yaa) {
                         // fused scaling (App. A.4 step 2, single-column supernode):
                         // M_nn = K_nn / l^4, M_an = Y_aa (K_an / l^2)
                         const double l0 = l[(long long)k * NJ];
-                        const double *yp = a.Yaa + (long long)k * W * W;
+                        const double *yp = yaa + (long long)k * W * W;
                         const double inv = 1.0 / (l0 * l0);
                         double kv[W];
 #pragma unroll
@@ -166,12 +166,27 @@ __global__ void __launch_bounds__(128) chain_up_kernel(ChainArgs a) {
 }
 
 template <int W, int MODE, int PF>
-__global__ void __launch_bounds__(128) chain_down_kernel(ChainArgs a) {
-    constexpr int D = W * (W + 1) / 2, NJ = W + 1;
+__global__ void __launch_bounds__(128) chain_up_kernel(ChainArgs a) {
+    constexpr int D = W * (W + 1) / 2;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int nb = (MODE == CH_BASIS) ? D : a.B;
     const int s = (int)(idx / nb), b = (int)(idx - (long long)s * nb);
     if (s >= a.P) return;
+    chain_up_body<W, MODE, PF>(a, s, b, a.X + (long long)b * a.nblk, a.Lt, a.Yaa);
+}
+
+// Few matrices (Newton solves, line-search steps): one WARP per (segment, matrix) copies the
+// segment's entries of X, L (and Y_aa for the fused scaling) into shared memory with coalesced
+// loads -- one round trip to memory instead of one per node --, lane 0 runs the recurrence on
+// the copies, and the warp writes the segment back.  (Thread-per-segment straight from global
+// memory paid ~4 us per node: 129 us for the 32-node final pass of one matrix.)
+#define CHAIN_SEG 32
+template <int W, int MODE, bool UP>
+__global__ void __launch_bounds__(128) chain_staged_kernel(ChainArgs a);
+
+template <int W, int MODE, int PF>
+__device__ __forceinline__ void chain_down_body(const ChainArgs &a, const int s, const int b, double *x, const double *l) {
+    constexpr int D = W * (W + 1) / 2, NJ = W + 1;
     double z[W][W];
 #pragma unroll
     for (int p = 0; p < W; ++p)
@@ -182,8 +197,6 @@ __global__ void __launch_bounds__(128) chain_down_kernel(ChainArgs a) {
             else z[p][q] = (TRI(p, q) == b) ? 1.0 : 0.0;
         }
     const int k0 = s * a.SEG, k1 = min(a.N, k0 + a.SEG);
-    double *x = a.X + (long long)b * a.nblk;
-    const double *l = a.Lt;
     double xb[PF][NJ], lb[PF][W];
 #pragma unroll
     for (int t = 0; t < PF; ++t) {
@@ -254,6 +267,91 @@ __global__ void __launch_bounds__(128) chain_down_kernel(ChainArgs a) {
         for (int p = 0; p < W; ++p)
 #pragma unroll
             for (int q = 0; q <= p; ++q) g[TRI(p, q)] = z[p][q];
+    }
+}
+
+template <int W, int MODE, int PF>
+__global__ void __launch_bounds__(128) chain_down_kernel(ChainArgs a) {
+    constexpr int D = W * (W + 1) / 2;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nb = (MODE == CH_BASIS) ? D : a.B;
+    const int s = (int)(idx / nb), b = (int)(idx - (long long)s * nb);
+    if (s >= a.P) return;
+    chain_down_body<W, MODE, PF>(a, s, b, a.X + (long long)b * a.nblk, a.Lt);
+}
+
+template <int W, int MODE, bool UP>
+__global__ void __launch_bounds__(128) chain_staged_kernel(ChainArgs a) {
+    constexpr int NJ = W + 1;
+    constexpr int WPC = (W <= 5) ? 4 : 2;                       // warps (items) per CTA: static shared memory < 48 KB
+    constexpr bool YS = UP && MODE == CH_FINAL;
+    __shared__ double xs[WPC][CHAIN_SEG * NJ], ls[WPC][CHAIN_SEG * NJ], ys[WPC][YS ? CHAIN_SEG * W * W : 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp >= WPC) return;
+    const long long item = (long long)blockIdx.x * WPC + warp;   // item = s * B + b
+    if (item >= (long long)a.P * a.B) return;
+    const int s = (int)(item / a.B), b = (int)(item - (long long)s * a.B);
+    const int k0 = s * a.SEG, k1 = min(a.N, k0 + a.SEG), cnt = (k1 - k0) * NJ;
+    double *xg = a.X + (long long)b * a.nblk + (long long)k0 * NJ;
+    const double *lg = a.Lt + (long long)k0 * NJ;
+    for (int i = lane; i < cnt; i += 32) {
+        xs[warp][i] = xg[i];
+        ls[warp][i] = lg[i];
+    }
+    const bool scale = YS && a.Yaa != nullptr;
+    if (scale) {
+        const double *yg = a.Yaa + (long long)k0 * W * W;
+        for (int i = lane; i < (k1 - k0) * W * W; i += 32) ys[warp][i] = yg[i];
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double *xv = xs[warp] - (long long)k0 * NJ;
+        const double *lv = ls[warp] - (long long)k0 * NJ;
+        if (UP) chain_up_body<W, MODE, 1>(a, s, b, xv, lv, scale ? ys[warp] - (long long)k0 * W * W : nullptr);
+        else chain_down_body<W, MODE, 1>(a, s, b, xv, lv);
+    }
+    __syncwarp();
+    if (MODE == CH_FINAL)
+        for (int i = lane; i < cnt; i += 32) xg[i] = xs[warp][i];
+}
+
+// Large batches (Schur assembly: one matrix per constraint): a warp takes 32 matrices of ONE segment,
+// lane = matrix.  Thread-per-(matrix, segment) straight from global memory makes every load
+// instruction touch 32 different lines (the matrices are nblk*8 bytes apart): ncu showed the
+// kernels stalled on the load/store queue (lg_throttle) at 12 % of the HBM rate.  Here the warp
+// copies each matrix's segment (SEG*NJ contiguous doubles) into shared memory with coalesced
+// cp.async, every lane runs the recurrence on its row (odd row stride: conflict-free), and the
+// rows are written back coalesced.  L and Y_aa are read by all lanes at the same address
+// (broadcast, L1-resident).
+template <int W, int MODE, bool UP>
+__global__ void __launch_bounds__(32) chain_staged_batch_kernel(ChainArgs a) {
+    constexpr int NJ = W + 1, RS = (CHAIN_SEG * NJ) | 1;
+    extern __shared__ double csb[];                               // 32 x RS
+    const int lane = threadIdx.x;
+    const int ngrp = (a.B + 31) / 32;
+    const int s = blockIdx.x / ngrp, g = blockIdx.x - s * ngrp;
+    const int b0 = g * 32, nmat = min(32, a.B - b0);
+    const int k0 = s * a.SEG, k1 = min(a.N, k0 + a.SEG), cnt = (k1 - k0) * NJ;
+    for (int mm = 0; mm < nmat; ++mm) {
+        const double *src = a.X + (long long)(b0 + mm) * a.nblk + (long long)k0 * NJ;
+        double *dst = csb + mm * RS;
+        for (int i = lane; i < cnt; i += 32) chain_cp_async8(dst + i, src + i);
+    }
+    asm volatile("cp.async.commit_group;");
+    asm volatile("cp.async.wait_group 0;");
+    __syncwarp();
+    if (lane < nmat) {
+        double *xv = csb + lane * RS - (long long)k0 * NJ;
+        if (UP) chain_up_body<W, MODE, 1>(a, s, b0 + lane, xv, a.Lt, (MODE == CH_FINAL) ? a.Yaa : nullptr);
+        else chain_down_body<W, MODE, 1>(a, s, b0 + lane, xv, a.Lt);
+    }
+    __syncwarp();
+    if (MODE == CH_FINAL) {
+        for (int mm = 0; mm < nmat; ++mm) {
+            double *dst = a.X + (long long)(b0 + mm) * a.nblk + (long long)k0 * NJ;
+            const double *src = csb + mm * RS;
+            for (int i = lane; i < cnt; i += 32) dst[i] = src[i];
+        }
     }
 }
 
@@ -471,6 +569,144 @@ __global__ void __launch_bounds__(256) chain_add_kernel(ChainArgs a) {
     }
 }
 
+// root of a chain: dense nn x nn front = root block + carried update (positions < W), right-looking
+template <int W>
+__device__ __forceinline__ bool chain_chol_root(const ChainArgs &a, double *x, double (&u)[W][W]) {
+    bool anybad = false;
+    const int nn = a.root_nj;
+    double *rb = x + a.root_off;
+    double f[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            double v = 0.0;
+            if (i < nn && j <= i) {
+                v = rb[i + j * nn];
+                if (i < W) v = u[i < W ? i : 0][j < W ? j : 0] + v;
+            }
+            f[i][j] = v;
+        }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        if (r < nn) {
+            const double d = f[r][r];
+            const bool bad = !(d > 0.0);
+            anybad |= bad;
+            const double rs = bad ? 1.0 : rsqrt(d);
+            double l[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) l[i] = (i > r) ? f[i][r] * rs : 0.0;
+            double dg = d * rs;
+            dg = fma(fma(-dg, dg, d), 0.5 * rs, dg);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i < nn) {
+                    if (i == r) rb[i + r * nn] = bad ? 1.0 : dg;
+                    else if (i > r) rb[i + r * nn] = l[i];
+                    else rb[i + r * nn] = 0.0;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j)
+                    if (j > r) f[i][j] = fma(-l[i], l[j], f[i][j]);
+        }
+    }
+    return anybad;
+}
+
+// one node of the chain Cholesky: xn[0..W] in -> L column out (in place), u = carried update matrix
+template <int W>
+__device__ __forceinline__ bool chain_chol_node(double *xn, double (&u)[W][W]) {
+    const double f0 = xn[0] + u[0][0];
+    const bool bad = !(f0 > 0.0);
+    const double rs = bad ? 1.0 : rsqrt(f0);
+    double li[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const double fa = (i + 1 < W) ? xn[1 + i] + u[i + 1][0] : xn[1 + i];
+        li[i] = fa * rs;
+    }
+    double un[W][W];
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            const double faa = (i + 1 < W) ? u[i + 1][j + 1] : 0.0;
+            un[i][j] = fma(-li[i], li[j], faa);
+        }
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) u[i][j] = un[i][j];
+    double dg = f0 * rs;
+    dg = fma(fma(-dg, dg, f0), 0.5 * rs, dg);
+    xn[0] = bad ? 1.0 : dg;
+#pragma unroll
+    for (int i = 0; i < W; ++i) xn[1 + i] = li[i];
+    return bad;
+}
+
+// Staged variant: a warp owns up to 32 matrices (one per lane).  The chain is cut into chunks of C
+// nodes; the warp copies the chunk of every one of its matrices into shared memory with coalesced
+// cp.async (each matrix's chunk is contiguous), double-buffered so that the next chunk is in
+// flight while the lanes run the recurrence on the current one, and writes the factor back
+// coalesced.  The kernel above issues one uncoalesced 8-byte load per lane and per entry, i.e. a
+// DRAM round trip per node (0.3 - 0.6 us): 1.7 ms for one matrix, 2.9 ms for 255 candidates.
+template <int W>
+__global__ void __launch_bounds__(32) chain_chol_staged_kernel(ChainArgs a, int *fail, int C, int R) {
+    constexpr int NJ = W + 1;
+    extern __shared__ double chsm[];
+    const int lane = threadIdx.x;
+    const int b0 = blockIdx.x * R;                      // R matrices per warp (lanes >= R idle): few matrices per
+    const int nmat = min(R, a.B - b0);                  // warp = long chunks = little copy overhead per node
+    const int rs = (C * NJ) | 1;                        // odd row stride: conflict-free lane access
+    double *buf0 = chsm, *buf1 = chsm + (size_t)R * rs;          // R = rows (matrices) per buffer
+    const int nchunks = (a.N + C - 1) / C;
+    double u[W][W];
+#pragma unroll
+    for (int p = 0; p < W; ++p)
+#pragma unroll
+        for (int q = 0; q <= p; ++q) u[p][q] = 0.0;
+    bool anybad = false;
+    auto stage = [&](int c, double *buf) {
+        const int k0 = c * C, cnt = min(C, a.N - k0) * NJ;
+        for (int mm = 0; mm < nmat; ++mm) {
+            const double *src = a.X + (long long)(b0 + mm) * a.nblk + (long long)k0 * NJ;
+            for (int i = lane; i < cnt; i += 32) chain_cp_async8(buf + (size_t)mm * rs + i, src + i);
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    if (nchunks > 0) stage(0, buf0);
+    for (int c = 0; c < nchunks; ++c) {
+        double *cur = (c & 1) ? buf1 : buf0;
+        if (c + 1 < nchunks) {
+            stage(c + 1, (c & 1) ? buf0 : buf1);
+            asm volatile("cp.async.wait_group 1;");
+        } else {
+            asm volatile("cp.async.wait_group 0;");
+        }
+        __syncwarp();
+        const int k0 = c * C, nk = min(C, a.N - k0);
+        if (lane < nmat) {
+            double *row = cur + (size_t)lane * rs;
+            for (int k = 0; k < nk; ++k) anybad |= chain_chol_node<W>(row + k * NJ, u);
+        }
+        __syncwarp();
+        for (int mm = 0; mm < nmat; ++mm) {
+            double *dst = a.X + (long long)(b0 + mm) * a.nblk + (long long)k0 * NJ;
+            for (int i = lane; i < nk * NJ; i += 32) dst[i] = cur[(size_t)mm * rs + i];
+        }
+        __syncwarp();
+    }
+    if (lane < nmat) {
+        anybad |= chain_chol_root<W>(a, a.X + (long long)(b0 + lane) * a.nblk, u);
+        if (anybad) fail[b0 + lane] = 1;
+    }
+}
+
 // Cholesky on a chain (chompack.cholesky, solvers.py:640, 884, 1218): the recurrence is NOT linear
 // (the pivot depends on the incoming update), so it stays sequential — but one THREAD per matrix
 // with the W x W update matrix in registers has a critical path of one rsqrt + three FP64 ops per
@@ -537,48 +773,7 @@ __global__ void __launch_bounds__(64) chain_chol_kernel(ChainArgs a, int *fail) 
             }
         }
     }
-    // root: dense nn x nn front = root block + carried update (positions < W), right-looking
-    const int nn = a.root_nj;
-    double *rb = x + a.root_off;
-    double f[8][8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            double v = 0.0;
-            if (i < nn && j <= i) {
-                v = rb[i + j * nn];
-                if (i < W) v = u[i < W ? i : 0][j < W ? j : 0] + v;
-            }
-            f[i][j] = v;
-        }
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        if (r < nn) {
-            const double d = f[r][r];
-            const bool bad = !(d > 0.0);
-            anybad |= bad;
-            const double rs = bad ? 1.0 : rsqrt(d);
-            double l[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) l[i] = (i > r) ? f[i][r] * rs : 0.0;
-            double dg = d * rs;
-            dg = fma(fma(-dg, dg, d), 0.5 * rs, dg);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (i < nn) {
-                    if (i == r) rb[i + r * nn] = bad ? 1.0 : dg;
-                    else if (i > r) rb[i + r * nn] = l[i];
-                    else rb[i + r * nn] = 0.0;
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j <= i; ++j)
-                    if (j > r) f[i][j] = fma(-l[i], l[j], f[i][j]);
-        }
-    }
+    anybad |= chain_chol_root<W>(a, x, u);
     if (anybad) fail[b] = 1;
 }
 
@@ -929,7 +1124,6 @@ __global__ void __launch_bounds__(128) chain_compl_kernel(ChainArgs a, const dou
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-#define CHAIN_SEG 32
 
 // chain structure test (called from small_setup)
 static void chain_detect(smcp_sym *s, const smcp_sym_desc *D, const std::vector<int> &nn, const std::vector<int> &na) {
@@ -979,9 +1173,26 @@ template <int W, int MODE>
 static void chain_launch_dir(bool up, const ChainArgs &a, cudaStream_t st) {
     const long long threads = (long long)a.P * (MODE == CH_BASIS ? a.D : a.B);
     const unsigned grid = (unsigned)((threads + 127) / 128);
-    if (MODE == CH_BASIS || a.B < 32) {
+    static const bool staged = !(getenv("SMCP_B200_CHAIN_STAGED") && atoi(getenv("SMCP_B200_CHAIN_STAGED")) == 0);
+    if (MODE != CH_BASIS && a.B < 32 && a.SEG == CHAIN_SEG && staged) {
+        constexpr int WPC = (W <= 5) ? 4 : 2;
+        const unsigned g2 = (unsigned)(((long long)a.P * a.B + WPC - 1) / WPC);
+        if (up) chain_staged_kernel<W, MODE, true><<<g2, 32 * WPC, 0, st>>>(a);
+        else chain_staged_kernel<W, MODE, false><<<g2, 32 * WPC, 0, st>>>(a);
+    } else if (MODE == CH_BASIS || a.B < 32) {
         if (up) chain_up_kernel<W, MODE, 4><<<grid, 128, 0, st>>>(a);
         else chain_down_kernel<W, MODE, 4><<<grid, 128, 0, st>>>(a);
+    } else if (staged && a.SEG == CHAIN_SEG && !getenv("SMCP_B200_NO_BATCH_STAGED")) {
+        constexpr int RS = (CHAIN_SEG * (W + 1)) | 1;
+        const int smem = 32 * RS * (int)sizeof(double);
+        const unsigned g3 = (unsigned)((long long)a.P * ((a.B + 31) / 32));
+        if (up) {
+            cudaFuncSetAttribute(chain_staged_batch_kernel<W, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            chain_staged_batch_kernel<W, MODE, true><<<g3, 32, smem, st>>>(a);
+        } else {
+            cudaFuncSetAttribute(chain_staged_batch_kernel<W, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            chain_staged_batch_kernel<W, MODE, false><<<g3, 32, smem, st>>>(a);
+        }
     } else {
         if (up) chain_up_kernel<W, MODE, 1><<<grid, 128, 0, st>>>(a);
         else chain_down_kernel<W, MODE, 1><<<grid, 128, 0, st>>>(a);
@@ -1052,7 +1263,7 @@ static int chain_prepare(smcp_hess *h) {
     const int W = s->chW, D = W * (W + 1) / 2;
     const size_t bytes = (size_t)s->chP * D * (D + 1) * sizeof(double);
     const size_t pbytes = (size_t)SCAN_G * D * (D + 1) * sizeof(double);
-    CUDA_TRY(cudaMalloc(&h->phi_up, 2 * (bytes + pbytes)));
+    if (!h->phi_up) CUDA_TRY(cudaMalloc(&h->phi_up, 2 * (bytes + pbytes)));      // reused from the pool of the symbolic object
     h->phi_dn = h->phi_up + bytes / sizeof(double);
     h->psi_up = h->phi_dn + bytes / sizeof(double);
     h->psi_dn = h->psi_up + pbytes / sizeof(double);
@@ -1121,7 +1332,33 @@ static int chain_cholesky(smcp_sym *s, double *X, int64_t batch, const char *nam
     ChainArgs a = {};
     if (chain_fill(s, a, X, nullptr, batch)) return -1;
     const unsigned grid = (unsigned)((batch + 63) / 64);
-    {
+    static const bool staged = !(getenv("SMCP_B200_CHAIN_STAGED") && atoi(getenv("SMCP_B200_CHAIN_STAGED")) == 0);
+    if (staged) {
+        // chunk length: 2 buffers x 32 rows of C*NJ doubles within ~96 KB; fewer matrices -> longer chunks
+        // the recurrence costs ~300 cycles per node whatever the number of active lanes, so a batch is
+        // spread over many warps: 8 matrices per warp (255 line-search candidates -> 32 SMs)
+        const int NJ = s->chW + 1, nmat = (int)std::min<int64_t>(batch >= 64 ? 8 : 32, batch);
+        int C = 6000 / (nmat * NJ);
+        C = std::max(8, std::min(C, 512));
+        const size_t smem = (size_t)2 * nmat * ((C * NJ) | 1) * sizeof(double);
+        const unsigned g2 = (unsigned)((batch + nmat - 1) / nmat);
+        LaunchScope ls(ctx, name, 1, (double)batch);
+#define CHOL_ST(W_)                                                                                                         \
+    do {                                                                                                                    \
+        CUDA_TRY(cudaFuncSetAttribute(chain_chol_staged_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+        chain_chol_staged_kernel<W_><<<g2, 32, smem, ctx->stream>>>(a, s->fail, C, nmat);                                    \
+    } while (0)
+        switch (s->chW) {
+            case 1: CHOL_ST(1); break;
+            case 2: CHOL_ST(2); break;
+            case 3: CHOL_ST(3); break;
+            case 4: CHOL_ST(4); break;
+            case 5: CHOL_ST(5); break;
+            case 6: CHOL_ST(6); break;
+            default: CHOL_ST(7); break;
+        }
+#undef CHOL_ST
+    } else {
         LaunchScope ls(ctx, name, 1, (double)batch);
         switch (s->chW) {
             case 1: chain_chol_kernel<1><<<grid, 64, 0, ctx->stream>>>(a, s->fail); break;

@@ -708,6 +708,18 @@ __global__ void __launch_bounds__(256) potrs_bwd_update_kernel(const double *__r
     if (lane == 0) y[c] -= s;
 }
 
+// The factor is read by ONE CTA and between two solves the Hessian kernels stream hundreds of MB
+// through L2, so every load of the solve would be a DRAM round trip: all SMs pull the lower
+// triangle into L2 first (4 MB at m = 1000, a few microseconds at HBM speed).
+__global__ void potrs_prefetch_kernel(const double *__restrict__ H, long long ld, long long m) {
+    const long long lines_per_col = (m + 15) / 16;
+    const long long total = m * lines_per_col;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long j = idx / lines_per_col, r = (idx % lines_per_col) * 16;
+        if (r + 15 >= j) asm volatile("prefetch.global.L2 [%0];" ::"l"(H + r + j * ld));
+    }
+}
+
 int d_potrs(smcp_ctx *ctx, const double *H, int64_t m, double *y_dev) {
     const int64_t single_max = 1536;
     const int64_t mm = (m <= single_max) ? m : PSB;
@@ -721,7 +733,8 @@ int d_potrs(smcp_ctx *ctx, const double *H, int64_t m, double *y_dev) {
     ctx->prof_mute++;
     struct Unmute { smcp_ctx *c; ~Unmute() { c->prof_mute--; } } unmute{ctx};
     if (m <= single_max) {
-        ctx->launches += 1;
+        ctx->launches += 2;
+        potrs_prefetch_kernel<<<ctx->num_sms, 256, 0, ctx->stream>>>(H, m, m);
         potrs_kernel<<<1, PS_THREADS, smem, ctx->stream>>>(H, m, 0, m, y_dev, 1, 1);
     } else {
         const int64_t nb = (m + PSB - 1) / PSB;

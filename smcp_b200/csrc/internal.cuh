@@ -149,6 +149,10 @@ struct smcp_sym {
     int max_nj_small = 0;        // largest frontal matrix left to the tree kernels when the top set is skipped
     double *big_bws = nullptr, *big_cat = nullptr;      // batched top-set workspaces (grown on demand)
     size_t big_bws_cap = 0, big_cat_cap = 0;
+    // buffers of destroyed smcp_hess objects, reused by the next one (a new scaling point every IPM
+    // iteration: cudaMalloc / cudaFree are synchronising driver calls and do not belong in the loop)
+    struct HessBufs { double *Lt, *Yaa, *Raa, *phi; };
+    std::vector<HessBufs> hess_pool;
     // host copies used by the operator setup
     std::vector<int> h_vec2blk;
     std::vector<int64_t> h_snptr;

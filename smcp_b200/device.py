@@ -271,6 +271,13 @@ class DeviceBackend:
             # workspaces of the batched line-search probes (255 candidates) sized at setup time
             _ck(lib, lib.smcp_sym_reserve(h, 255))
         self._pool = []
+        # chordal-matrix buffers are recycled through this pool; fill it up front so that no
+        # cudaMalloc (a synchronising driver call) happens inside the IPM iterations
+        if symb.nblk * 8 * 40 <= (256 << 20):
+            for _ in range(40):
+                p = C.c_void_p()
+                _ck(lib, lib.smcp_csp_alloc(h, 1, C.byref(p)))
+                self._pool.append(p)
         self._op = None
         self._tok = None
         self.m = 0
