@@ -326,7 +326,9 @@ __global__ void __launch_bounds__(128) chain_staged_kernel(ChainArgs a) {
 template <int W, int MODE, bool UP>
 __global__ void __launch_bounds__(32) chain_staged_batch_kernel(ChainArgs a) {
     constexpr int NJ = W + 1, RS = (CHAIN_SEG * NJ) | 1;
-    extern __shared__ double csb[];                               // 32 x RS
+    constexpr bool YS = UP && MODE == CH_FINAL;
+    extern __shared__ double csb[];                               // 32 x RS | L segment | Y_aa segment
+    double *lsm = csb + 32 * RS, *ysm = lsm + CHAIN_SEG * NJ;
     const int lane = threadIdx.x;
     const int ngrp = (a.B + 31) / 32;
     const int s = blockIdx.x / ngrp, g = blockIdx.x - s * ngrp;
@@ -337,13 +339,19 @@ __global__ void __launch_bounds__(32) chain_staged_batch_kernel(ChainArgs a) {
         double *dst = csb + mm * RS;
         for (int i = lane; i < cnt; i += 32) chain_cp_async8(dst + i, src + i);
     }
+    // the factor (and Y_aa for the fused scaling) of the segment: shared by the 32 matrices
+    for (int i = lane; i < cnt; i += 32) chain_cp_async8(lsm + i, a.Lt + (long long)k0 * NJ + i);
+    const bool scale = YS && a.Yaa != nullptr;
+    if (scale)
+        for (int i = lane; i < (k1 - k0) * W * W; i += 32) chain_cp_async8(ysm + i, a.Yaa + (long long)k0 * W * W + i);
     asm volatile("cp.async.commit_group;");
     asm volatile("cp.async.wait_group 0;");
     __syncwarp();
     if (lane < nmat) {
         double *xv = csb + lane * RS - (long long)k0 * NJ;
-        if (UP) chain_up_body<W, MODE, 1>(a, s, b0 + lane, xv, a.Lt, (MODE == CH_FINAL) ? a.Yaa : nullptr);
-        else chain_down_body<W, MODE, 1>(a, s, b0 + lane, xv, a.Lt);
+        const double *lv = lsm - (long long)k0 * NJ;
+        if (UP) chain_up_body<W, MODE, 1>(a, s, b0 + lane, xv, lv, scale ? ysm - (long long)k0 * W * W : nullptr);
+        else chain_down_body<W, MODE, 1>(a, s, b0 + lane, xv, lv);
     }
     __syncwarp();
     if (MODE == CH_FINAL) {
@@ -1184,7 +1192,7 @@ static void chain_launch_dir(bool up, const ChainArgs &a, cudaStream_t st) {
         else chain_down_kernel<W, MODE, 4><<<grid, 128, 0, st>>>(a);
     } else if (staged && a.SEG == CHAIN_SEG && !getenv("SMCP_B200_NO_BATCH_STAGED")) {
         constexpr int RS = (CHAIN_SEG * (W + 1)) | 1;
-        const int smem = 32 * RS * (int)sizeof(double);
+        const int smem = (32 * RS + CHAIN_SEG * (W + 1) + CHAIN_SEG * W * W) * (int)sizeof(double);
         const unsigned g3 = (unsigned)((long long)a.P * ((a.B + 31) / 32));
         if (up) {
             cudaFuncSetAttribute(chain_staged_batch_kernel<W, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -38,6 +38,16 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// m16n8k8 FP64 tensor-core MMA (sm_90+; SASS DMMA.16x8x8).  Fragments (PTX ISA / CuTe
+// SM90_16x8x8_F64F64F64F64_TN): g = lane >> 2, t = lane & 3;
+//   a[v]: row g + 8*(v & 1), k = t + 4*(v >> 1);  b[v]: col g, k = t + 4*v;
+//   c[v]: row g + 8*(v >> 1), col 2*t + (v & 1).
+__device__ __forceinline__ void dmma16x8x8(double (&c)[4], const double (&a)[4], const double (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+                 : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
+}
+
 template <bool TN>
 __device__ __forceinline__ void load_tile(double *sm, const double *G, long long ld, long long row0,
                                           long long nrows, long long k0, long long K, int tid) {
@@ -79,11 +89,13 @@ gemm_dmma_kernel(const double *__restrict__ A, long long lda, const double *__re
     const int wn = (warp >> 2) * 32;      // 4 warps along N
     const int g = lane >> 2, t = lane & 3;
 
-    double acc[4][4][2];
+    double acc[2][4][4];           // 2 x 4 tiles of 16 x 8 per warp (32 x 32)
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[a][b][v] = 0.0;
 
     // split-K: slice blockIdx.z works on k in [kbeg, kend) and writes its own partial result;
     // batched: blockIdx.z is the matrix index and split_stride the stride of C
@@ -117,34 +129,41 @@ gemm_dmma_kernel(const double *__restrict__ A, long long lda, const double *__re
         const double *as = As + (kt % STAGES) * 128 * LDK;
         const double *bs = Bs + (kt % STAGES) * 128 * LDK;
 #pragma unroll
-        for (int kk = 0; kk < BK; kk += 4) {
-            double af[4], bf[4];
+        for (int kk = 0; kk < BK; kk += 8) {
+            double af[2][4], bf[4][2];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) af[a] = as[(wm + a * 8 + g) * LDK + kk + t];
+            for (int a = 0; a < 2; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) bf[b] = bs[(wn + b * 8 + g) * LDK + kk + t];
+                for (int v = 0; v < 4; ++v) af[a][v] = as[(wm + a * 16 + g + 8 * (v & 1)) * LDK + kk + t + 4 * (v >> 1)];
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int b = 0; b < 4; ++b)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+                for (int v = 0; v < 2; ++v) bf[b][v] = bs[(wn + b * 8 + g) * LDK + kk + t + 4 * v];
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) dmma16x8x8(acc[a][b], af[a], bf[b]);
         }
     }
     cp_async_wait<0>();
-    // epilogue: C(i, j), i = i0 + wm + a*8 + g, j = j0 + wn + b*8 + 2t + {0,1}
+    // epilogue: C(i, j), i = i0 + wm + a*16 + g + 8*(v>>1), j = j0 + wn + b*8 + 2t + (v&1)
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        long long i = i0 + wm + a * 8 + g;
-        if (i >= M) continue;
+    for (int a = 0; a < 2; ++a) {
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        for (int h = 0; h < 2; ++h) {
+            long long i = i0 + wm + a * 16 + g + 8 * h;
+            if (i >= M) continue;
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                long long j = j0 + wn + b * 8 + 2 * t + e;
-                if (j >= N) continue;
-                if (tri && i + tri_off < j) continue;
-                double *c = C + i + j * ldc;
-                double v = alpha * acc[a][b][e];
-                *c = accumulate ? (*c + v) : v;
+            for (int b = 0; b < 4; ++b) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    long long j = j0 + wn + b * 8 + 2 * t + e;
+                    if (j >= N) continue;
+                    if (tri && i + tri_off < j) continue;
+                    double *c = C + i + j * ldc;
+                    double v = alpha * acc[a][b][2 * h + e];
+                    *c = accumulate ? (*c + v) : v;
+                }
             }
         }
     }
