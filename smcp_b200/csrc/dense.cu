@@ -329,7 +329,10 @@ int d_gemm_tn(smcp_ctx *ctx, const double *A, int64_t lda, const double *B, int6
 // Rows/columns >= nv are treated as identity.  On return a[] is the row of L (zeros above the
 // diagonal); the return value is 0 or the 1-based index of the first non-positive pivot
 // (dpotrf's info), after which the result is meaningless but finite work continues.
-__device__ __forceinline__ int warp_chol32(double (&a)[32], const int lane, const int nv) {
+// The multipliers of a step are exchanged through a 32-entry column in shared memory (double
+// buffered): one STS + 16 broadcast LDS.128 per step instead of 2 x 31 shuffles, whose
+// scoreboard-limited issue made the first version run at 0.14 instructions per cycle.
+__device__ __forceinline__ int warp_chol32(double (&a)[32], const int lane, const int nv, double *colbuf /* 2 x 32, 16-byte aligned */) {
     int bad = 0;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -342,10 +345,15 @@ __device__ __forceinline__ int warp_chol32(double (&a)[32], const int lane, cons
         const double sq = sqrt(d);
         const double l = (lane == j) ? sq : ((lane > j && lane < nv && j < nv) ? a[j] / sq : 0.0);
         a[j] = l;
+        double *cb = colbuf + (j & 1) * 32;
+        cb[lane] = l;
+        __syncwarp();
+        const double2 *cb2 = reinterpret_cast<const double2 *>(cb);
 #pragma unroll
-        for (int c = j + 1; c < 32; ++c) {
-            const double lc = __shfl_sync(0xffffffffu, l, c);
-            a[c] = fma(-l, lc, a[c]);
+        for (int c2 = (j + 1) / 2; c2 < 16; ++c2) {
+            const double2 lc = cb2[c2];
+            if (2 * c2 > j) a[2 * c2] = fma(-l, lc.x, a[2 * c2]);
+            a[2 * c2 + 1] = fma(-l, lc.y, a[2 * c2 + 1]);
         }
     }
     return bad;
@@ -357,6 +365,7 @@ __device__ __forceinline__ int warp_chol32(double (&a)[32], const int lane, cons
 // CTA of a fused kernel races with CTAs that are scheduled late.
 __global__ void __launch_bounds__(32) potrf_diag_kernel(double *H, long long ld, int kb, long long k0, int *info) {
     __shared__ __align__(16) double LT[32 * LDT];      // LT[c*LDT + r] = L(r, c) for c < 32 (first block column)
+    __shared__ __align__(16) double colbuf[64];
     const int lane = threadIdx.x;
     double *D = H + k0 + k0 * ld;
     double a[32], b[32];
@@ -400,7 +409,7 @@ __global__ void __launch_bounds__(32) potrf_diag_kernel(double *H, long long ld,
                 }
             }
         }
-        const int bad = warp_chol32(a, lane, nv);
+        const int bad = warp_chol32(a, lane, nv, colbuf);
         if (bad && lane == 0 && *info == 0) *info = (int)(k0 + 32 * h + bad);   // dpotrf's info
 #pragma unroll
         for (int c = 0; c < 32; ++c)
@@ -511,9 +520,8 @@ int d_potrf(smcp_ctx *ctx, double *H, int64_t ld, int64_t m, int64_t ncols, int3
     struct Unmute { smcp_ctx *c; ~Unmute() { c->prof_mute--; } } unmute{ctx};
     cudaStream_t sB = ctx->stream, sA = ctx->stream2;
     static const bool lookahead = !(getenv("SMCP_B200_LOOKAHEAD") && atoi(getenv("SMCP_B200_LOOKAHEAD")) == 0);
-    // the second stream pays off once the trailing updates are long enough to hide a panel (m >= 4096);
-    // below that the factorisation is a chain of short kernels and one stream is as fast
-    const bool two = lookahead && (sA != nullptr) && (nblocks > 1) && (m >= 4096);
+    // (measured at m = 1000: 1.49 -> 1.29 ms; below ~512 there is nothing to overlap)
+    const bool two = lookahead && (sA != nullptr) && (nblocks > 1) && (m >= 512);
     if (!two) sA = sB;
     while ((int64_t)ctx->potrf_ev.size() < 2 * nblocks + 2) {
         cudaEvent_t e;
@@ -587,6 +595,53 @@ int d_potrf(smcp_ctx *ctx, double *H, int64_t ld, int64_t m, int64_t ncols, int3
 // (fixed summation order, no atomics).
 // ---------------------------------------------------------------------------------------
 #define PS_THREADS 1024
+// y[i] -= sum_{j < 64} A(i, j) x[j] for i < rows.  TR = false: A(i, j) = A[i + j*ld] (rows of a
+// column panel); TR = true: A(i, j) = A[j + i*ld] (columns of a row panel).  tpr threads share
+// an output when there are few of them; every thread keeps 8 loads in flight.
+template <bool TR>
+__device__ __forceinline__ void potrs_gemv(const double *__restrict__ A, long long ld, long long rows, const double *x, double *y, int t, int nt) {
+    int tpr = 1;
+    while (tpr < 16 && rows * (tpr * 2) <= nt) tpr *= 2;
+    const int per = NB / tpr;                       // columns per thread: 64 .. 4
+    const int part = t & (tpr - 1);
+    const int j0 = part * per;
+    for (long long base = 0; base < rows; base += nt / tpr) {
+        const long long i = base + (t / tpr);
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        if (i < rows && t < (nt / tpr) * tpr) {
+            const double *Ar = TR ? A + i * ld + j0 : A + i + (long long)j0 * ld;
+            const long long st = TR ? 1 : ld;
+            if (per >= 8) {
+                for (int j = 0; j < per; j += 8) {
+                    double v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] = Ar[(long long)(j + q) * st];
+                    s0 = fma(v[0], x[j0 + j], s0);
+                    s1 = fma(v[1], x[j0 + j + 1], s1);
+                    s2 = fma(v[2], x[j0 + j + 2], s2);
+                    s3 = fma(v[3], x[j0 + j + 3], s3);
+                    s0 = fma(v[4], x[j0 + j + 4], s0);
+                    s1 = fma(v[5], x[j0 + j + 5], s1);
+                    s2 = fma(v[6], x[j0 + j + 6], s2);
+                    s3 = fma(v[7], x[j0 + j + 7], s3);
+                }
+            } else {
+                double v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = Ar[(long long)q * st];
+                s0 = fma(v[0], x[j0], s0);
+                s1 = fma(v[1], x[j0 + 1], s1);
+                s2 = fma(v[2], x[j0 + 2], s2);
+                s3 = fma(v[3], x[j0 + 3], s3);
+            }
+        }
+        double sacc = (s0 + s1) + (s2 + s3);
+        // the tpr partial sums of an output sit in consecutive lanes of one warp: fixed-order tree
+        for (int o = 1; o < tpr; o <<= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+        if (part == 0 && i < rows && t < (nt / tpr) * tpr) y[i] -= sacc;
+    }
+}
+
 __global__ void __launch_bounds__(PS_THREADS) potrs_kernel(const double *__restrict__ Hfull, long long ld, long long i0, long long m,
                                                            double *__restrict__ yfull, int do_fwd, int do_bwd) {
     extern __shared__ double psm[];
@@ -624,19 +679,9 @@ __global__ void __launch_bounds__(PS_THREADS) potrs_kernel(const double *__restr
             if (lane + 32 < kb) ys[k0 + lane + 32] = x1;
         }
         __syncthreads();
-        for (long long i = k0 + kb + tid; i < m; i += PS_THREADS) {
-            const double *Lr = H + i + k0 * ld;
-            const double *xk = ys + k0;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll 4
-            for (int j = 0; j < NB; j += 4) {       // here kb == NB (rows remain below the block)
-                s0 = fma(Lr[(long long)j * ld], xk[j], s0);
-                s1 = fma(Lr[(long long)(j + 1) * ld], xk[j + 1], s1);
-                s2 = fma(Lr[(long long)(j + 2) * ld], xk[j + 2], s2);
-                s3 = fma(Lr[(long long)(j + 3) * ld], xk[j + 3], s3);
-            }
-            ys[i] -= (s0 + s1) + (s2 + s3);
-        }
+        // rows below the block (then kb == NB): 8 loads in flight per thread, several threads per row
+        // when few rows are left -- the loads are L2 round trips, four at a time left them exposed
+        if (m - k0 - kb > 0) potrs_gemv<false>(H + (k0 + kb) + k0 * ld, ld, m - k0 - kb, ys + k0, ys + k0 + kb, tid, PS_THREADS);
         __syncthreads();
     }
     // backward: L^T x = y
@@ -653,6 +698,16 @@ __global__ void __launch_bounds__(PS_THREADS) potrs_kernel(const double *__restr
             const double *Lc = H + (k0 + c) * ld;
             double s0 = 0.0, s1 = 0.0;
             long long i = k0 + kb + lane;
+            for (; i + 224 < m; i += 256) {          // 8 loads in flight
+                double v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = Lc[i + 32 * q];
+#pragma unroll
+                for (int q = 0; q < 8; q += 2) {
+                    s0 = fma(v[q], ys[i + 32 * q], s0);
+                    s1 = fma(v[q + 1], ys[i + 32 * (q + 1)], s1);
+                }
+            }
             for (; i + 32 < m; i += 64) {
                 s0 = fma(Lc[i], ys[i], s0);
                 s1 = fma(Lc[i + 32], ys[i + 32], s1);
