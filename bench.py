@@ -314,7 +314,12 @@ def run_b200(args):
     if roof is not None and os.path.exists(traffic_file):
         with open(traffic_file) as fh:
             tr = json.load(fh)
-        roof["traffic"] = tr.get(roof["kernel"])
+        ent = tr.get(roof["kernel"])
+        if isinstance(ent, dict):
+            # DRAM bytes (read + write) of one launch of the dominant kernel, from an `ncu --set full` capture
+            roof["traffic"] = ent.get("bytes")
+            roof["traffic_unit"] = "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum)"
+            roof["traffic_source"] = ent.get("source")
 
     cpu = cpu_baseline(args.workload, fam, K)
 
