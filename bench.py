@@ -213,7 +213,11 @@ class IterTimer:
 
 
 def run_b200(args):
-    os.environ["NCCL_DEBUG"] = os.environ.get("SMCP_NCCL_DEBUG", "WARN")    # keep stdout to the one JSON line
+    # keep stdout to the one JSON line: NCCL prints its version banner on stdout at NCCL_DEBUG >= VERSION
+    if os.environ.get("SMCP_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = os.environ["SMCP_NCCL_DEBUG"]
+    else:
+        os.environ.pop("NCCL_DEBUG", None)
     rank, world, local, pg = dist_setup(args)
     os.environ["LOCAL_RANK"] = str(local)
     from smcp_b200 import solvers, device
@@ -323,6 +327,22 @@ def run_b200(args):
 
     cpu = cpu_baseline(args.workload, fam, K)
 
+    # time-to-solve at SMCP's default tolerances (the second half of BASELINE.json's metric): the same
+    # problem solved to optimality through the public API, wall clock over the iterations
+    tts = None
+    if world == 1:
+        solvers.options["maxiters"] = 100
+        timer3 = IterTimer(ctx.sync)
+        solvers._iteration_hook = timer3
+        sol3 = P.solve_feas(kktsolver="chol", primalstart=start)
+        ctx.sync()
+        solvers._iteration_hook = None
+        ks = sorted(timer3.t)
+        tts = {"status": sol3["status"], "iterations": int(sol3["iterations"]),
+               "seconds": (timer3.t[ks[-1]] - timer3.t[ks[0]]) if len(ks) > 1 else None,
+               "primal_objective": sol3["primal objective"], "dual_objective": sol3["dual objective"],
+               "primal_infeasibility": sol3["primal infeasibility"], "gap": sol3["gap"]}
+
     out = {
         "metric": "s_per_ipm_iteration", "value": dev_s, "unit": "s/iter", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": dev_s * 1e3, "higher_is_better": False,
@@ -338,6 +358,7 @@ def run_b200(args):
         "cpu_baseline": cpu,
         "kernel_ms_per_step": {k: v["ms"] / K for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])},
         "family_rooflines": per_family,
+        "time_to_solve": tts,
         "status": sol["status"], "iterations": iters,
         "fp64_gemm_peak_tflops": fp64_peak,
     }

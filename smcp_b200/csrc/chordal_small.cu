@@ -1215,17 +1215,21 @@ int ks_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
         a.t.X = U;
         a.t.Lt = h->Lt;
         a.t.Yaa = h->Yaa;
-        if (s->chain) {
+        bool ch = s->chain;
+        if (ch) {
             if (chain_prepare(h)) return -1;
+            ch = h->chain_ok;          // accuracy guard: see chain_prepare
+        }
+        if (ch) {
             if (chain_sweep(s, true, U, h->Lt, h->phi_up, h->psi_up, h->Yaa, batch, big ? "hessian_up_chain_batch" : "hessian_up_chain")) return -1;
         } else if (launch_sweep(s, sweep_up_kernel<SW_HUP>, WS_HUP, a, s->up, batch, big ? "hessian_up_batch" : "hessian_up")) return -1;
-        if (big || s->chain) {
+        if (big || ch) {
             // one thread per (supernode, matrix) for the single-column supernodes, warps for the rest
             smcp_ctx *ctx = s->ctx;
             fill_common(s, a, s->flat, batch);
             long long items = (long long)s->d.nsn * batch;
             long long grid = std::min<long long>((items + 255) / 256, (long long)ctx->num_sms * 16);
-            if (!s->chain) {      // chain: fused into the final pass of the up sweep
+            if (!ch) {      // chain: fused into the final pass of the up sweep
                 LaunchScope ls(ctx, "hessian_scale_batch", 1, (double)batch);
                 hscale_nn1_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(a);
             }
@@ -1236,7 +1240,7 @@ int ks_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
             a.list = nullptr;
             a.nlist = 0;
         } else if (launch_flat<FL_HSCALE>(s, a, batch, "hessian_scale")) return -1;
-        if (s->chain) return chain_sweep(s, false, U, h->Lt, h->phi_dn, h->psi_dn, nullptr, batch, big ? "hessian_down_chain_batch" : "hessian_down_chain");
+        if (ch) return chain_sweep(s, false, U, h->Lt, h->phi_dn, h->psi_dn, nullptr, batch, big ? "hessian_down_chain_batch" : "hessian_down_chain");
         return launch_sweep(s, sweep_down_kernel, WS_DOWN, a, s->down, batch, big ? "hessian_down_batch" : "hessian_down");
     }
     if (!h->have_Raa) {

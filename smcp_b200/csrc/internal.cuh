@@ -166,6 +166,8 @@ struct smcp_hess {
     bool have_Raa = false;
     double *phi_up = nullptr, *phi_dn = nullptr, *psi_up = nullptr, *psi_dn = nullptr;   // chain path: segment propagators of the two sweeps
     bool have_phi = false;
+    bool chain_ok = true;      // the segment propagators of this scaling point are tame enough for the segment-parallel sweeps
+    double chain_gamma = 0.0;  // largest |entry| of the propagators (growth of the boundary recurrence)
     const double *L = nullptr; // the factor it was built from (not owned)
 };
 

@@ -90,3 +90,33 @@ def test_chain_hessian_matches_oracle_and_sequential(n, bw, eps, tol):
     To = Lo.copy()[None, :]
     sn.llt(symb, To)
     assert _rel(outs["chain"][2] * w, To[0] * w) < 1e-12
+
+
+def test_full_solve_converges_with_accuracy_guard():
+    """Solve a band SDP to SMCP's default tolerances.  Late iterates have cond(S) > 1e10: the
+    segment propagators grow and the segment-parallel sweeps lose digits (the solver used to stall
+    at a primal residual of ~1e-5 on the benchmark problem); the guard in chain_prepare switches
+    those scaling points to the sequential sweeps.  The result must match a run that uses the
+    sequential sweeps throughout: same status, same iteration count, same objectives."""
+    import smcp_b200 as S
+    from smcp_b200 import solvers
+    from smcp_b200.device import DeviceBackend
+    solvers.options["show_progress"] = False
+    solvers.options["maxiters"] = 100
+    solvers.set_backend_factory(lambda symb: DeviceBackend(symb))
+    sols = {}
+    for mode in ("guarded", "sequential"):
+        if mode == "sequential":
+            os.environ["SMCP_B200_NO_CHAIN"] = "1"
+        try:
+            P = S.band_SDP(1500, 120, 5, seed=0)
+            sols[mode] = P.solve_feas(kktsolver="chol", primalstart={"x": P._X0})
+        finally:
+            os.environ.pop("SMCP_B200_NO_CHAIN", None)
+    solvers.set_backend_factory(None)
+    a, b = sols["guarded"], sols["sequential"]
+    assert a["status"] == "optimal" and b["status"] == "optimal", (a["status"], b["status"])
+    assert abs(a["iterations"] - b["iterations"]) <= 1, (a["iterations"], b["iterations"])
+    assert a["primal infeasibility"] <= 1e-8
+    for key in ("primal objective", "dual objective"):
+        assert abs(a[key] - b[key]) <= 1e-8 * max(1.0, abs(b[key])), (key, a[key], b[key])
