@@ -29,6 +29,12 @@ if cfg == "C2":
 elif cfg == "C4":
     P = S.mtxnorm_SDP(200, 200, 500, density=1.0, seed=0)
     method = "esd"
+    if os.environ.get("RUNCFG_METHOD") == "feas":
+        # the reference's benchmark flow ("M1"): primal phase 1, then the feasible-start solver
+        t1 = time.time()
+        X0, sol1 = P.solve_phase1(kktsolver="chol")
+        print("phase 1: %.2f s, %s iterations" % (time.time() - t1, sol1["iterations"] if sol1 else 0), flush=True)
+        method, kw = "feas", {"primalstart": {"x": X0}}
 elif cfg == "C3":
     n = int(sys.argv[3]) if len(sys.argv) > 3 else 2000
     m = int(sys.argv[4]) if len(sys.argv) > 4 else 10000
@@ -46,6 +52,9 @@ elif cfg == "C5":
     e = rng.integers(0, n, size=(3 * n // 2, 2))
     P = S.maxcut_SDP(n, e)
     method = "esd"
+    if os.environ.get("RUNCFG_METHOD") == "feas":
+        # X = I is strictly feasible for the max-cut relaxation (diag(X) = 1)
+        method, kw = "feas", {"primalstart": {"x": sp.identity(n, format="csc")}}
 else:
     raise SystemExit("unknown config")
 print("%s: %s generated in %.1f s" % (cfg, P, time.time() - t0), flush=True)
