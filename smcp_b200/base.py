@@ -134,9 +134,16 @@ class SDP(object):
         As = A[:, 1:].tocsc().copy()
         scale = np.ones(A.shape[0])
         scale[Id] = 1.0 / np.sqrt(2.0)
-        As = sp.diags(scale) @ As
-        M = (As.T @ As).tocsc()
-        u = spla.spsolve(M, self.b)
+        As = (sp.diags(scale) @ As).tocsc()
+        # least-norm start: (As^T As) u = b.  Dense constraint matrices (mtxnorm: every A_i fills the
+        # same 40 400 rows) go through BLAS on the non-empty rows; sparse ones through SciPy's solver
+        rows = np.unique(As.indices)
+        if As.nnz > 0.2 * len(rows) * max(1, m) and len(rows) * m * 8 <= (2 << 30):
+            D = np.asarray(As[rows, :].todense())
+            u = np.linalg.solve(D.T @ D, self.b)
+        else:
+            M = (As.T @ As).tocsc()
+            u = spla.spsolve(M, self.b)
         x = 0.5 * (A[:, 1:] @ u)
         I, J = misc.ind2sub(n, self.I)
         X0 = sp.csc_matrix((x[self.I], (I, J)), shape=(n, n))

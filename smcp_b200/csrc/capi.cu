@@ -258,7 +258,6 @@ extern "C" int smcp_sym_create(smcp_ctx *ctx, const smcp_sym_desc *D, smcp_sym *
     for (int i = 0; i <= nsn; ++i) tp3[i] = i;
     for (int i = 0; i < nsn; ++i) ts3[i] = i;
     if (upload_sched(s, nsn, tp3, ts3, dp3, di3, &s->flat)) return -1;
-    s->h_root_boff = (long long)D->blkptr[nsn > 0 ? nsn - 1 : 0];
     s->max_nj_small = s->max_nj;
     // large frontal matrices: dense multi-CTA path; an explicit SMCP_B200_BIG_NJ also applies to
     // tiny-clique patterns (tests), which then stay on the CTA-per-supernode kernels

@@ -54,7 +54,6 @@ __global__ void tree_kernel(TreeArgs a) {
         __syncthreads();
         __threadfence();
         for (int p = a.T.task_ptr[t]; p < a.T.task_ptr[t + 1]; ++p) {
-            if (a.T.task_sn[p] + 1 == a.skip_sn1) continue;      // dense root path (front.cu)
             if (a.skipflag && a.skipflag[a.T.task_sn[p]]) continue;   // dense top-set path (bigfront.cu)
             Node q = node_of(a.S, a.T.task_sn[p]);
             if (OP == OP_CHOL) op_chol<false>(a, q, b);

@@ -30,7 +30,6 @@ struct TreeArgs {
     double *cta_ws;
     long long ws_stride;
     int use_smem;
-    int skip_sn1;        // supernode (index + 1) left to the dense root path, 0 = none
     const int *skipflag; // per supernode: 1 = left to the dense top-set path (bigfront.cu); may be null
 };
 

@@ -134,12 +134,6 @@ struct smcp_sym {
     int chW = 0, chN = 0, chP = 0, ch_root_off = 0, ch_root_nj = 0;
     double *ch_state = nullptr;      // batch x P x D boundary states
     size_t ch_state_cap = 0;
-    // large root supernode processed by dense multi-CTA kernels for single matrices (front.cu)
-    int big_root = -1, root_nn = 0, root_nch = 0;
-    const int *root_ch = nullptr, *root_inv = nullptr;
-    double *root_ws = nullptr;       // 3 x nn x nn
-    int *root_info = nullptr;
-    long long h_root_boff = 0;
     // top set of large supernodes (and their ancestors) processed by dense kernels for single matrices (bigfront.cu)
     std::vector<BigNode> big;    // ascending supernode index = post-order
     const int *big_flag = nullptr, *big_inv = nullptr, *big_ch = nullptr;
@@ -216,14 +210,7 @@ int big_hess_prep(smcp_sym *s, const BigNode &q, const double *L0, const double 
 int big_hess_prep_inv(smcp_sym *s, const BigNode &q, const double *Yaa_all, double *Raa_all);
 int big_hess_fwd_batched(smcp_sym *s, const double *Lt, const double *Yaa_all, double *U, int64_t batch);
 
-// dense root supernode (front.cu)
-int root_setup(smcp_sym *s, const smcp_sym_desc *D);
-int root_cholesky(smcp_sym *s, double *X, int64_t b);
-int root_llt(smcp_sym *s, double *X, int64_t b);
-int root_hess_up(smcp_sym *s, const double *Lt, double *X, int64_t b);
-int root_hess_inv(smcp_sym *s, const double *Lt, double *X, int64_t b);
-int root_projinv(smcp_sym *s, double *X, int64_t b);
-int root_completion(smcp_sym *s, double *X, const double *Xin, int64_t b);
+// blocked triangular solves (front.cu)
 int d_trsm_left_lower(smcp_ctx *ctx, bool trans, const double *L, int64_t ldl, int64_t n, double *B, int64_t ldb, int64_t nrhs);
 
 // dense kernels (dense.cu)
