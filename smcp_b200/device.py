@@ -410,6 +410,25 @@ class DeviceBackend:
             _ck(self.lib, self.lib.smcp_csp_get(self.sym, self._slot(buf, k), out[k]))
         return out
 
+    def trsm(self, Lbuf, B, trans="N"):
+        """``chompack.trsm(L, B[, trans='T'])`` (``solvers.py:491-492``): B <- L^{-1} B or L^{-T} B for a
+        dense n x k matrix whose rows are in the internal order of ``symb``.  Returns a new array
+        (the device path keeps such blocks resident; this host round trip exists for tests)."""
+        B = np.asarray(B, dtype=np.float64)
+        n, k = B.shape
+        nblk = self.symb.nblk
+        count = max(1, -(-(n * k) // nblk))
+        flat = np.zeros(count * nblk)
+        flat[:n * k] = B.reshape(-1, order="F")
+        buf = self.alloc_batch(count)
+        try:
+            self.set_batch(buf, flat.reshape(count, nblk))
+            _ck(self.lib, self.lib.smcp_csp_trsm(self.sym, Lbuf, buf, n, k, 1 if trans == "T" else 0))
+            out = self.get_batch(buf, count).reshape(-1)[:n * k].reshape(n, k, order="F")
+        finally:
+            self.free_batch(buf)
+        return out
+
     def cholesky_batch(self, buf, count):
         info = np.zeros(count, dtype=np.int32)
         _ck(self.lib, self.lib.smcp_csp_cholesky(self.sym, buf, int(count), info))

