@@ -182,6 +182,10 @@ int smcp_host_maxcardsearch(int64_t n, const int64_t *colptr, const int64_t *row
  * (elimination tree) may be NULL */
 int smcp_host_embed(int64_t n, const int64_t *colptr, const int64_t *rowind, int64_t *fcolptr,
                     int64_t *frowind, int64_t *parent);
+/* the alpha x alpha gather map of chompack.symbolic's clique tree (smcp_sym_desc.aaidx) from the
+ * supernode arrays of smcp_sym_desc; nn = columns and nj = rows of every supernode */
+int smcp_host_aaidx(int64_t nsn, const int64_t *snpar, const int64_t *nn, const int64_t *nj, const int64_t *relptr,
+                    const int64_t *relidx, const int64_t *blkptr, const int64_t *updptr, int64_t *aaidx);
 
 #ifdef __cplusplus
 }

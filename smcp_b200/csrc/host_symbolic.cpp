@@ -196,4 +196,34 @@ int smcp_host_embed(int64_t n, const int64_t *colptr, const int64_t *rowind, int
     return 0;
 }
 
+// alpha x alpha gather map of the clique tree (smcp_b200/symbolic.py:Symbolic, "aaidx"): for every
+// supernode k with separator alpha_k, the blkval offset of entry (alpha_i, alpha_j) of the chordal
+// matrix, column-major na_k x na_k at updptr[k].  An entry lives in the parent's block when its
+// column is one of the parent's own columns, otherwise it is found through the parent's map
+// (top-down: parents have larger indices).  nupd reaches 1.7e8 on the n = 20 000 max-cut pattern,
+// where the NumPy version spent 8 of the 10 seconds of the whole symbolic phase.
+int smcp_host_aaidx(int64_t nsn, const int64_t *snpar, const int64_t *nn, const int64_t *nj, const int64_t *relptr,
+                    const int64_t *relidx, const int64_t *blkptr, const int64_t *updptr, int64_t *aaidx) {
+    if (nsn < 0 || !aaidx) return -1;
+    for (int64_t k = nsn - 1; k >= 0; --k) {
+        const int64_t a = nj[k] - nn[k];
+        if (a == 0) continue;
+        const int64_t pk = snpar[k];
+        if (pk < 0) return -2;                         // a separator needs a parent
+        const int64_t *rel = relidx + relptr[k];
+        const int64_t nnp = nn[pk], njp = nj[pk], nap = njp - nnp;
+        const int64_t *par = aaidx + updptr[pk];
+        int64_t *out = aaidx + updptr[k];
+        for (int64_t j = 0; j < a; ++j) {
+            const int64_t rj = rel[j];
+            for (int64_t i = 0; i < a; ++i) {
+                const int64_t ri = rel[i];
+                const int64_t lo_r = ri > rj ? ri : rj, lo_c = ri > rj ? rj : ri;
+                out[j * a + i] = (lo_c < nnp) ? blkptr[pk] + lo_c * njp + lo_r : par[(lo_c - nnp) * nap + (lo_r - nnp)];
+            }
+        }
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -88,6 +88,7 @@ API = {
     "smcp_host_min_degree": (_int, [_i64, _i64p, _i64p, _i64p]),
     "smcp_host_maxcardsearch": (_int, [_i64, _i64p, _i64p, _i64p]),
     "smcp_host_embed": (_int, [_i64, _i64p, _i64p, _i64p, C.c_void_p, C.c_void_p]),
+    "smcp_host_aaidx": (_int, [_i64, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p]),
 }
 
 

@@ -275,6 +275,36 @@ def _postorder(parent):
     return post
 
 
+def _py_aaidx(nsn, snpar, nn, na, nj, relptr, relidx, blkptr, updptr, nupd):
+    """Specification of ``smcp_host_aaidx``: blkval offsets of the alpha x alpha entries of every
+    supernode, column-major per supernode (top-down: parents have larger index)."""
+    aaidx = np.empty(nupd, dtype=np.int64)
+    for k in range(nsn - 1, -1, -1):
+        a = int(na[k])
+        if a == 0:
+            continue
+        pk = snpar[k]
+        rel = relidx[relptr[k]:relptr[k + 1]]
+        ri = np.repeat(rel[None, :], a, axis=0).T   # ri[i,j] = rel[i]
+        rj = ri.T                                   # rj[i,j] = rel[j]
+        lo_r = np.maximum(ri, rj)
+        lo_c = np.minimum(ri, rj)
+        out = np.empty((a, a), dtype=np.int64)
+        nnp = int(nn[pk])
+        njp = int(nj[pk])
+        own = lo_c < nnp
+        out[own] = blkptr[pk] + lo_c[own] * njp + lo_r[own]
+        if not own.all():
+            nap = int(na[pk])
+            par = aaidx[updptr[pk]:updptr[pk + 1]].reshape(nap, nap)  # [col, row] storage
+            rr = lo_r[~own] - nnp
+            cc = lo_c[~own] - nnp
+            out[~own] = par[cc, rr]
+        # store column-major: element (i,j) at j*a+i
+        aaidx[updptr[k]:updptr[k + 1]] = out.T.reshape(-1)
+    return aaidx
+
+
 class Symbolic:
     """Supernodal clique tree of a *chordal* lower-triangular pattern given in a perfect
     elimination ordering (the ``symb = symbolic(Vp)`` object of ``solvers.py:314, 1555``).
@@ -435,30 +465,14 @@ class Symbolic:
         self.depth = depth
 
         # alpha x alpha gather map (top-down: parents have larger index)
-        aaidx = np.empty(self.nupd, dtype=np.int64)
-        for k in range(nsn - 1, -1, -1):
-            a = int(na[k])
-            if a == 0:
-                continue
-            pk = snpar[k]
-            rel = relidx[relptr[k]:relptr[k + 1]]
-            ri = np.repeat(rel[None, :], a, axis=0).T   # ri[i,j] = rel[i]
-            rj = ri.T                                   # rj[i,j] = rel[j]
-            lo_r = np.maximum(ri, rj)
-            lo_c = np.minimum(ri, rj)
-            out = np.empty((a, a), dtype=np.int64)
-            nnp = int(nn[pk])
-            njp = int(nj[pk])
-            own = lo_c < nnp
-            out[own] = blkptr[pk] + lo_c[own] * njp + lo_r[own]
-            if not own.all():
-                nap = int(na[pk])
-                par = aaidx[updptr[pk]:updptr[pk + 1]].reshape(nap, nap)  # [col, row] storage
-                rr = lo_r[~own] - nnp
-                cc = lo_c[~own] - nnp
-                out[~own] = par[cc, rr]
-            # store column-major: element (i,j) at j*a+i
-            aaidx[updptr[k]:updptr[k + 1]] = out.T.reshape(-1)
+        lib = _native()
+        if lib is not None:
+            aaidx = np.empty(self.nupd, dtype=np.int64)
+            if lib.smcp_host_aaidx(nsn, _i64(snpar), _i64(nn), _i64(nj), _i64(relptr), _i64(relidx), _i64(blkptr),
+                                   _i64(updptr), aaidx) != 0:
+                raise RuntimeError("smcp_host_aaidx failed")
+        else:
+            aaidx = _py_aaidx(nsn, snpar, nn, na, nj, relptr, relidx, blkptr, updptr, self.nupd)
         self.aaidx = aaidx
 
         # vector space <-> blkval

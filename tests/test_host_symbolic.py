@@ -56,3 +56,14 @@ def test_min_degree_dense_tail_shortcut():
     J = np.concatenate([J.ravel(), np.arange(0, n - 25)])
     cp, ri = sy.lower_pattern(n, I, J)
     assert np.array_equal(sy.min_degree(n, cp, ri), sy._py_min_degree(n, cp, ri))
+
+
+@pytest.mark.parametrize("n,ne,band,seed", [(30, 40, 0, 2), (200, 300, 1, 3), (300, 2000, 0, 5), (150, 0, 3, 6), (1, 0, 0, 0)])
+def test_native_aaidx_matches_python(n, ne, band, seed):
+    cp, ri = _random_pattern(n, ne, seed, band)
+    p = sy.min_degree(n, cp, ri)
+    fc, fr, _ = sy.embed(n, cp, ri, p)
+    symb = sy.Symbolic(n, fc, fr)                # built with the native map
+    ref = sy._py_aaidx(symb.nsn, symb.snpar, symb.nn, symb.na, symb.nj, symb.relptr, symb.relidx, symb.blkptr,
+                       symb.updptr, symb.nupd)
+    assert symb.aaidx.dtype == np.int64 and np.array_equal(symb.aaidx, ref)
