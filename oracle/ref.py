@@ -145,3 +145,10 @@ def SCMcolumn2(H, Av, V, Ip, Jp, Kl, j):
     Hm = dmatrix(H)
     m.SCMcolumn2(Hm, spmatrix(Av), dmatrix(V), imatrix(Ip), imatrix(Jp), imatrix(Kl), int(j))
     return to_numpy(Hm)
+
+
+def sdpa_read(fname, neg=False):
+    """The reference's own ``misc.sdpa_read`` (``misc.c:139-245``) -> (scipy csc, b, blockstruct)."""
+    mod, _ = _load()
+    A, b, bs = mod.sdpa_read(fname, neg=bool(neg))
+    return to_scipy(A), to_numpy(b).ravel(), to_numpy(bs).ravel().astype(np.int64)

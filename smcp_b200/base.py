@@ -29,13 +29,26 @@ class SDP(object):
     """SDP object: ``n``, ``m``, ``A`` (CCS n^2 x (m+1)), ``b``, aggregate sparsity ``I``."""
 
     def __init__(self, A=None, b=None, name=None):
-        self._A = misc.as_csc(A) if A is not None else None
-        self._b = np.asarray(b, dtype=np.float64).ravel() if b is not None else None
-        self._pname = name
+        """``SDP(A, b)`` from problem data, or ``SDP(filename)`` from a sparse SDPA (dat-s) file
+        (``base.py:60-95, 177-195``: the file's primal is negated into SMCP's standard form)."""
         self._I = None
         self._ischordal = None
         self._blockstruct = None
         self._X0 = self._y0 = self._S0 = None
+        if isinstance(A, str):
+            import os
+            self._A, self._b, self._blockstruct = misc.sdpa_read(A, neg=True)
+            self._pname = name or os.path.splitext(os.path.basename(A))[0]
+            return
+        self._A = misc.as_csc(A) if A is not None else None
+        self._b = np.asarray(b, dtype=np.float64).ravel() if b is not None else None
+        self._pname = name
+
+    def write_sdpa(self, fname):
+        """Writes the problem as a sparse SDPA file (``base.py:197-215``; one block unless the
+        object was read from a file with a block structure)."""
+        bs = self._blockstruct if self._blockstruct is not None else np.array([self.n], dtype=np.int64)
+        misc.sdpa_write(fname, self._need(), self.b, bs, neg=True)
 
     def __str__(self):
         return "<SDP: n=%i, m=%i, nnz=%i> %s" % (self.n, self.m, self.nnz, self._pname)

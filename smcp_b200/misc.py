@@ -92,3 +92,94 @@ def phase1_sdp(A, u):
     cols.append(np.full(n + 1, m + 1))
     return as_csc(sp.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
                                 shape=(n2 * n2, m + 2)))
+
+
+# --------------------------------------------------------------------------------------
+# sparse SDPA ("dat-s") files: the format of SDPLIB and of the reference's benchmark problems
+# (``misc.sdpa_read`` / ``sdpa_readhead`` / ``sdpa_write``, ``src/C/misc.c:139-352``)
+# --------------------------------------------------------------------------------------
+def _sdpa_tokens(text):
+    """Numbers of an SDPA body: everything that is not part of a number is a separator
+    (the format allows ``{ } ( ) ,`` around the block structure and the vector b)."""
+    import re
+    return re.findall(r"[+-]?(?:\d+\.?\d*(?:[eEdD][+-]?\d+)?|\.\d+(?:[eEdD][+-]?\d+)?)", text)
+
+
+def sdpa_read(fname, neg=False):
+    """``A, b, blockstruct = sdpa_read(fname[, neg=False])`` (``misc.c:139-245``).
+
+    Reads a sparse SDPA file into the CVXOPT-facing layout of SMCP: ``A`` is CCS of shape
+    n^2 x (m+1), column k = vec of the lower triangle of F_k (entry (i, j), i <= j, of block
+    ``blk`` goes to row ``(i-1+off)*n + (j-1+off)``), ``b`` the m-vector of the file and
+    ``blockstruct`` the signed block sizes (negative = diagonal block).  ``neg=True`` negates
+    all data, which turns the SDPA primal into SMCP's standard form (``base.py:177-195``).
+    Unlike the reference the entries need not be sorted by matrix number."""
+    with open(fname, "r") as fh:
+        lines = fh.readlines()
+    k = 0
+    while k < len(lines) and (lines[k].lstrip()[:1] in ("*", '"') or not lines[k].strip()):
+        k += 1
+    m = int(_sdpa_tokens(lines[k])[0])
+    nblocks = int(_sdpa_tokens(lines[k + 1])[0])
+    tok = _sdpa_tokens("".join(lines[k + 2:]).replace("D", "e").replace("d", "e"))
+    blockstruct = np.array([int(float(t)) for t in tok[:nblocks]], dtype=np.int64)
+    boff = np.concatenate([[0], np.cumsum(np.abs(blockstruct))])
+    n = int(boff[-1])
+    b = np.array([float(t) for t in tok[nblocks:nblocks + m]], dtype=np.float64)
+    body = np.array([float(t) for t in tok[nblocks + m:]], dtype=np.float64)
+    body = body[:5 * (len(body) // 5)].reshape(-1, 5)
+    mno = body[:, 0].astype(np.int64)
+    bno = body[:, 1].astype(np.int64)
+    ii = body[:, 2].astype(np.int64) + boff[bno - 1]
+    jj = body[:, 3].astype(np.int64) + boff[bno - 1]
+    v = body[:, 4]
+    keep = v != 0
+    rows = (ii[keep] - 1) * n + (jj[keep] - 1)
+    sgn = -1.0 if neg else 1.0
+    A = sp.csc_matrix((sgn * v[keep], (rows, mno[keep])), shape=(n * n, m + 1))
+    return as_csc(A), sgn * b, blockstruct
+
+
+def sdpa_readhead(fname):
+    """``n, m, blockstruct = sdpa_readhead(fname)``: the header of a sparse SDPA file."""
+    with open(fname, "r") as fh:
+        lines = fh.readlines()
+    k = 0
+    while k < len(lines) and (lines[k].lstrip()[:1] in ("*", '"') or not lines[k].strip()):
+        k += 1
+    m = int(_sdpa_tokens(lines[k])[0])
+    nblocks = int(_sdpa_tokens(lines[k + 1])[0])
+    tok = _sdpa_tokens("".join(lines[k + 2:k + 4]))
+    blockstruct = np.array([int(float(t)) for t in tok[:nblocks]], dtype=np.int64)
+    return int(np.abs(blockstruct).sum()), m, blockstruct
+
+
+def sdpa_write(fname, A, b, blockstruct, neg=False):
+    """Writes ``(A, b, blockstruct)`` as a sparse SDPA file (``misc.c:281-352``): one line
+    ``<matno> <blkno> <i> <j> <value>`` per stored lower-triangular entry, written as the upper
+    triangular entry (j, i) the format asks for; 12 significant digits like the reference."""
+    A = as_csc(A)
+    b = np.asarray(b, dtype=np.float64).ravel()
+    blockstruct = np.asarray(blockstruct, dtype=np.int64).ravel()
+    n = int(np.abs(blockstruct).sum())
+    boff = np.concatenate([[0], np.cumsum(np.abs(blockstruct))])
+    sgn = -1.0 if neg else 1.0
+    with open(fname, "w") as fh:
+        fh.write("* sparse SDPA data file (created by smcp_b200)\n")
+        fh.write("%i = m\n" % len(b))
+        fh.write("%i = nBlocks\n" % len(blockstruct))
+        fh.write(" ".join("%i" % s for s in blockstruct) + "\n")
+        fh.write(" ".join("%.12g" % (sgn * x) for x in b) + "\n")
+        for k in range(A.shape[1]):
+            r = A.indices[A.indptr[k]:A.indptr[k + 1]]
+            v = A.data[A.indptr[k]:A.indptr[k + 1]]
+            Il, Jl = r % n, r // n                      # row >= column (lower triangle)
+            if np.any(Jl > Il):
+                raise ValueError("strictly upper triangular element in A")
+            blk = np.searchsorted(boff, Jl, side="right")        # 1-based block of the column
+            if np.any(Il >= boff[blk]):
+                raise ValueError("matrix contains elements outside the blocks")
+            for q in range(len(r)):
+                if v[q] != 0.0:
+                    fh.write("%i %i %i %i %.12g\n" % (k, blk[q], Jl[q] - boff[blk[q] - 1] + 1,
+                                                      Il[q] - boff[blk[q] - 1] + 1, sgn * v[q]))

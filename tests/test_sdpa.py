@@ -1,0 +1,85 @@
+"""Sparse SDPA (dat-s) reader / writer, pinned on the reference's own
+``misc.sdpa_read`` compiled unmodified from ``src/C/misc.c`` (oracle/_ref)."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from smcp_b200 import misc
+
+
+SDPA_TEXT = """* a small block-diagonal problem (two blocks, the second one diagonal)
+"second comment line"
+3 = mDIM
+2 = nBLOCK
+{2, -3}
+{1.5, -2, 0.25}
+0 1 1 1 1.0
+0 1 1 2 -0.5
+0 1 2 2 2.0
+0 2 1 1 3.0
+0 2 3 3 1.0
+1 1 1 1 1.0
+1 2 2 2 -1.0
+2 1 1 2 0.75
+2 2 1 1 0
+3 1 2 2 1e-3
+3 2 3 3 2.5D+0
+"""
+
+
+@pytest.fixture()
+def sdpa_file(tmp_path):
+    p = tmp_path / "small.dat-s"
+    p.write_text(SDPA_TEXT)
+    return str(p)
+
+
+def test_sdpa_read_known_answer(sdpa_file):
+    A, b, bs = misc.sdpa_read(sdpa_file)
+    n = 5
+    assert A.shape == (n * n, 4) and np.array_equal(bs, [2, -3])
+    assert np.allclose(b, [1.5, -2.0, 0.25])
+    D = A.toarray()
+    # entry (i, j), i <= j, of block with offset o -> row (i-1+o)*n + (j-1+o)
+    assert D[0 * n + 0, 0] == 1.0 and D[0 * n + 1, 0] == -0.5 and D[1 * n + 1, 0] == 2.0
+    assert D[2 * n + 2, 0] == 3.0 and D[4 * n + 4, 0] == 1.0
+    assert D[0, 1] == 1.0 and D[3 * n + 3, 1] == -1.0
+    assert D[0 * n + 1, 2] == 0.75 and np.count_nonzero(D[:, 2]) == 1          # explicit zero dropped
+    assert D[1 * n + 1, 3] == 1e-3 and D[4 * n + 4, 3] == 2.5                   # Fortran exponent
+    An, bn, _ = misc.sdpa_read(sdpa_file, neg=True)
+    assert np.array_equal(An.toarray(), -D) and np.array_equal(bn, -b)
+    assert misc.sdpa_readhead(sdpa_file)[:2] == (5, 3)
+
+
+def test_sdpa_read_matches_reference_build(sdpa_file):
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    for neg in (False, True):
+        A, b, bs = misc.sdpa_read(sdpa_file, neg=neg)
+        Ar, br, bsr = ref.sdpa_read(sdpa_file, neg=neg)
+        assert np.array_equal(bs, bsr) and np.array_equal(b, br)
+        assert A.shape == Ar.shape and (sp.csc_matrix(A) != sp.csc_matrix(Ar)).nnz == 0
+
+
+def test_sdpa_roundtrip_and_constructor(tmp_path):
+    import smcp_b200 as S
+    rng = np.random.default_rng(0)
+    n, m = 6, 4
+    rows, cols, vals = [], [], []
+    for k in range(m + 1):
+        for _ in range(5):
+            i, j = sorted(rng.integers(0, n, size=2))
+            rows.append(j + n * i)            # lower triangle: row j >= column i
+            cols.append(k)
+            vals.append(float(rng.standard_normal()))
+    A = misc.as_csc(sp.csc_matrix((vals, (rows, cols)), shape=(n * n, m + 1)))
+    b = rng.standard_normal(m)
+    P = S.SDP(A, b)
+    f = str(tmp_path / "rt.dat-s")
+    P.write_sdpa(f)
+    Q = S.SDP(f)
+    assert Q.n == n and Q.m == m
+    assert np.allclose(Q.b, b, rtol=1e-11) and abs(Q.A - A).max() <= 1e-11 * abs(A).max()
