@@ -37,8 +37,23 @@ class SDP(object):
         self._X0 = self._y0 = self._S0 = None
         if isinstance(A, str):
             import os
-            self._A, self._b, self._blockstruct = misc.sdpa_read(A, neg=True)
-            self._pname = name or os.path.splitext(os.path.basename(A))[0]
+            fp, ext = os.path.splitext(A)
+            if ext == ".bz2":
+                # compressed SDPLIB files (``base.py:180-190``): decompress next to a temporary name
+                import bz2, tempfile
+                with open(A, "rb") as fc, tempfile.NamedTemporaryFile("wb", suffix=".dat-s", delete=False) as fo:
+                    fo.write(bz2.decompress(fc.read()))
+                    tmp = fo.name
+                try:
+                    self._A, self._b, self._blockstruct = misc.sdpa_read(tmp, neg=True)
+                finally:
+                    os.remove(tmp)
+                fp = os.path.splitext(fp)[0]
+            elif ext == ".dat-s":
+                self._A, self._b, self._blockstruct = misc.sdpa_read(A, neg=True)
+            else:
+                raise NameError("Unknown file extension")
+            self._pname = name or os.path.basename(fp)
             return
         self._A = misc.as_csc(A) if A is not None else None
         self._b = np.asarray(b, dtype=np.float64).ravel() if b is not None else None
@@ -108,13 +123,27 @@ class SDP(object):
     def issparse(self):
         return len(self.I) <= 0.5 * (self.n * (self.n + 1) / 2)
 
-    @property
-    def nnzs(self):
-        return np.diff(self._need().indptr)
+    def get_nnz(self, i=None):
+        """Number of non-zeros in the lower triangle of A_0 .. A_m, or of A_i (``base.py:279-293``)."""
+        cnt = np.diff(self._need().indptr)
+        if i is None:
+            return cnt
+        if not 0 <= i <= self.m:
+            raise ValueError("index out of range")
+        return int(cnt[i])
 
-    @property
-    def nzcols(self):
-        return misc.nzcolumns(self._need())
+    nnzs = property(get_nnz, doc="Vector with number of nonzeros in lower triangle of A0,A1,...,Am")
+
+    def get_nzcols(self, i=None):
+        """Number of non-zero columns of A_1 .. A_m, or of A_i, i >= 1 (``base.py:299-310``)."""
+        nzc = misc.nzcolumns(self._need())
+        if i is None:
+            return nzc
+        if not 0 < i <= self.m:
+            raise ValueError("index out of range")
+        return int(nzc[i - 1])
+
+    nzcols = property(get_nzcols, doc="Vector with number of nonzero columns in A1,..,Am")
 
     @property
     def ischordal(self):

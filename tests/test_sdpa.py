@@ -83,3 +83,19 @@ def test_sdpa_roundtrip_and_constructor(tmp_path):
     Q = S.SDP(f)
     assert Q.n == n and Q.m == m
     assert np.allclose(Q.b, b, rtol=1e-11) and abs(Q.A - A).max() <= 1e-11 * abs(A).max()
+
+
+def test_sdp_from_bz2_and_counts(sdpa_file, tmp_path):
+    import bz2
+    import smcp_b200 as S
+    z = str(tmp_path / "small.dat-s.bz2")
+    with open(sdpa_file, "rb") as fi, open(z, "wb") as fo:
+        fo.write(bz2.compress(fi.read()))
+    P, Q = S.SDP(sdpa_file), S.SDP(z)
+    assert (P.A != Q.A).nnz == 0 and np.array_equal(P.b, Q.b) and Q._pname == "small"
+    assert np.array_equal(P.get_nnz(), [5, 2, 1, 2]) and P.get_nnz(1) == 2
+    assert np.array_equal(P.get_nzcols(), P.nzcols) and P.get_nzcols(1) == 2
+    with pytest.raises(ValueError):
+        P.get_nzcols(0)
+    with pytest.raises(NameError):
+        S.SDP(str(tmp_path / "x.txt"))
