@@ -1248,3 +1248,77 @@ def conelp(c, G, h, dims=None, kktsolver="chol"):
     sol["z"] = z
     sol["s"] = sv
     return sol
+
+
+def lp(c, G, h, kktsolver="chol"):
+    """Linear program  min c'x  s.t. Gx + s = h, s >= 0  through ``conelp`` (``solvers.py:2602-2603``)."""
+    G = sp.csc_matrix(G)
+    return conelp(c, G, h, dims={"l": G.shape[0], "q": [], "s": []}, kktsolver=kktsolver)
+
+
+def _stack(blocks_G, blocks_h):
+    G = sp.vstack([sp.csc_matrix(g) for g in blocks_G], format="csc")
+    h = np.concatenate([np.asarray(v, dtype=np.float64).reshape(-1, order="F") for v in blocks_h])
+    return G, h
+
+
+def socp(c, Gl=None, hl=None, Gq=None, hq=None, kktsolver="chol"):
+    """Second-order cone program through ``conelp`` (``solvers.py:2606-2648``; the reference's version
+    fails on its first ``dims['l'].append`` — this one follows its documented contract): ``Gq[k]``,
+    ``hq[k]`` describe the k-th cone ``s_k = hq[k] - Gq[k] x`` with ``s_k[0] >= ||s_k[1:]||``.
+    Returns ``conelp``'s dictionary with ``zl, sl`` and the lists ``zq, sq`` instead of ``z, s``."""
+    if Gq is None or hq is None:
+        raise ValueError("'Gq' and 'hq' cannot be zero")
+    dims = {"l": 0, "q": [], "s": []}
+    Gs_, hs_ = [], []
+    if Gl is not None and hl is not None:
+        dims["l"] = sp.csc_matrix(Gl).shape[0]
+        Gs_.append(Gl)
+        hs_.append(hl)
+    for Gk, hk in zip(Gq, hq):
+        dims["q"].append(sp.csc_matrix(Gk).shape[0])
+        Gs_.append(Gk)
+        hs_.append(hk)
+    G, h = _stack(Gs_, hs_)
+    sol = conelp(c, G, h, dims=dims, kktsolver=kktsolver)
+    z, s = sol.pop("z"), sol.pop("s")
+    N = dims["l"]
+    sol["zl"] = z[:N] if (N and z is not None) else None
+    sol["sl"] = s[:N] if (N and s is not None) else None
+    sol["zq"], sol["sq"] = [], []
+    for nq in dims["q"]:
+        sol["zq"].append(z[N:N + nq] if z is not None else None)
+        sol["sq"].append(s[N:N + nq] if s is not None else None)
+        N += nq
+    return sol
+
+
+def sdp(c, Gl=None, hl=None, Gs=None, hs=None, kktsolver="chol"):
+    """Semidefinite program through ``conelp`` (``solvers.py:2651-2699``): ``Gs[k]`` is
+    ns_k^2 x n (column j = vec of the symmetric matrix multiplying x_j, column-major), ``hs[k]``
+    an ns_k x ns_k matrix.  Returns ``conelp``'s dictionary with ``zl, sl`` and the lists
+    ``zs, ss`` of ns_k x ns_k arrays instead of ``z, s``."""
+    if Gs is None or hs is None:
+        raise ValueError("'Gs' and 'hs' cannot be zero")
+    dims = {"l": 0, "q": [], "s": []}
+    G_, h_ = [], []
+    if Gl is not None and hl is not None:
+        dims["l"] = sp.csc_matrix(Gl).shape[0]
+        G_.append(Gl)
+        h_.append(hl)
+    for Gk, hk in zip(Gs, hs):
+        dims["s"].append(int(round(math.sqrt(sp.csc_matrix(Gk).shape[0]))))
+        G_.append(Gk)
+        h_.append(hk)
+    G, h = _stack(G_, h_)
+    sol = conelp(c, G, h, dims=dims, kktsolver=kktsolver)
+    z, s = sol.pop("z"), sol.pop("s")
+    N = dims["l"]
+    sol["zl"] = z[:N] if (N and z is not None) else None
+    sol["sl"] = s[:N] if (N and s is not None) else None
+    sol["zs"], sol["ss"] = [], []
+    for ns in dims["s"]:
+        sol["zs"].append(z[N:N + ns * ns].reshape(ns, ns, order="F") if z is not None else None)
+        sol["ss"].append(s[N:N + ns * ns].reshape(ns, ns, order="F") if s is not None else None)
+        N += ns * ns
+    return sol

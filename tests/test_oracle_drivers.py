@@ -117,3 +117,30 @@ def test_product_backend_fails_loudly_without_cuda():
         pass
     with pytest.raises(RuntimeError):
         S.band_SDP(10, 3, 1, seed=0)
+
+
+def test_lp_socp_sdp_front_ends(oracle_backend):
+    """solvers.lp / socp / sdp (solvers.py:2602-2699) are thin wrappers over conelp: the CVXOPT
+    user-guide cone LP split into its parts must give the same optimum through each of them, and a
+    small LP has a known vertex solution."""
+    from smcp_b200 import solvers
+    c_, G_, h_, dims = CONELP
+    # LP: min -4x - 5y  s.t. 2x + y <= 3, x + 2y <= 3, x, y >= 0  ->  x = y = 1
+    sol = solvers.lp(np.array([-4.0, -5.0]), np.array([[2.0, 1.0], [1.0, 2.0], [-1.0, 0.0], [0.0, -1.0]]),
+                     np.array([3.0, 3.0, 0.0, 0.0]))
+    assert sol["status"] == "optimal" and np.allclose(sol["x"], [1.0, 1.0], atol=1e-6)
+    # the 's' part of the user-guide problem alone, through sdp(), against conelp() on the same data
+    Gs, hs = G_[10:19, :], h_[10:19].reshape(3, 3, order="F")
+    a = solvers.conelp(c_, Gs, h_[10:19], {"l": 0, "q": [], "s": [3]})
+    b = solvers.sdp(c_, Gs=[Gs], hs=[hs])
+    assert a["status"] == b["status"]
+    if a["status"] == "optimal":
+        assert np.allclose(a["x"], b["x"], atol=1e-7)
+        assert b["zs"][0].shape == (3, 3) and b["zl"] is None
+    # 'l' + 'q' parts through socp()
+    a = solvers.conelp(c_, G_[:10, :], h_[:10], {"l": 2, "q": [4, 4], "s": []})
+    b = solvers.socp(c_, Gl=G_[:2, :], hl=h_[:2], Gq=[G_[2:6, :], G_[6:10, :]], hq=[h_[2:6], h_[6:10]])
+    assert a["status"] == b["status"]
+    if a["status"] == "optimal":
+        assert np.allclose(a["x"], b["x"], atol=1e-7)
+        assert len(b["zq"]) == 2 and len(b["sq"][1]) == 4 and len(b["zl"]) == 2
