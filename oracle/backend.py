@@ -72,6 +72,12 @@ class OracleBackend:
     def projected_inverse(self, buf):
         sn.projected_inverse(self.symb, buf)
 
+    def trsm(self, Lbuf, B, trans="N"):
+        """chompack.trsm: returns L^{-1} B / L^{-T} B (rows of B in the internal order)."""
+        out = np.array(B, dtype=np.float64)
+        sn.trsm(self.symb, Lbuf, out, trans)
+        return out
+
     def llt(self, buf):
         sn.llt(self.symb, buf)
 

@@ -22,7 +22,7 @@ import scipy.sparse.linalg as spla
 from . import misc, solvers
 from .symbolic import Symbolic, embed, maxcardsearch, min_degree, lower_pattern
 
-__all__ = ["SDP", "band_SDP", "mtxnorm_SDP", "rand_SDP", "maxcut_SDP", "mk_rand"]
+__all__ = ["SDP", "band_SDP", "mtxnorm_SDP", "rand_SDP", "maxcut_SDP", "mk_rand", "completion"]
 
 
 class SDP(object):
@@ -38,6 +38,9 @@ class SDP(object):
         if isinstance(A, str):
             import os
             fp, ext = os.path.splitext(A)
+            if ext == ".bz2" and fp.endswith(".pkl"):
+                self._load(A)
+                return
             if ext == ".bz2":
                 # compressed SDPLIB files (``base.py:180-190``): decompress next to a temporary name
                 import bz2, tempfile
@@ -51,6 +54,9 @@ class SDP(object):
                 fp = os.path.splitext(fp)[0]
             elif ext == ".dat-s":
                 self._A, self._b, self._blockstruct = misc.sdpa_read(A, neg=True)
+            elif ext == ".pkl":
+                self._load(A)
+                return
             else:
                 raise NameError("Unknown file extension")
             self._pname = name or os.path.basename(fp)
@@ -58,6 +64,28 @@ class SDP(object):
         self._A = misc.as_csc(A) if A is not None else None
         self._b = np.asarray(b, dtype=np.float64).ravel() if b is not None else None
         self._pname = name
+
+    def _load(self, fname):
+        """Load problem data saved by ``save`` (``base.py:219-238``)."""
+        import bz2, pickle
+        raw = open(fname, "rb").read()
+        D = pickle.loads(bz2.decompress(raw) if fname.endswith(".bz2") else raw)
+        self._A = misc.as_csc(D["A"])
+        self._b = np.asarray(D["b"], dtype=np.float64).ravel()
+        self._X0, self._y0, self._S0, self._pname = D["X0"], D["y0"], D["S0"], D["pname"]
+
+    def save(self, fname=None, compress=False):
+        """Save problem data (and the generator's strictly feasible point, if any) to a pickle file
+        ``<fname>.pkl`` or ``<fname>.pkl.bz2`` (``base.py:240-270``); refuses to overwrite."""
+        import bz2, os, pickle
+        fname = (fname or self._pname) + (".pkl.bz2" if compress else ".pkl")
+        if os.path.isfile(fname):
+            raise IOError("file %s already exists" % fname)
+        D = {"A": self._need(), "b": self._b, "X0": self._X0, "y0": self._y0, "S0": self._S0, "pname": self._pname}
+        raw = pickle.dumps(D)
+        with open(fname, "wb") as f:
+            f.write(bz2.compress(raw) if compress else raw)
+        return fname
 
     def write_sdpa(self, fname):
         """Writes the problem as a sparse SDPA file (``base.py:197-215``; one block unless the
@@ -458,3 +486,32 @@ class maxcut_SDP(SDP):
         self._A = misc.as_csc(sp.csc_matrix((vals, (rows, cols)), shape=(n * n, n + 1)))
         self._b = np.ones(n)
         self._pname = "maxcut_n%i" % n
+
+
+def completion(X):
+    """Maximum-determinant positive definite completion of the sparse symmetric matrix ``X``
+    (lower triangle used) as a dense n x n array; raises ``ArithmeticError`` if none exists
+    (``base.py:952-973``: ``symbolic`` under a fill-reducing ordering, ``chompack.completion``,
+    then two ``chompack.trsm`` on the identity: X_hat = L^{-T} L^{-1})."""
+    from .chordal import cspmatrix
+    from . import chordal
+    X = sp.tril(sp.csc_matrix(X), format="coo")
+    n = X.shape[0]
+    cp, ri = lower_pattern(n, X.row, X.col)
+    p = maxcardsearch(n, cp, ri)
+    fc, fr, _ = embed(n, cp, ri, p)
+    if fc[-1] != cp[-1]:
+        p = min_degree(n, cp, ri)
+        fc, fr, _ = embed(n, cp, ri, p)
+    symb = Symbolic(n, fc, fr)
+    ops = solvers._make_backend(symb)
+    lo = sp.tril(X, format="csc")
+    full = (lo + sp.tril(lo, -1).T).tocsr()
+    L = cspmatrix.from_vec(ops, np.asarray(full[p[symb.Ip], p[symb.Jp]]).ravel())
+    chordal.completion(L)                       # ArithmeticError if X has no PD completion
+    Z = ops.trsm(L.buf, np.eye(n), "N")
+    Z = ops.trsm(L.buf, Z, "T")                 # internal order: vertex p[perm[i]] at position i
+    order = p[symb.perm]
+    out = np.empty((n, n))
+    out[np.ix_(order, order)] = Z
+    return out

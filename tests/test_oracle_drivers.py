@@ -144,3 +144,29 @@ def test_lp_socp_sdp_front_ends(oracle_backend):
     if a["status"] == "optimal":
         assert np.allclose(a["x"], b["x"], atol=1e-7)
         assert len(b["zq"]) == 2 and len(b["sq"][1]) == 4 and len(b["zl"]) == 2
+
+
+def test_base_completion_is_max_det(oracle_backend):
+    """base.completion(X) (base.py:952-973): the result agrees with X on the pattern and its inverse
+    is zero off the pattern (the defining property of the maximum-determinant completion); a matrix
+    without a positive definite completion raises ArithmeticError."""
+    import scipy.sparse as sp
+    import smcp_b200 as S
+    rng = np.random.default_rng(0)
+    n = 12
+    G = rng.standard_normal((n, n))
+    W = G @ G.T + n * np.eye(n)
+    mask = np.eye(n, dtype=bool)
+    for (i, j) in [(1, 0), (2, 1), (3, 2), (5, 2), (7, 3), (8, 7), (9, 0), (10, 9), (11, 4), (6, 5), (4, 3)]:
+        mask[i, j] = mask[j, i] = True
+    X = sp.csc_matrix(np.tril(W * mask))
+    Xh = S.completion(X)
+    assert np.allclose(Xh, Xh.T, atol=1e-12)
+    assert np.allclose(Xh[mask], W[mask], rtol=1e-10)
+    # inverse vanishes outside the (chordal embedding of the) pattern; the pattern above is a forest + diagonal = chordal
+    Inv = np.linalg.inv(Xh)
+    assert np.abs(Inv[~mask]).max() < 1e-9 * np.abs(Inv).max()
+    bad = W * mask
+    bad[0, 0] = -1.0
+    with pytest.raises(ArithmeticError):
+        S.completion(sp.csc_matrix(np.tril(bad)))

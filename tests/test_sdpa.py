@@ -99,3 +99,21 @@ def test_sdp_from_bz2_and_counts(sdpa_file, tmp_path):
         P.get_nzcols(0)
     with pytest.raises(NameError):
         S.SDP(str(tmp_path / "x.txt"))
+
+
+@pytest.mark.parametrize("compress", [False, True])
+def test_save_and_load_pickle(tmp_path, compress):
+    import smcp_b200 as S
+    from smcp_b200 import solvers
+    from oracle.backend import OracleBackend
+    solvers.set_backend_factory(lambda symb: OracleBackend(symb))      # generators probe the cone
+    try:
+        P = S.band_SDP(12, 4, 2, seed=3)
+    finally:
+        solvers.set_backend_factory(None)
+    f = P.save(str(tmp_path / "prob"), compress=compress)
+    Q = S.SDP(f)
+    assert (P.A != Q.A).nnz == 0 and np.array_equal(P.b, Q.b) and Q._pname == P._pname
+    assert (P._X0 != Q._X0).nnz == 0
+    with pytest.raises(IOError):
+        P.save(str(tmp_path / "prob"), compress=compress)
