@@ -1,30 +1,40 @@
 #!/usr/bin/env python
 """Headline benchmark: seconds per interior-point iteration of SMCP's feasible-start solver
 (method "M1" of the reference's benchmark tables = ``solve_feas`` with ``kktsolver='chol'``,
-doc/source/benchmarks/index.rst:91) on BASELINE.json configs[1]: band SDP n=5000, bandwidth
-5, m=1000.
+doc/source/benchmarks/index.rst:91) on the north-star configuration of BASELINE.json:
+rand_SDP n = 2000 on a sparse aggregate pattern, m = 10 000 (configs[2]; it fits one GPU:
+H is 800 MB), each A_i with round(0.005 |V|) non-zeros like the reference's own non-chordal
+benchmark (doc/source/benchmarks/index.rst, "Nonchordal sparsity patterns").  At N = 1 the
+same JSON line carries BASELINE configs[1] (band SDP n = 5000, bandwidth 5, m = 1000) under
+``secondary``.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
 
 A *step* is one IPM iteration of ``chordalsolver_feas`` through the public API
-(``band_SDP(...).solve_feas(kktsolver='chol')``): chordal completion of the iterate, m
-barrier-Hessian evaluations + the DMMA contraction that assemble the Schur complement H,
-the dense Cholesky of H, the Newton solves with iterative refinement, and the step-length
-probes.  W warm-up iterations, then exactly K timed iterations.
+(``SDP.solve_feas(kktsolver='chol')``): chordal completion of the iterate, assembly of the
+Schur complement H, its dense Cholesky, the Newton solves with iterative refinement and the
+step-length probes.  W warm-up iterations, then exactly K timed iterations.
 
-* ``e2e``   – wall-clock seconds per iteration measured through the public API with host
-  buffers (every iteration moves its m-vectors and reductions across PCIe; bytes counted).
-* ``value`` – the same K iterations, device time only: the sum of the CUDA-event durations
-  of every kernel launched by the library (events on the library's own stream), i.e. the
-  iteration with its inputs resident in HBM and no host gaps.
-* ``roofline`` – the dominant kernel family of those iterations against the measured peak.
+* ``e2e``   – wall-clock seconds per iteration through the public API with host buffers
+  (every iteration moves its m-vectors and reductions across PCIe; bytes counted).  Lead with
+  this number.
+* ``value`` – the same K iterations, device time only (sum of the CUDA-event durations of
+  every kernel family on the library's streams): the iteration without host gaps.
+* ``schur_potrf`` – the part of the step BASELINE.json's metric singles out: device seconds of
+  the Schur-complement assembly + the Cholesky of H per iteration (event pairs around the
+  C-ABI regions, no synchronisation), with SURVEY 8(d)'s flop model and the flops actually
+  executed.  This is the part that is sharded over the GPUs.
+* ``roofline`` – the dominant kernel family of the step against the measured peak.
 * ``cpu_baseline`` – the CPU oracle (the reference's algorithm restated on NumPy/SciPy,
-  ``oracle/``) timed on this box's host cores on a bounded sample and composed with the
-  per-iteration operation counts of the same run.
+  ``oracle/``; the sparse-constraint Schur columns through the reference's own compiled
+  ``misc.SCMcolumn2`` when ``oracle/_ref`` is built) timed on this box's host cores at the
+  workload's real starting iterate; the per-column Schur loop runs on a stratified sample of
+  columns and is scaled to m, every other phase runs in full.
 
-With N > 1 (torchrun, one rank per GPU) the Schur-complement columns are sharded 1-D
-block-cyclically over the ranks and the column blocks of H are exchanged with NCCL
-broadcasts; everything else is replicated.  The problem is fixed, so scaling is "strong".
+With N > 1 (torchrun, one rank per GPU) the columns of H are owned 1-D block-cyclically
+(256-column blocks): every rank assembles its own blocks, the factorisation broadcasts
+panels with NCCL and every rank updates the blocks it owns; chordal single-matrix
+operations are replicas.  The problem is fixed, so scaling is "strong".
 """
 from __future__ import annotations
 
@@ -42,16 +52,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (n, m, bw)
-    "band_n5000_m1000_bw5": (5000, 1000, 5),
-    "band_n500_m100_bw3": (500, 100, 3),
+    "rand_n2000_m10000": dict(kind="rand", n=2000, m=10000, density=0.005),
+    "band_n5000_m1000_bw5": dict(kind="band", n=5000, m=1000, bw=5),
+    # small stand-ins for tests of this script
+    "rand_n300_m400": dict(kind="rand", n=300, m=400, density=0.01),
+    "band_n500_m100_bw3": dict(kind="band", n=500, m=100, bw=3),
 }
-FAMILIES = ["completion", "completion_batch", "cholesky", "cholesky_batch", "projected_inverse", "llt",
-            "hessian_prep", "hessian_prep_inv", "hessian_up", "hessian_down", "hessian_inv",
-            "hessian_up_batch", "hessian_down_batch", "hessian_inv_batch",
-            "scatter_cols", "schur_gemm_dmma", "potrf_diag",
-            "potrf_trsm", "potrf_syrk_dmma", "potrs", "amap", "aadj", "level1", "reduce", "chordal_trsm",
-            "scm_sparse", "setup"]
+DEFAULT = "rand_n2000_m10000"
+SECONDARY = "band_n5000_m1000_bw5"
+DIST_BLOCK = 256
 
 
 def parse():
@@ -60,7 +69,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="band_n5000_m1000_bw5", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
+    ap.add_argument("--secondary", default=None, choices=sorted(WORKLOADS) + ["none"],
+                    help="second workload reported under 'secondary' (default: %s at N = 1)" % SECONDARY)
+    ap.add_argument("--no-solve", action="store_true", help="skip the time-to-solve run")
     return ap.parse_args()
 
 
@@ -90,6 +102,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def wait_first(self, timeout=10.0):
+        # nvidia-smi needs ~1 s to attach to the driver and perturbs CUDA calls while it does: wait for
+        # its first sample so that only steady-state polling overlaps the timed region
+        t0 = time.perf_counter()
+        while not self.rows and time.perf_counter() - t0 < timeout and self.proc is not None:
+            time.sleep(0.05)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -113,7 +132,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def dist_setup(args):
+def dist_setup():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -154,18 +173,25 @@ def measured_fp64_peak():
         return None
 
 
-# families whose LaunchScope work is already in algorithmic BYTES per launch
-BYTE_FAMILIES = {"potrs", "amap_dense", "amap", "aadj", "potrf_panel"}
+# families whose LaunchScope work is algorithmic BYTES per launch; *_dmma / potrf_tile / trsm_slab carry flops;
+# the chordal families carry the number of matrices processed (16*|Vp| bytes each)
+BYTE_FAMILIES = {"potrs", "amap_dense", "amap", "aadj", "potrf_panel", "gemm_thin"}
+FLOP_FAMILIES = {"potrf_tile", "trsm_slab", "gemm_smallk", "potrf_dmma"}
+NO_MODEL = {"front_elem", "front_elem_batch", "setup", "scm_position", "scm_sparse", "chordal_trsm", "front_trsm_diag",
+            "level1", "reduce", "scatter_cols"}
 
 
 def roofline_of(name, f, nvp, hbm_peak, hbm_src, fp64_peak):
     """achieved = algorithmic bytes (or flops) per launch / average launch duration (CUDA events on
     the library's stream).  Chordal kernels: 16*|Vp| bytes per matrix (one read + one write of every
-    pattern entry, SURVEY.md 8d); GEMMs: 2*K flops per computed entry of the lower-triangular result;
+    pattern entry, SURVEY.md 8d); GEMMs / factorisations / triangular solves: their flops;
     potrs: 8*m^2 bytes (the factor is read twice); amap/aadj: the stored entries of Av."""
+    if name in NO_MODEL or f["work"] <= 0:
+        return {"kernel": name, "bound": None, "achieved": None, "peak": None, "unit": None, "frac": None,
+                "traffic": None, "note": "no per-launch work model for this family"}
     per_launch_s = f["ms"] * 1e-3 / max(1, f["launches"])
     work = f["work"] / max(1, f["launches"])
-    if name.endswith("_dmma"):
+    if name.endswith("_dmma") or name in FLOP_FAMILIES:
         ach = work / per_launch_s / 1e12
         peak = fp64_peak if fp64_peak else 40.0
         return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
@@ -192,10 +218,69 @@ def load_peaks():
 
 
 # --------------------------------------------------------------------------------------
+def rand_pattern(n):
+    """Sparse aggregate pattern of the rand workloads: tridiagonal plus 6n random off-diagonal pairs
+    (|V| ~ 8n > m: the A_i live on V)."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(0)
+    e = rng.integers(0, n, size=(6 * n, 2))
+    I = np.concatenate([np.maximum(e[:, 0], e[:, 1]), np.arange(n), np.arange(1, n)])
+    J = np.concatenate([np.minimum(e[:, 0], e[:, 1]), np.arange(n), np.arange(0, n - 1)])
+    return sp.coo_matrix((np.ones(len(I)), (I, J)), shape=(n, n))
+
+
 def build_problem(workload):
+    """The generators run their cone tests (mk_rand) on the installed backend."""
     import smcp_b200 as S
-    n, m, bw = WORKLOADS[workload]
-    return S.band_SDP(n, m, bw, seed=0)
+    w = WORKLOADS[workload]
+    if w["kind"] == "band":
+        return S.band_SDP(w["n"], w["m"], w["bw"], seed=0)
+    return S.rand_SDP(rand_pattern(w["n"]), w["m"], density=w["density"], seed=0)
+
+
+def config_of(workload, world=None):
+    w = WORKLOADS[workload]
+    cfg = {"workload": workload, "n": w["n"], "m": w["m"], "solver": "chordalsolver_feas",
+           "kktsolver": "chol", "scaling_mode": "primal"}
+    if w["kind"] == "rand":
+        cfg["nnz_per_constraint"] = "round(%g |V|)" % w["density"]
+    else:
+        cfg["bandwidth"] = w["bw"]
+    return cfg
+
+
+def flop_model(prob):
+    """Schur + potrf flops per iteration of the REFERENCE's algorithm,
+    (m - Ns) F_H + F_ip + F_T2 + m^3/3, and the flops this implementation executes for the same H."""
+    symb, m, Ns = prob.symb, prob.m, prob.Ns
+    nn = np.diff(symb.snptr).astype(np.float64)
+    nj = np.diff(symb.rowptr).astype(np.float64)
+    na = nj - nn
+    F_H = float(np.sum(4 * nn ** 3 + 6 * na * nn ** 2 + 6 * na ** 2 * nn))
+    Av = prob.Av
+    nnzc = np.diff(Av.indptr).astype(np.float64)
+    md = m - Ns
+    tail = np.cumsum(nnzc[::-1])[::-1]                  # sum_{i >= j} nnz(A_i)
+    F_ip = 2.0 * float(np.sum(tail[:md]))
+    nnzL = float(symb.nvp)
+    F_T2 = F_T2x = 0.0
+    if Ns:
+        Ip, Jp = symb.Ip, symb.Jp
+        Kl = np.empty(Ns)
+        for j in range(md, m):
+            r = Av.indices[Av.indptr[j]:Av.indptr[j + 1]]
+            Kl[j - md] = len(np.unique(np.concatenate([Ip[r], Jp[r]])))
+        F_T2 = float(np.sum(4.0 * nnzL * Kl + 4.0 * nnzc[md:] * tail[md:]))
+        # executed: dense inverse of S once (two chordal solves with n right-hand sides), then the position
+        # form: 5 flops per (position, entry of A_j) + 2 per entry of the rows i >= j
+        rows_sp = Av.indices[Av.indptr[md]:Av.indptr[m]]
+        npos = len(np.unique(rows_sp))
+        F_T2x = 4.0 * nnzL * symb.n + float(np.sum(5.0 * npos * nnzc[md:] + 2.0 * tail[md:]))
+    F_potrf = m ** 3 / 3.0
+    return {"F_H_per_column": F_H, "dense_columns": int(md), "sparse_columns": int(Ns),
+            "model_flops": md * F_H + F_ip + F_T2 + F_potrf,
+            "executed_flops": md * F_H + F_ip + F_T2x + F_potrf,
+            "potrf_flops": F_potrf}
 
 
 class IterTimer:
@@ -212,31 +297,14 @@ class IterTimer:
             fn()
 
 
-def run_b200(args):
-    # keep stdout to the one JSON line: NCCL prints its version banner on stdout at NCCL_DEBUG >= VERSION
-    if os.environ.get("SMCP_NCCL_DEBUG"):
-        os.environ["NCCL_DEBUG"] = os.environ["SMCP_NCCL_DEBUG"]
-    else:
-        os.environ.pop("NCCL_DEBUG", None)
-    rank, world, local, pg = dist_setup(args)
-    os.environ["LOCAL_RANK"] = str(local)
-    from smcp_b200 import solvers, device
-    from smcp_b200.device import Context, TRAFFIC
-    ctx = Context.get(local)
-    if world > 1:
-        import torch
-        idt = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            idt = torch.frombuffer(bytearray(device.comm_unique_id()), dtype=torch.uint8).clone()
-        pg.broadcast(idt, src=0)
-        # column blocks of H: 128 columns keep the DMMA tiles full; 64 when that would leave ranks idle
-        blk = 128 if WORKLOADS[args.workload][1] >= 256 * world else 64
-        device.init_comm(rank, world, bytes(idt.numpy().tobytes()), block=blk, device=local)
-
-    W, K = args.warmup, args.steps
+def measure_workload(workload, W, K, ctx, rank, world, pg, local, do_solve, hbm, fp64_peak):
+    """Two passes over the same W + K iterations (wall clock, then per-family device time) and, at
+    N = 1, the solve to the default tolerances."""
+    from smcp_b200 import solvers
+    from smcp_b200.device import TRAFFIC
     solvers.options["show_progress"] = False
     solvers.options["maxiters"] = W + K
-    P = build_problem(args.workload)              # generator runs its cone tests on the GPU
+    P = build_problem(workload)
     n, m = P.n, P.m
     start = {"x": P._X0}
 
@@ -246,33 +314,40 @@ def run_b200(args):
 
     # ---- pass 1: end-to-end wall clock through the public API ------------------------
     timer = IterTimer(ctx.sync)
-    traffic0 = {}
-    launches = {}
-    timer.marks[W] = lambda: (traffic0.update(TRAFFIC), launches.update(a=ctx.launch_count()), barrier())
+    snap = {}
+
+    def mark_start():
+        snap["traffic"] = dict(TRAFFIC)
+        snap["launches"] = ctx.launch_count()
+        ctx.region_reset()
+        barrier()
+        ctx.sync()
+        timer.t[W] = time.perf_counter()
+
+    timer.marks[W] = mark_start
     solvers._iteration_hook = timer
-    # nvidia-smi needs ~1 s to attach to the driver and perturbs CUDA calls while it does: wait for
-    # its first sample before the solve starts so that only steady-state polling overlaps the timed region
     sampler = ClockSampler(local)
     sampler.start()
-    t_wait = time.perf_counter()
-    while not sampler.rows and time.perf_counter() - t_wait < 10.0 and sampler.proc is not None:
-        time.sleep(0.05)
+    sampler.wait_first()
     barrier()
     sol = P.solve_feas(kktsolver="chol", primalstart=start)
     ctx.sync()
+    barrier()
     clocks = sampler.stop()
     iters = sol["iterations"]
     assert iters >= W + K, "solver stopped after %d iterations (< warmup+steps)" % iters
     e2e_s = (timer.t[W + K] - timer.t[W]) / K
-    n_launch = None
-    h2d = d2h = 0
-    # traffic/launch counters at the end of iteration W+K
-    # (re-run bookkeeping: counters were snapshotted at iteration W; read the totals now and
-    #  subtract what happened after W+K — nothing, maxiters = W+K stops the loop there,
-    #  except the final residual evaluation of iteration W+K+1 which is a handful of vectors)
-    h2d = (TRAFFIC["h2d"] - traffic0["h2d"]) // K
-    d2h = (TRAFFIC["d2h"] - traffic0["d2h"]) // K
-    n_launch = (ctx.launch_count() - launches["a"])
+    # counters: maxiters = W + K stops the loop there; after it only the final residual evaluation runs
+    h2d = (TRAFFIC["h2d"] - snap["traffic"]["h2d"]) // K
+    d2h = (TRAFFIC["d2h"] - snap["traffic"]["d2h"]) // K
+    n_launch = ctx.launch_count() - snap["launches"]
+    regions = {}
+    for nm in ("kkt_assemble", "kkt_factor", "kkt_solve", "kkt_allgather"):
+        ms, calls = ctx.region_get(nm)
+        regions[nm] = {"ms_per_step": ms / K, "calls_per_step": calls / K}
+    prob = solvers._last_problem
+    fm = flop_model(prob) if prob is not None else None
+    nvp = prob.symb.nvp if prob is not None else 0
 
     # ---- pass 2: same iterations, device time per kernel family (CUDA events) --------
     fam = {}
@@ -280,7 +355,7 @@ def run_b200(args):
     timer2.marks[W] = lambda: (ctx.prof_reset(), ctx.prof_enable(True))
     timer2.marks[W + K] = lambda: ctx.prof_enable(False)
     solvers._iteration_hook = timer2
-    sol2 = P.solve_feas(kktsolver="chol", primalstart=start)
+    P.solve_feas(kktsolver="chol", primalstart=start)
     ctx.prof_enable(False)
     solvers._iteration_hook = None
     dev_ms = 0.0
@@ -290,47 +365,53 @@ def run_b200(args):
             fam[nm] = {"ms": ms, "launches": cnt, "work": ctx.prof_get_work(nm)}
             dev_ms += ms
     dev_s = dev_ms * 1e-3 / K
+    sp_s = (regions["kkt_assemble"]["ms_per_step"] + regions["kkt_factor"]["ms_per_step"]
+            + regions["kkt_allgather"]["ms_per_step"]) * 1e-3
 
     # max over ranks
     if pg is not None:
         import torch
-        t = torch.tensor([e2e_s, dev_s], dtype=torch.float64)
+        t = torch.tensor([e2e_s, dev_s, sp_s], dtype=torch.float64)
         pg.all_reduce(t, op=pg.ReduceOp.MAX)
-        e2e_s, dev_s = float(t[0]), float(t[1])
+        e2e_s, dev_s, sp_s = float(t[0]), float(t[1]), float(t[2])
 
+    out = {"e2e_s": e2e_s, "dev_s": dev_s, "h2d": int(h2d), "d2h": int(d2h), "launches": int(n_launch),
+           "clocks": clocks, "status": sol["status"], "iterations": int(iters), "n": n, "m": m, "nvp": int(nvp)}
     if rank != 0:
-        return
-    # ---- roofline of the dominant kernel family ---------------------------------------
-    bw = WORKLOADS[args.workload][2]
-    nvp = sum(min(bw + 1, n - j) for j in range(n))          # |Vp| of the band pattern
-    hbm_peak, hbm_src = load_peaks()
-    fp64_peak = measured_fp64_peak()
+        return out
+    hbm_peak, hbm_src = hbm
     top = max(fam.items(), key=lambda kv: kv[1]["ms"])[0] if fam else None
-    roof = roofline_of(top, fam[top], nvp, hbm_peak, hbm_src, fp64_peak) if top is not None else None
-    # the same figure for every family that takes more than 3% of the step (explains `value`)
+    out["roofline"] = roofline_of(top, fam[top], nvp, hbm_peak, hbm_src, fp64_peak) if top else None
     per_family = {}
     for nm, f in fam.items():
         if f["ms"] >= 0.03 * dev_ms:
             r = roofline_of(nm, f, nvp, hbm_peak, hbm_src, fp64_peak)
             per_family[nm] = {"ms_per_step": f["ms"] / K, "launches_per_step": f["launches"] / K,
                               "bound": r["bound"], "achieved": r["achieved"], "unit": r["unit"], "frac": r["frac"]}
+    out["family_rooflines"] = per_family
+    out["kernel_ms_per_step"] = {k: v["ms"] / K for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    if roof is not None and os.path.exists(traffic_file):
+    if out["roofline"] is not None and os.path.exists(traffic_file):
         with open(traffic_file) as fh:
-            tr = json.load(fh)
-        ent = tr.get(roof["kernel"])
+            ent = json.load(fh).get(out["roofline"]["kernel"])
         if isinstance(ent, dict):
-            # DRAM bytes (read + write) of one launch of the dominant kernel, from an `ncu --set full` capture
-            roof["traffic"] = ent.get("bytes")
-            roof["traffic_unit"] = "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum)"
-            roof["traffic_source"] = ent.get("source")
+            out["roofline"]["traffic"] = ent.get("bytes")
+            out["roofline"]["traffic_unit"] = "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum)"
+            out["roofline"]["traffic_source"] = ent.get("source")
+    peak = fp64_peak if fp64_peak else 40.0
+    out["schur_potrf"] = {
+        "seconds_per_iter": sp_s, "regions_ms_per_step": regions, "flop_model": fm,
+        "tflops_model": (fm["model_flops"] / sp_s / 1e12) if fm and sp_s > 0 else None,
+        "tflops_executed": (fm["executed_flops"] / sp_s / 1e12) if fm and sp_s > 0 else None,
+        "frac_of_fp64_peak_executed": (fm["executed_flops"] / sp_s / 1e12 / peak) if fm and sp_s > 0 else None,
+        "potrf_tflops": (fm["potrf_flops"] / (regions["kkt_factor"]["ms_per_step"] * 1e-3) / 1e12)
+        if fm and regions["kkt_factor"]["ms_per_step"] > 0 else None,
+        "note": "device seconds of smcp_kkt_assemble* + smcp_kkt_factor* per iteration, max over ranks; model = "
+                "SURVEY 8(d) flops of the reference's algorithm, executed = flops of the algorithm run here"}
 
-    cpu = cpu_baseline(args.workload, fam, K)
-
-    # time-to-solve at SMCP's default tolerances (the second half of BASELINE.json's metric): the same
-    # problem solved to optimality through the public API, wall clock over the iterations
-    tts = None
-    if world == 1:
+    # time-to-solve at SMCP's default tolerances (the second half of BASELINE.json's metric)
+    out["time_to_solve"] = None
+    if do_solve and world == 1:
         solvers.options["maxiters"] = 100
         timer3 = IterTimer(ctx.sync)
         solvers._iteration_hook = timer3
@@ -338,125 +419,213 @@ def run_b200(args):
         ctx.sync()
         solvers._iteration_hook = None
         ks = sorted(timer3.t)
-        tts = {"status": sol3["status"], "iterations": int(sol3["iterations"]),
-               "seconds": (timer3.t[ks[-1]] - timer3.t[ks[0]]) if len(ks) > 1 else None,
-               "primal_objective": sol3["primal objective"], "dual_objective": sol3["dual objective"],
-               "primal_infeasibility": sol3["primal infeasibility"], "gap": sol3["gap"]}
+        out["time_to_solve"] = {
+            "status": sol3["status"], "iterations": int(sol3["iterations"]),
+            "seconds": (timer3.t[ks[-1]] - timer3.t[ks[0]]) if len(ks) > 1 else None,
+            "primal_objective": sol3["primal objective"], "dual_objective": sol3["dual objective"],
+            "primal_infeasibility": sol3["primal infeasibility"], "gap": sol3["gap"]}
+    return out
 
+
+def run_b200(args):
+    rank, world, local, pg = dist_setup()
+    # NCCL's communicator lines stay visible (stderr), stdout carries only the JSON line
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    os.environ["LOCAL_RANK"] = str(local)
+    from smcp_b200 import device
+    from smcp_b200.device import Context
+    ctx = Context.get(local)
+    if world > 1:
+        import torch
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(device.comm_unique_id()), dtype=torch.uint8).clone()
+        pg.broadcast(idt, src=0)
+        device.init_comm(rank, world, bytes(idt.numpy().tobytes()), block=DIST_BLOCK, device=local)
+
+    W, K = args.warmup, args.steps
+    hbm = load_peaks()
+    fp64_peak = measured_fp64_peak() if rank == 0 else None
+    main = measure_workload(args.workload, W, K, ctx, rank, world, pg, local, not args.no_solve, hbm, fp64_peak)
+    sec_name = args.secondary if args.secondary is not None else (SECONDARY if world == 1 and args.workload == DEFAULT else "none")
+    sec = None
+    if sec_name != "none" and sec_name != args.workload:
+        sec = measure_workload(sec_name, W, K, ctx, rank, world, pg, local, not args.no_solve, hbm, fp64_peak)
+    if rank != 0:
+        return
+    cpu = cpu_baseline(args.workload)
+    cfg = config_of(args.workload)
+    cfg["l2"] = "working set > L2 per iteration (H alone is %d MB)" % (8 * main["m"] ** 2 // 2 ** 20)
+    cfg["parallelism"] = "schur-columns block-cyclic x%d (blocks of %d columns)" % (world, DIST_BLOCK)
     out = {
-        "metric": "s_per_ipm_iteration", "value": dev_s, "unit": "s/iter", "n_gpus": world,
-        "steps": K, "warmup": W, "ms_per_step": dev_s * 1e3, "higher_is_better": False,
+        "metric": "s_per_ipm_iteration", "value": main["dev_s"], "unit": "s/iter", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": main["dev_s"] * 1e3, "higher_is_better": False,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "n": n, "m": m, "solver": "chordalsolver_feas",
-                   "kktsolver": "chol", "scaling_mode": "primal",
-                   "l2": "working set > L2 per iteration (Av 240 MB + W 240 MB + H 8 MB)",
-                   "parallelism": "schur-columns block-cyclic x%d" % world},
-        "e2e": {"value": e2e_s, "unit": "s/iter", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-        "gpu_launches": int(n_launch),
-        "clocks": clocks,
-        "roofline": roof,
+        "config": cfg,
+        "e2e": {"value": main["e2e_s"], "unit": "s/iter", "h2d_bytes_per_step": main["h2d"], "d2h_bytes_per_step": main["d2h"]},
+        "gpu_launches": main["launches"],
+        "clocks": main["clocks"],
+        "roofline": main["roofline"],
         "cpu_baseline": cpu,
-        "kernel_ms_per_step": {k: v["ms"] / K for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])},
-        "family_rooflines": per_family,
-        "time_to_solve": tts,
-        "status": sol["status"], "iterations": iters,
+        "schur_potrf": main["schur_potrf"],
+        "kernel_ms_per_step": main["kernel_ms_per_step"],
+        "family_rooflines": main["family_rooflines"],
+        "time_to_solve": main["time_to_solve"],
+        "status": main["status"], "iterations": main["iterations"],
         "fp64_gemm_peak_tflops": fp64_peak,
     }
+    if sec is not None:
+        out["secondary"] = {
+            "config": config_of(sec_name), "e2e": {"value": sec["e2e_s"], "unit": "s/iter",
+                                                   "h2d_bytes_per_step": sec["h2d"], "d2h_bytes_per_step": sec["d2h"]},
+            "value": sec["dev_s"], "unit": "s/iter", "gpu_launches": sec["launches"], "roofline": sec["roofline"],
+            "schur_potrf": sec["schur_potrf"], "kernel_ms_per_step": sec["kernel_ms_per_step"],
+            "family_rooflines": sec["family_rooflines"], "time_to_solve": sec["time_to_solve"], "clocks": sec["clocks"]}
     print(json.dumps(out))
 
 
 # --------------------------------------------------------------------------------------
-def cpu_baseline(workload, fam=None, K=1, budget_s=20.0):
-    """The reference's algorithm (oracle/) on this box's host cores: unit times measured on
-    a bounded sample of the SAME workload, composed into seconds per iteration with the
-    per-iteration operation counts of an M1 iteration:
-        1 completion + 1 llt + (m + 6) forward Hessians + 3 inverse Hessians
-        + m trailing gemv's over Av[:, j:m] + potrf(m) + 3 potrs + 7 Amap + 7 Aadj."""
+def cpu_baseline(workload, budget_s=25.0):
+    """The reference's algorithm (oracle/) on this box's host cores, ONE iteration of the M1 method at
+    the workload's real starting iterate (the generator's strictly feasible X0):
+
+      every phase that does not loop over the constraints runs in full and is timed as it runs
+      (completion of X, llt, Hessian factor, one KKT solve with its Hessian / Amap / Aadj / potrs
+      calls, one completion probe and one Cholesky probe of the line search, dpotrf of an m x m matrix);
+      the per-column loop of the Schur assembly (solvers.py:479-497) runs on a stratified sample of
+      columns (every (m/S)-th column of the dense and of the sparse group) and is scaled by m/S.
+
+    The phases are combined with the operation counts of a regular (non-centering) M1 iteration
+    (SURVEY.md 3.1): 1 assembly + 1 potrf, 9 KKT solves (3 Newton systems x (1 + 2 refinement
+    rounds)), 6 KKT residuals, 8 + 8 line-search probes, 2 completions, 1 Cholesky, 1 llt."""
+    os.environ["SMCP_B200_NO_NATIVE_HOST"] = "1"      # pure-NumPy symbolic analysis: no repo .so in this arm
     from smcp_b200 import solvers
-    from smcp_b200.symbolic import Symbolic, lower_pattern
-    from oracle.backend import OracleBackend
+    from oracle.backend import OracleBackend, _scm_column2
     from oracle import supernodal as sn
+    from oracle import ref as oref
     import scipy.linalg as sl
-    import scipy.sparse as sp
     try:
         from threadpoolctl import threadpool_info
         nthreads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
     except Exception:
         nthreads = 1
-    n, m, bw = WORKLOADS[workload]
-    rng = np.random.default_rng(0)
-    I = np.concatenate([np.arange(j, min(j + bw + 1, n)) for j in range(n)])
-    J = np.concatenate([np.full(min(j + bw + 1, n) - j, j) for j in range(n)])
-    cp, ri = lower_pattern(n, I, J)
-    symb = Symbolic(n, cp, ri)
-    ob = OracleBackend(symb)
-    nvp = symb.nvp
-    # a well-conditioned scaling point on the pattern
-    v = 0.05 * rng.standard_normal(nvp)
-    v[symb.diag_vec] = 2.0
-    X = ob.from_vec(v)
-    t0 = time.perf_counter()
-    L = X.copy()
-    sn.cholesky(symb, L)
-    t_chol = time.perf_counter() - t0
-    Y = L.copy()
-    t0 = time.perf_counter()
-    sn.projected_inverse(symb, Y)
-    t_pinv = time.perf_counter() - t0
-    Lc = Y.copy()
-    t0 = time.perf_counter()
-    sn.completion(symb, Lc)
-    t_compl = time.perf_counter() - t0
-    Ll = L.copy()
-    t0 = time.perf_counter()
-    sn.llt(symb, Ll)
-    t_llt = time.perf_counter() - t0
-    hf = sn.HessianFactor(symb, L, Y)
-    # The reference applies the Hessian to one constraint matrix per call (solvers.py:479-497) in
-    # chompack's C code; the NumPy port pays ~0.8 s of interpreter overhead per call on the 5000
-    # supernodes of this pattern, which C does not.  Timing a BATCH of columns per call amortises
-    # that overhead and is the fairer stand-in for the reference's per-column cost; the single-call
-    # time is reported in `sample` as well.
-    U1 = rng.standard_normal((1, symb.nblk)) * (symb.wdot > 0)
-    t0 = time.perf_counter()
-    sn.hessian(hf, U1.copy())
-    t_h_single = time.perf_counter() - t0
-    ncols = 48
-    U = rng.standard_normal((ncols, symb.nblk)) * (symb.wdot > 0)
-    t0 = time.perf_counter()
-    sn.hessian(hf, U)
-    t_h = (time.perf_counter() - t0) / ncols
-    t0 = time.perf_counter()
-    sn.hessian_inv(hf, U1.copy())
-    t_hinv = time.perf_counter() - t0
-    # gemv over the trailing columns of a dense Av (reference: base.gemv(Av[:, j:m], ...) which
-    # also copies the slice, solvers.py:486); sample 8 columns j, average (m - j) ~ m/2
-    msub = min(m, 256)
-    Avs = sp.csc_matrix(rng.standard_normal((nvp, msub)))
-    x = rng.standard_normal(nvp)
-    t0 = time.perf_counter()
-    reps = 4
-    for _ in range(reps):
-        sl_ = Avs[:, msub // 2:]
-        _ = sl_.T @ x
-    t_gemv_avg = (time.perf_counter() - t0) / reps * (m / 2.0) / (msub / 2.0)
-    Hm = rng.standard_normal((m, m))
-    Hm = Hm @ Hm.T + m * np.eye(m)
-    t0 = time.perf_counter()
-    Lh = sl.cholesky(Hm, lower=True)
-    t_potrf = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    sl.cho_solve((Lh, True), x[:m])
-    t_potrs = time.perf_counter() - t0
-    t_amap = t_gemv_avg * 2.0      # full Av
-    per_iter = (t_compl + t_llt + (m + 6) * t_h + 3 * t_hinv + m * t_gemv_avg + t_potrf + 3 * t_potrs
-                + 14 * t_amap)
+    w = WORKLOADS[workload]
+    prev = solvers._backend_factory if hasattr(solvers, "_backend_factory") else None
+    solvers.set_backend_factory(lambda symb: OracleBackend(symb, batch_columns=32))
+    try:
+        P = build_problem(workload)
+        solvers.options["show_progress"] = False
+        opt = solvers._read_options(P.n, feas=True)
+        prob = solvers._Problem(P._A, P._b, opt, "chol", None)
+        ob, symb, m, Ns = prob.ops, prob.symb, prob.m, prob.Ns
+        md = m - Ns
+        tm = {}
+
+        def timed(key, fn):
+            t0 = time.perf_counter()
+            r = fn()
+            tm[key] = time.perf_counter() - t0
+            return r
+
+        X = prob.from_original(P._X0).buf
+        L = X.copy()
+        timed("completion", lambda: sn.completion(symb, L))
+        Sh = L.copy()
+        timed("llt", lambda: sn.llt(symb, Sh))
+        hf = timed("hessian_factor", lambda: ob.hessian_factor(L, X))
+        Lc = Sh.copy()
+        timed("cholesky", lambda: sn.cholesky(symb, Lc))
+        # ---- Schur assembly, sampled columns --------------------------------------------
+        Av = ob.Av
+        t_dense = t_sparse = 0.0
+        nd = ns_ = 0
+        if md:
+            S = max(1, min(md, 48))
+            cols = np.unique(np.linspace(0, md - 1, S).astype(int))
+            t0 = time.perf_counter()
+            U = np.zeros((len(cols), symb.nblk))
+            for q, j in enumerate(cols):
+                c0, c1 = Av.indptr[j], Av.indptr[j + 1]
+                U[q, symb.vec2blk[Av.indices[c0:c1]]] = Av.data[c0:c1]
+            sn.hessian(hf, U)
+            for q, j in enumerate(cols):
+                at = U[q, symb.vec2blk] * ob.halfdiag
+                # base.gemv(Av[:, j:m], ..., trans='T') incl. the slice copy of the reference (solvers.py:486)
+                _ = Av[:, j:].T @ at
+            t_dense = (time.perf_counter() - t0) * md / len(cols)
+            nd = len(cols)
+        if Ns:
+            Ip, Jp = symb.Ip, symb.Jp
+            S = max(1, min(Ns, 24))
+            cols = md + np.unique(np.linspace(0, Ns - 1, S).astype(int))
+            use_ref = oref.available()
+            H = np.zeros((m, m), order="F") if not use_ref else None
+            if use_ref:
+                # persistent cvxopt-ABI objects like the reference's solver holds them (H, Av, Ip, Jp are
+                # created once per solve, solvers.py:346-367, 547): only V and kkl are per-column objects
+                refmod, _ = oref._load()
+                Hm, Avm = oref.dmatrix(np.zeros((m, m))), oref.spmatrix(Av)
+                Ipm, Jpm = oref.imatrix(Ip), oref.imatrix(Jp)
+            t0 = time.perf_counter()
+            for jj in cols:
+                c0, c1 = Av.indptr[jj], Av.indptr[jj + 1]
+                rows_j = Av.indices[c0:c1]
+                Kj = np.unique(np.concatenate([Ip[rows_j], Jp[rows_j]]))
+                V = np.zeros((symb.n, len(Kj)))
+                V[symb.iperm[Kj], np.arange(len(Kj))] = 1.0
+                sn.trsm(symb, hf.Lbuf, V, 'N')
+                sn.trsm(symb, hf.Lbuf, V, 'T')
+                kkl = np.zeros(symb.n, dtype=np.int64)
+                kkl[Kj] = np.arange(len(Kj))
+                if use_ref:
+                    # the reference's own compiled SCMcolumn2 (misc.c:620-663); its V is indexed by vertex
+                    refmod.SCMcolumn2(Hm, Avm, oref.dmatrix(V[symb.iperm, :]), Ipm, Jpm, oref.imatrix(kkl), int(jj))
+                else:
+                    _scm_column2(H, Av, V, symb.iperm, Ip, Jp, kkl, int(jj))
+            t_sparse = (time.perf_counter() - t0) * Ns / len(cols)
+            ns_ = len(cols)
+            H = Hm = None
+        tm["assembly"] = t_dense + t_sparse
+        # ---- dense factorisation and one KKT solve -----------------------------------------
+        rng = np.random.default_rng(0)
+        G = rng.standard_normal((m, min(m, 64)))
+        Hm = G @ G.T + m * np.eye(m)
+        ob.Hf = timed("potrf", lambda: sl.cholesky(Hm, lower=True, check_finite=False, overwrite_a=True))
+        bx = Sh.copy()
+        by = rng.standard_normal(m)
+
+        def kkt_solve():
+            r1 = bx.copy()
+            sn.hessian(hf, r1.reshape(1, -1))
+            y = ob.schur_solve(by + ob.Amap(r1))
+            x = ob.Aadj(y) - bx
+            sn.hessian(hf, x.reshape(1, -1))
+            return x, y
+        x, y = timed("kkt_solve", kkt_solve)
+
+        def kkt_res():
+            r = x.copy()
+            sn.hessian_inv(hf, r.reshape(1, -1))
+            return r + ob.Aadj(y) - bx, ob.Amap(x) - by
+        timed("kkt_res", kkt_res)
+        counts = {"assembly": 1, "potrf": 1, "kkt_solve": 9, "kkt_res": 6, "completion": 2 + 8, "cholesky": 1 + 8,
+                  "llt": 1, "hessian_factor": 1}
+        per_iter = sum(tm[k] * c for k, c in counts.items())
+    finally:
+        solvers.set_backend_factory(prev)
+        os.environ.pop("SMCP_B200_NO_NATIVE_HOST", None)
     return {"value": per_iter, "unit": "s/iter", "cores": int(nthreads), "kind": "port",
-            "sample": ("unit times of the oracle on this workload's pattern: completion %.3fs, llt %.3fs, "
-                       "hessian %.4fs/col (batch of %d columns per call; %.3fs for a single-matrix call), "
-                       "inverse hessian %.4fs, trailing gemv %.4fs/col (%d-column slice), dpotrf(m) %.4fs; "
-                       "composed with the op counts of one M1 iteration (m+6 Hessians, m gemv's, 1 potrf, ...)"
-                       % (t_compl, t_llt, t_h, ncols, t_h_single, t_hinv, t_gemv_avg, msub, t_potrf))}
+            "phase_seconds": {k: round(v, 6) for k, v in tm.items()}, "phase_counts": counts,
+            "sample": ("one M1 iteration at the generator's starting iterate X0: every phase run in full and timed "
+                       "(%s), the per-column Schur loop on %d of %d dense and %d of %d sparse columns (stratified, scaled "
+                       "to m; sparse columns: 2 chordal trsm + %s), combined with the op counts of a regular M1 "
+                       "iteration %s" % (", ".join("%s %.3fs" % (k, v) for k, v in tm.items() if k != "assembly"),
+                                         nd, md, ns_, Ns,
+                                         "the reference's compiled misc.SCMcolumn2 (oracle/_ref)" if (Ns and oref.available())
+                                         else "the NumPy restatement of misc.SCMcolumn2", json.dumps(counts)))}
 
 
 def run_reference(args):
@@ -464,7 +633,6 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    n, m, bw = WORKLOADS[args.workload]
     vals = []
     cpu = None
     for _ in range(max(1, min(args.steps, 2))):
@@ -472,16 +640,15 @@ def run_reference(args):
         vals.append(cpu["value"])
     v = float(np.mean(vals))
     cpu["value"] = v
+    cfg = config_of(args.workload)
     out = {"impl": "reference", "metric": "s_per_ipm_iteration", "value": v, "unit": "s/iter",
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * 1e3,
            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-           "data": "synthetic",
-           "config": {"workload": args.workload, "n": n, "m": m, "solver": "chordalsolver_feas",
-                      "kktsolver": "chol", "scaling_mode": "primal"},
+           "data": "synthetic", "config": cfg,
            "cpu_baseline": cpu,
            "e2e": {"value": v, "unit": "s/iter", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "note": "cvxopt/chompack are not installable here; this is the oracle port of the reference's "
-                   "CPU path (oracle/), each step a bounded sample composed to one iteration"}
+                   "CPU path (oracle/), each step one sampled iteration as described in cpu_baseline.sample"}
     print(json.dumps(out))
 
 

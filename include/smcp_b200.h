@@ -52,6 +52,10 @@ int smcp_prof_get_work(smcp_ctx *ctx, const char *name, double *work_out);
 /* comma-separated names of the families that have accumulated time since the last reset */
 int smcp_prof_list(smcp_ctx *ctx, char *buf, int64_t cap);
 int smcp_prof_reset(smcp_ctx *ctx);
+/* device time of whole API regions ("kkt_assemble", "kkt_factor", "kkt_solve", "kkt_allgather"): one
+ * event pair per call on the context's stream, no synchronisation until read; ms and calls since reset */
+int smcp_region_get(smcp_ctx *ctx, const char *name, double *ms_out, int64_t *calls_out);
+int smcp_region_reset(smcp_ctx *ctx);
 /* write (flush) a buffer larger than L2 */
 int smcp_flush_l2(smcp_ctx *ctx);
 
@@ -167,6 +171,10 @@ int smcp_comm_destroy(smcp_ctx *ctx);
  * assembled by smcp_kkt_assemble_cyclic(block = 128): owners factor and ncclBroadcast their panels,
  * every rank updates its own column tiles; on return every rank holds the complete factor */
 int smcp_kkt_factor_dist(smcp_op *op, int rank, int nranks, int32_t *info_host);
+/* the same with an explicit distribution block (a multiple of 128 columns; the `block` given to
+ * smcp_kkt_assemble_cyclic).  256 keeps 8 ranks busy at m = 10 000 while each trailing update still
+ * runs with K = 256 */
+int smcp_kkt_factor_block(smcp_op *op, int64_t block, int rank, int nranks, int32_t *info_host);
 /* all-gather the block-cyclic column blocks of H assembled by each rank */
 int smcp_kkt_allgather(smcp_op *op, int64_t block, int rank, int nranks);
 
@@ -186,6 +194,24 @@ int smcp_host_embed(int64_t n, const int64_t *colptr, const int64_t *rowind, int
  * supernode arrays of smcp_sym_desc; nn = columns and nj = rows of every supernode */
 int smcp_host_aaidx(int64_t nsn, const int64_t *snpar, const int64_t *nn, const int64_t *nj, const int64_t *relptr,
                     const int64_t *relidx, const int64_t *blkptr, const int64_t *updptr, int64_t *aaidx);
+
+/* ---- the dense LAPACK/BLAS calls of the path on host buffers (column-major) -----------------
+ * Parity tests and micro-benchmarks of the kernels behind smcp_kkt_factor / smcp_kkt_solve and the
+ * frontal matrices of large supernodes; `ms_out` (may be NULL) receives the device time.
+ * smcp_dense_potrf: cvxopt.lapack.potrf(A) (solvers.py:501, 1931); ncols < m factors the leading
+ *   ncols columns and leaves the Schur complement in the trailing block (a frontal matrix of
+ *   chompack.cholesky).  info as dpotrf.
+ * smcp_dense_trsm: B <- L^{-1} B (trans = 0) or L^{-T} B (trans = 1), L lower triangular: the two
+ *   halves of cvxopt.lapack.potrs (solvers.py:526) and chompack.trsm on a dense supernode (491-492).
+ * smcp_dense_gemm: C = [C +] alpha op(A) op(B)^T on the FP64 tensor cores; ta / tb = 1: the operand
+ *   is stored K-major (A[k + i*lda]); tri = 1: lower triangle only (the contraction of
+ *   solvers.py:486 and every frontal update). */
+int smcp_dense_potrf(smcp_ctx *ctx, double *A_host, int64_t lda, int64_t m, int64_t ncols, int32_t *info_host, double *ms_out);
+int smcp_dense_trsm(smcp_ctx *ctx, int trans, const double *L_host, int64_t ldl, int64_t n, double *B_host, int64_t ldb,
+                    int64_t nrhs, double *ms_out);
+int smcp_dense_gemm(smcp_ctx *ctx, int ta, int tb, const double *A_host, int64_t lda, const double *B_host, int64_t ldb,
+                    double *C_host, int64_t ldc, int64_t M, int64_t N, int64_t K, double alpha, int accumulate, int tri,
+                    double *ms_out);
 
 #ifdef __cplusplus
 }

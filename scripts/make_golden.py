@@ -186,7 +186,11 @@ def gen_drivers():
         sol = getattr(P, "solve_" + method)(kktsolver="chol", **kw)
         traces[name] = {"status": sol["status"], "iterations": sol["iterations"],
                         "primal objective": sol["primal objective"], "dual objective": sol["dual objective"],
-                        "gap": sol["gap"], "y": [float(v) for v in np.asarray(sol["y"]).ravel()]}
+                        "gap": sol["gap"], "y": [float(v) for v in np.asarray(sol["y"]).ravel()],
+                        # per-iteration statistics: the self-dual embedding is compared iterate by iterate down
+                        # to the rounding floor of its Newton solves (see tests/test_golden.py)
+                        "trace": [[float(r[k]) for k in ("pcost", "dcost", "gap", "pres", "dres")] for r in sol["trace"]
+                                  if all(r.get(k) is not None for k in ("pcost", "dcost", "gap", "pres", "dres"))]}
     solvers.set_backend_factory(None)
     with open(os.path.join(OUT, "driver_traces.json"), "w") as f:
         json.dump(traces, f, indent=1, sort_keys=True)
@@ -197,9 +201,10 @@ if __name__ == "__main__":
     from oracle import ref
     if not ref.available():
         raise SystemExit("oracle/_ref is not built: run `make -C oracle` (needs /root/reference)")
-    gen_misc(ref)
-    gen_scm(ref)
-    gen_dense()
+    if sys.argv[1:] != ["drivers"]:        # `make_golden.py drivers` regenerates driver_traces.json only
+        gen_misc(ref)
+        gen_scm(ref)
+        gen_dense()
     gen_drivers()
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):

@@ -207,8 +207,13 @@ int big_setup(smcp_sym *s, const smcp_sym_desc *D) {
     // (4 nn^3 + 6 na nn^2 + 6 na^2 nn flops) is too much for one CTA;
     // SMCP_B200_BIG_FLOPS overrides the threshold (0 disables the path), SMCP_B200_BIG_NJ adds a
     // criterion on the front size (tests force tiny fronts through the dense path with it)
-    const char *envf = getenv("SMCP_B200_BIG_FLOPS"), *envn = getenv("SMCP_B200_BIG_NJ");
+    // A third criterion covers the completion (and the inverse-Hessian factor): both need the Cholesky
+    // factor of the na x na separator block whatever nn is (na^3/3 flops) -- a 1-column
+    // supernode under a 500-row separator is 4e7 flops that one CTA of the tree kernel needs 20 ms for
+    // (rand_SDP n = 2000: 43 ms per completion before this rule).  SMCP_B200_BIG_COMPL_FLOPS overrides.
+    const char *envf = getenv("SMCP_B200_BIG_FLOPS"), *envn = getenv("SMCP_B200_BIG_NJ"), *envc = getenv("SMCP_B200_BIG_COMPL_FLOPS");
     const double thr_flops = envf ? atof(envf) : 2.0e6;
+    const double thr_compl = envc ? atof(envc) : (thr_flops > 0.0 ? 6.0e6 : 0.0);
     const int thr_nj = envn ? atoi(envn) : 0;
     if (thr_flops <= 0.0 && thr_nj <= 0) return 0;
     std::vector<int> flag(nsn, 0);
@@ -216,7 +221,7 @@ int big_setup(smcp_sym *s, const smcp_sym_desc *D) {
     for (int k = 0; k < nsn; ++k) {
         const double nj = (double)(D->rowptr[k + 1] - D->rowptr[k]), nn = (double)(D->snptr[k + 1] - D->snptr[k]), na = nj - nn;
         const double fl = 4.0 * nn * nn * nn + 6.0 * na * nn * nn + 6.0 * na * na * nn;
-        if ((thr_flops > 0.0 && fl >= thr_flops) || (thr_nj > 0 && nj >= thr_nj)) { flag[k] = 1; any = true; }
+        if ((thr_flops > 0.0 && fl >= thr_flops) || (thr_nj > 0 && nj >= thr_nj) || (thr_compl > 0.0 && na * na * na / 3.0 >= thr_compl)) { flag[k] = 1; any = true; }
     }
     if (!any) return 0;
     // ancestor closure: post-order => parents have larger indices

@@ -56,6 +56,54 @@ LaunchScope::~LaunchScope() {
     }
 }
 
+static cudaEvent_t region_event(smcp_ctx *ctx) {
+    if (!ctx->region_pool.empty()) {
+        cudaEvent_t e = ctx->region_pool.back();
+        ctx->region_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+static void region_resolve(smcp_ctx *ctx, RegionAcc &a) {
+    for (auto &pr : a.pending) {
+        float ms = 0.f;
+        cudaEventSynchronize(pr.second);
+        if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) a.ms += ms;
+        ctx->region_pool.push_back(pr.first);
+        ctx->region_pool.push_back(pr.second);
+    }
+    a.pending.clear();
+}
+RegionScope::RegionScope(smcp_ctx *c, const char *name) : ctx(c), acc(&c->regions[name]) {
+    if (acc->pending.size() >= 4096) region_resolve(ctx, *acc);
+    e0 = region_event(ctx);
+    e1 = region_event(ctx);
+    cudaEventRecord(e0, ctx->stream);
+}
+RegionScope::~RegionScope() {
+    cudaEventRecord(e1, ctx->stream);
+    acc->pending.push_back({e0, e1});
+    acc->calls += 1;
+}
+extern "C" int smcp_region_get(smcp_ctx *ctx, const char *name, double *ms_out, int64_t *calls_out) {
+    auto it = ctx->regions.find(name);
+    if (it == ctx->regions.end()) { *ms_out = 0.0; *calls_out = 0; return 0; }
+    region_resolve(ctx, it->second);
+    *ms_out = it->second.ms;
+    *calls_out = it->second.calls;
+    return 0;
+}
+extern "C" int smcp_region_reset(smcp_ctx *ctx) {
+    for (auto &kv : ctx->regions) {
+        region_resolve(ctx, kv.second);
+        kv.second.ms = 0.0;
+        kv.second.calls = 0;
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------
@@ -97,6 +145,8 @@ extern "C" int smcp_ctx_destroy(smcp_ctx *ctx) {
     cudaEventDestroy(ctx->pev0);
     cudaEventDestroy(ctx->pev1);
     for (cudaEvent_t e : ctx->potrf_ev) cudaEventDestroy(e);
+    for (auto &kv : ctx->regions) region_resolve(ctx, kv.second);
+    for (cudaEvent_t e : ctx->region_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -865,6 +915,7 @@ static int assemble_sparse_range(smcp_op *op, smcp_hess *h, int64_t s0, int64_t 
 }
 
 extern "C" int smcp_kkt_assemble(smcp_op *op, smcp_hess *h, int64_t j0, int64_t j1) {
+    RegionScope rs(op->sym->ctx, "kkt_assemble");
     const int64_t m = op->m, md = op->md;
     if (j1 > m) j1 = m;
     int64_t d0 = std::max<int64_t>(j0, 0), d1 = std::min<int64_t>(j1, md);
@@ -876,6 +927,7 @@ extern "C" int smcp_kkt_assemble(smcp_op *op, smcp_hess *h, int64_t j0, int64_t 
 
 // the column blocks q = rank (mod nranks) of `block` columns each, as ONE batch
 extern "C" int smcp_kkt_assemble_cyclic(smcp_op *op, smcp_hess *h, int64_t block, int rank, int nranks) {
+    RegionScope rs(op->sym->ctx, "kkt_assemble");
     const int64_t m = op->m, md = op->md;
     if (block < 1 || nranks < 1 || rank < 0 || rank >= nranks) { smcp_set_error("smcp_kkt_assemble_cyclic: bad arguments"); return -2; }
     std::vector<std::pair<int64_t, int64_t>> dense;
@@ -898,7 +950,10 @@ extern "C" int smcp_kkt_assemble_cyclic(smcp_op *op, smcp_hess *h, int64_t block
 
 extern "C" int smcp_kkt_factor(smcp_op *op, int32_t *info_host) {
     smcp_ctx *ctx = op->sym->ctx;
-    if (d_potrf(ctx, op->H, op->m, op->m, op->m, op->info_dev, 0, 1)) return -1;
+    {
+        RegionScope rs(ctx, "kkt_factor");
+        if (d_potrf(ctx, op->H, op->m, op->m, op->m, op->info_dev, 0, 1)) return -1;
+    }
     CUDA_TRY(cudaMemcpyAsync(info_host, op->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -912,16 +967,118 @@ extern "C" int smcp_kkt_factor_dist(smcp_op *op, int rank, int nranks, int32_t *
     smcp_ctx *ctx = op->sym->ctx;
     if (nranks < 1 || rank < 0 || rank >= nranks) { smcp_set_error("smcp_kkt_factor_dist: bad arguments"); return -2; }
     if (nranks > 1 && !ctx->nccl_comm) { smcp_set_error("NCCL communicator not initialised"); return -2; }
-    if (d_potrf(ctx, op->H, op->m, op->m, op->m, op->info_dev, rank, nranks)) return -1;
+    {
+        RegionScope rs(ctx, "kkt_factor");
+        if (d_potrf(ctx, op->H, op->m, op->m, op->m, op->info_dev, rank, nranks)) return -1;
+    }
     CUDA_TRY(cudaMemcpyAsync(info_host, op->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// as smcp_kkt_factor_dist with an explicit distribution block (a multiple of 128 columns; the block
+// smcp_kkt_assemble_cyclic was called with)
+extern "C" int smcp_kkt_factor_block(smcp_op *op, int64_t block, int rank, int nranks, int32_t *info_host) {
+    smcp_ctx *ctx = op->sym->ctx;
+    if (nranks < 1 || rank < 0 || rank >= nranks || block < 128 || block % 128) { smcp_set_error("smcp_kkt_factor_block: bad arguments"); return -2; }
+    if (nranks > 1 && !ctx->nccl_comm) { smcp_set_error("NCCL communicator not initialised"); return -2; }
+    {
+        RegionScope rs(ctx, "kkt_factor");
+        if (d_potrf(ctx, op->H, op->m, op->m, op->m, op->info_dev, rank, nranks, block)) return -1;
+    }
+    CUDA_TRY(cudaMemcpyAsync(info_host, op->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// dense kernels on host buffers (column-major), the LAPACK/BLAS calls of the path on their own:
+// lapack.potrf (solvers.py:501), the triangular solves behind lapack.potrs (solvers.py:526) and
+// chompack.trsm on a dense root supernode (solvers.py:491-492), blas.gemm-shaped frontal updates.
+// Used by the parity tests and scripts/bench_dense.py; `ms_out` (optional) is the device time.
+// ---------------------------------------------------------------------------------------
+struct DevBuf {
+    double *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+extern "C" int smcp_dense_potrf(smcp_ctx *ctx, double *A_host, int64_t lda, int64_t m, int64_t ncols, int32_t *info_host, double *ms_out) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (m <= 0 || lda < m) { smcp_set_error("smcp_dense_potrf: bad arguments"); return -2; }
+    DevBuf A, I;
+    CUDA_TRY(cudaMalloc(&A.p, (size_t)lda * m * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&I.p, 64));
+    CUDA_TRY(cudaMemcpyAsync(A.p, A_host, (size_t)lda * m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (d_potrf(ctx, A.p, lda, m, ncols, (int32_t *)I.p, 0, 1)) return -1;
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(A_host, A.p, (size_t)lda * m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(info_host, I.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ms_out) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        *ms_out = ms;
+    }
+    return 0;
+}
+
+extern "C" int smcp_dense_trsm(smcp_ctx *ctx, int trans, const double *L_host, int64_t ldl, int64_t n, double *B_host, int64_t ldb,
+                               int64_t nrhs, double *ms_out) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (n <= 0 || nrhs <= 0 || ldl < n || ldb < n) { smcp_set_error("smcp_dense_trsm: bad arguments"); return -2; }
+    DevBuf L, B;
+    CUDA_TRY(cudaMalloc(&L.p, (size_t)ldl * n * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&B.p, (size_t)ldb * nrhs * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(L.p, L_host, (size_t)ldl * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(B.p, B_host, (size_t)ldb * nrhs * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (d_trsm_left_lower(ctx, trans != 0, L.p, ldl, n, B.p, ldb, nrhs)) return -1;
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(B_host, B.p, (size_t)ldb * nrhs * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ms_out) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        *ms_out = ms;
+    }
+    return 0;
+}
+
+// C = [C +] alpha op(A) op(B)^T in the convention of launch_gemm (dense.cu): ta/tb = 1 reads the
+// operand K-major (A[k + i*lda]); tri = 1 computes the lower triangle only
+extern "C" int smcp_dense_gemm(smcp_ctx *ctx, int ta, int tb, const double *A_host, int64_t lda, const double *B_host, int64_t ldb,
+                               double *C_host, int64_t ldc, int64_t M, int64_t N, int64_t K, double alpha, int accumulate, int tri,
+                               double *ms_out) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t na = (size_t)lda * (ta ? M : K), nb = (size_t)ldb * (tb ? N : K), nc = (size_t)ldc * N;
+    DevBuf A, B, Cd;
+    CUDA_TRY(cudaMalloc(&A.p, na * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&B.p, nb * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&Cd.p, nc * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(A.p, A_host, na * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(B.p, B_host, nb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(Cd.p, C_host, nc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (launch_gemm(ctx, ta != 0, tb != 0, A.p, lda, B.p, ldb, Cd.p, ldc, M, N, K, alpha, accumulate, tri, 0, "dense_gemm_dmma")) return -1;
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(C_host, Cd.p, nc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ms_out) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        *ms_out = ms;
+    }
     return 0;
 }
 
 extern "C" int smcp_kkt_solve(smcp_op *op, double *host_y) {
     smcp_ctx *ctx = op->sym->ctx;
     CUDA_TRY(cudaMemcpyAsync(op->yv, host_y, (size_t)op->m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    if (d_potrs(ctx, op->H, op->m, op->yv)) return -1;
+    {
+        RegionScope rs(ctx, "kkt_solve");
+        if (d_potrs(ctx, op->H, op->m, op->yv)) return -1;
+    }
     CUDA_TRY(cudaMemcpyAsync(host_y, op->yv, (size_t)op->m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -1014,6 +1171,7 @@ int comm_bcast(smcp_ctx *ctx, double *ptr, size_t count, int root, cudaStream_t 
 // block, i.e. the lower trapezoid) so that all ranks end up with the full lower triangle.
 extern "C" int smcp_kkt_allgather(smcp_op *op, int64_t block, int rank, int nranks) {
     smcp_ctx *ctx = op->sym->ctx;
+    RegionScope rs(ctx, "kkt_allgather");
     (void)rank;
     if (!ctx->nccl_comm) { smcp_set_error("NCCL communicator not initialised"); return -2; }
     const int64_t m = op->m;

@@ -76,18 +76,22 @@ __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_dmma_kernel(const double *__restrict__ A, long long lda, const double *__restrict__ B, long long ldb,
                  double *__restrict__ C, long long ldc, long long M, long long N, long long K, double alpha,
                  int accumulate, int tri, long long tri_off, long long kchunk, long long split_stride,
-                 int jt0, int jtstride, long long bsA, long long bsB, int batched) {
+                 int jt0, int jtstride, int jtb, long long bsA, long long bsB, int batched) {
     extern __shared__ double smem[];
     double *As = smem;                              // STAGES x 128 x LDK
     double *Bs = smem + STAGES * 128 * LDK;
     const long long i0 = (long long)blockIdx.x * BM;
-    // column tiles jt0, jt0 + jtstride, ...: the block-cyclic owner of a column block updates only its own tiles
-    const long long j0 = ((long long)jt0 + (long long)blockIdx.y * jtstride) * BN;
+    // column blocks jt0, jt0 + jtstride, ... of jtb tiles each: the block-cyclic owner of a column block
+    // updates only its own tiles
+    const long long j0 = (((long long)jt0 + (long long)(blockIdx.y / jtb) * jtstride) * jtb + (blockIdx.y % jtb)) * BN;
+    if (j0 >= N) return;
     if (tri && (i0 + BM - 1 + tri_off < j0)) return;        // tile entirely above the diagonal
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp & 3) * 32;       // 4 warps along M
     const int wn = (warp >> 2) * 32;      // 4 warps along N
     const int g = lane >> 2, t = lane & 3;
+    // diagonal tiles of a triangular product: warp tiles entirely above the diagonal only help with the loads
+    const bool wskip = tri && (i0 + wm + 31 + tri_off < j0 + wn);
 
     double acc[2][4][4];           // 2 x 4 tiles of 16 x 8 per warp (32 x 32)
 #pragma unroll
@@ -128,6 +132,7 @@ gemm_dmma_kernel(const double *__restrict__ A, long long lda, const double *__re
         }
         const double *as = As + (kt % STAGES) * 128 * LDK;
         const double *bs = Bs + (kt % STAGES) * 128 * LDK;
+        if (wskip) continue;
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 8) {
             double af[2][4], bf[4][2];
@@ -146,6 +151,7 @@ gemm_dmma_kernel(const double *__restrict__ A, long long lda, const double *__re
         }
     }
     cp_async_wait<0>();
+    if (wskip) return;
     // epilogue: C(i, j), i = i0 + wm + a*16 + g + 8*(v>>1), j = j0 + wn + b*8 + 2t + (v&1)
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
@@ -182,26 +188,179 @@ __global__ void splitk_reduce_kernel(const double *__restrict__ P, long long spl
     }
 }
 
+// K <= 16 (rank-k updates of the thin supernodes of a top set: nn = 1 .. 9 columns over a ~1100-row
+// separator): the product is bound by reading and writing C, a 128 x 128 DMMA tile with a 3-stage
+// pipeline is all overhead.  32 x 32 outputs per CTA, operands staged in shared memory once.
+#define SK_MAX 16
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) gemm_smallk_kernel(const double *__restrict__ A, long long lda, const double *__restrict__ B, long long ldb,
+                                                          double *__restrict__ C, long long ldc, long long M, long long N, int K, double alpha,
+                                                          int accumulate, int tri, long long tri_off) {
+    __shared__ double As[SK_MAX][33], Bs[SK_MAX][33];
+    const long long i0 = (long long)blockIdx.x * 32, j0 = (long long)blockIdx.y * 32;
+    if (tri && i0 + 31 + tri_off < j0) return;
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < 32 * K; idx += 256) {
+        // TA: A'(i, k) = A[k + i*lda] (k contiguous); else A[i + k*lda] (i contiguous)
+        const int r = TA ? idx / K : idx % 32, k = TA ? idx % K : idx / 32;
+        As[k][r] = (i0 + r < M) ? (TA ? A[k + (i0 + r) * lda] : A[(i0 + r) + (long long)k * lda]) : 0.0;
+    }
+    for (int idx = tid; idx < 32 * K; idx += 256) {
+        const int r = TB ? idx / K : idx % 32, k = TB ? idx % K : idx / 32;
+        Bs[k][r] = (j0 + r < N) ? (TB ? B[k + (j0 + r) * ldb] : B[(j0 + r) + (long long)k * ldb]) : 0.0;
+    }
+    __syncthreads();
+    const int tx = tid & 31, ty = tid >> 5;
+    const long long i = i0 + tx;
+    if (i >= M) return;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int jj = ty + 8 * q;
+        const long long j = j0 + jj;
+        if (j >= N || (tri && i + tri_off < j)) continue;
+        double s = 0.0;
+        for (int k = 0; k < K; ++k) s = fma(As[k][tx], Bs[k][jj], s);
+        double *c = C + i + j * ldc;
+        const double v = alpha * s;
+        *c = accumulate ? (*c + v) : v;
+    }
+}
+
+// N <= 16 with a long K (a thin supernode against its ~1100-row separator: M_an = Y_aa K_an D^-1,
+// Z_an = M_an - Z_aa Lt, ...): a matrix times a few vectors.  The product is bound by streaming A
+// once; a 128 x 128 DMMA tile would use 1/128 of its columns and a single wave of 9 CTAs.
+//   TA = false (A[i + k*lda]): a CTA owns 32 rows, its 8 warps split K, lane = row (coalesced);
+//   TA = true  (A[k + i*lda]): a warp owns a row, lanes stride over K (coalesced).
+// Partial sums are combined in a fixed order (bitwise reproducible).
+#define TN_MAX 16
+#define TN_KC 128      // k-chunk of B staged in shared memory
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) gemm_thin_kernel(const double *__restrict__ A, long long lda, const double *__restrict__ B, long long ldb,
+                                                        double *__restrict__ C, long long ldc, long long M, int N, long long K, double alpha,
+                                                        int accumulate) {
+    __shared__ double tnsm[8 * 32 * TN_MAX];                                   // the B chunk, then the partial sums
+    double (*Bs)[TN_MAX + 1] = reinterpret_cast<double (*)[TN_MAX + 1]>(tnsm);   // TN_KC x (TN_MAX + 1)
+    double (*red)[32][TN_MAX] = reinterpret_cast<double (*)[32][TN_MAX]>(tnsm);  // 8 x 32 x TN_MAX
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double acc[TN_MAX];
+#pragma unroll
+    for (int n = 0; n < TN_MAX; ++n) acc[n] = 0.0;
+    const long long i0 = (long long)blockIdx.x * (TA ? 8 : 32);
+    for (long long k0 = 0; k0 < K; k0 += TN_KC) {
+        const int kc = (int)min((long long)TN_KC, K - k0);
+        __syncthreads();
+        for (int idx = tid; idx < TN_KC * N; idx += 256) {
+            // TB: B'(n, k) = B[k + n*ldb] (k contiguous); else B[n + k*ldb] (n contiguous)
+            const int n = TB ? idx / TN_KC : idx % N, k = TB ? idx % TN_KC : idx / N;
+            Bs[k][n] = (k < kc) ? (TB ? B[(k0 + k) + (long long)n * ldb] : B[n + (k0 + k) * ldb]) : 0.0;
+        }
+        __syncthreads();
+        if (!TA) {
+            // warp w takes k = w, w + 8, ... of the chunk; lane = row
+            const long long i = i0 + lane;
+            double a8[TN_KC / 8];          // all loads of the chunk in flight before the first fma
+#pragma unroll
+            for (int q = 0; q < TN_KC / 8; ++q) {
+                const int k = warp + 8 * q;
+                a8[q] = (i < M && k < kc) ? A[i + (k0 + k) * lda] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < TN_KC / 8; ++q)
+#pragma unroll
+                for (int n = 0; n < TN_MAX; ++n)
+                    if (n < N) acc[n] = fma(a8[q], Bs[warp + 8 * q][n], acc[n]);
+        } else {
+            const long long i = i0 + warp;
+            double a2[TN_KC / 32];
+#pragma unroll
+            for (int q = 0; q < TN_KC / 32; ++q) {
+                const int k = lane + 32 * q;
+                a2[q] = (i < M && k < kc) ? A[(k0 + k) + i * lda] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < TN_KC / 32; ++q)
+#pragma unroll
+                for (int n = 0; n < TN_MAX; ++n)
+                    if (n < N) acc[n] = fma(a2[q], Bs[lane + 32 * q][n], acc[n]);
+        }
+    }
+    if (!TA) {
+        __syncthreads();
+#pragma unroll
+        for (int n = 0; n < TN_MAX; ++n)
+            if (n < N) red[warp][lane][n] = acc[n];
+        __syncthreads();
+        for (int idx = tid; idx < 32 * N; idx += 256) {
+            const int r = idx % 32, n = idx / 32;
+            const long long i = i0 + r;
+            if (i >= M) continue;
+            double s = 0.0;
+            for (int w = 0; w < 8; ++w) s += red[w][r][n];
+            double *c = C + i + (long long)n * ldc;
+            *c = accumulate ? (*c + alpha * s) : alpha * s;
+        }
+    } else {
+        const long long i = i0 + warp;
+#pragma unroll
+        for (int n = 0; n < TN_MAX; ++n)
+            if (n < N) {
+                double s = acc[n];
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+                if (lane == 0 && i < M) {
+                    double *c = C + i + (long long)n * ldc;
+                    *c = accumulate ? (*c + alpha * s) : alpha * s;
+                }
+            }
+    }
+}
+
 int launch_gemm(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, const double *B, int64_t ldb,
                        double *C, int64_t ldc, int64_t M, int64_t N, int64_t K, double alpha, int accumulate,
                        int tri, int64_t tri_off, const char *name) {
-    return launch_gemm_cyc(ctx, ta, tb, A, lda, B, ldb, C, ldc, M, N, K, alpha, accumulate, tri, tri_off, name, 0, 1);
+    if (M > 0 && N > 0 && N <= TN_MAX && K > SK_MAX && !tri) {
+        const unsigned grid = (unsigned)((M + (ta ? 8 : 32) - 1) / (ta ? 8 : 32));
+        LaunchScope ls(ctx, "gemm_thin", 1, 8.0 * (double)K * (double)M);
+#define TNL(TA_, TB_) gemm_thin_kernel<TA_, TB_><<<grid, 256, 0, ctx->stream>>>(A, lda, B, ldb, C, ldc, M, (int)N, K, alpha, accumulate)
+        if (ta && tb) TNL(true, true);
+        else if (!ta && !tb) TNL(false, false);
+        else if (ta) TNL(true, false);
+        else TNL(false, true);
+#undef TNL
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
+    if (M > 0 && N > 0 && K > 0 && K <= SK_MAX) {
+        dim3 grid((unsigned)((M + 31) / 32), (unsigned)((N + 31) / 32));
+        LaunchScope ls(ctx, "gemm_smallk", 1, 2.0 * (double)K * (double)M * (double)N * (tri ? 0.5 : 1.0));
+#define SK_LAUNCH(TA_, TB_) gemm_smallk_kernel<TA_, TB_><<<grid, 256, 0, ctx->stream>>>(A, lda, B, ldb, C, ldc, M, N, (int)K, alpha, accumulate, tri, tri_off)
+        if (ta && tb) SK_LAUNCH(true, true);
+        else if (!ta && !tb) SK_LAUNCH(false, false);
+        else if (ta) SK_LAUNCH(true, false);
+        else SK_LAUNCH(false, true);
+#undef SK_LAUNCH
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
+    return launch_gemm_cyc(ctx, ta, tb, A, lda, B, ldb, C, ldc, M, N, K, alpha, accumulate, tri, tri_off, name, 0, 1, 1);
 }
 
 // as launch_gemm, restricted to the column tiles jt0, jt0 + jtstride, ... (128 columns each)
 int launch_gemm_cyc(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, const double *B, int64_t ldb,
                     double *C, int64_t ldc, int64_t M, int64_t N, int64_t K, double alpha, int accumulate,
-                    int tri, int64_t tri_off, const char *name, int jt0, int jtstride) {
+                    int tri, int64_t tri_off, const char *name, int jt0, int jtstride, int jtb) {
     if (M <= 0 || N <= 0) return 0;
+    if (jtb < 1) jtb = 1;
     const long long ntile_n = (N + BN - 1) / BN;
-    if (jt0 >= ntile_n) return 0;
-    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((ntile_n - jt0 + jtstride - 1) / jtstride));
+    const long long nblock_n = (ntile_n + jtb - 1) / jtb;          // column blocks of jtb tiles
+    if (jt0 >= nblock_n) return 0;
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)(((nblock_n - jt0 + jtstride - 1) / jtstride) * jtb));
+    auto tile_of = [&](unsigned bj) { return ((long long)jt0 + (long long)(bj / jtb) * jtstride) * jtb + (bj % jtb); };
     // split-K when the (lower-triangular) tile grid cannot fill the GPU and K is long: the Schur
     // assembly contracts over |blkval| ~ 10^4..10^6 rows into an m x m block
     long long ntiles = 0;
     for (unsigned bj = 0; bj < grid.y; ++bj)
         for (unsigned bi = 0; bi < grid.x; ++bi)
-            if (!tri || (long long)bi * BM + BM - 1 + tri_off >= ((long long)jt0 + (long long)bj * jtstride) * BN) ++ntiles;
+            if (tile_of(bj) < ntile_n && (!tri || (long long)bi * BM + BM - 1 + tri_off >= tile_of(bj) * BN)) ++ntiles;
     int splits = 1;
     if (!accumulate && alpha == 1.0 && K >= 2048 && ntiles > 0 && ntiles < ctx->num_sms) {
         splits = (int)(ctx->num_sms / ntiles);
@@ -232,15 +391,15 @@ int launch_gemm_cyc(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t ld
     // algorithmic flops: 2*K per computed entry of the (lower-triangular) result
     double pairs = 0.0;
     for (int64_t j = 0; j < N; ++j) {
-        const int64_t jt = j / BN;
-        if (jt < jt0 || (jt - jt0) % jtstride) continue;
+        const int64_t jb = j / BN / jtb;
+        if (jb < jt0 || (jb - jt0) % jtstride) continue;
         int64_t lo = tri ? j - tri_off : 0;            // rows i >= lo
         if (lo < 0) lo = 0;
         if (lo < M) pairs += (double)(M - lo);
     }
     {
         LaunchScope ls(ctx, name, 1, 2.0 * (double)K * pairs);
-#define GEMM_LAUNCH(TA_, TB_) gemm_dmma_kernel<TA_, TB_><<<grid, GEMM_THREADS, smem, ctx->stream>>>(A, lda, B, ldb, Cout, ldout, M, N, K, alpha, accumulate, tri, tri_off, kchunk, split_stride, jt0, jtstride, 0LL, 0LL, 0)
+#define GEMM_LAUNCH(TA_, TB_) gemm_dmma_kernel<TA_, TB_><<<grid, GEMM_THREADS, smem, ctx->stream>>>(A, lda, B, ldb, Cout, ldout, M, N, K, alpha, accumulate, tri, tri_off, kchunk, split_stride, jt0, jtstride, jtb, 0LL, 0LL, 0)
         if (ta && tb) GEMM_LAUNCH(true, true);
         else if (!ta && !tb) GEMM_LAUNCH(false, false);
         else if (ta) GEMM_LAUNCH(true, false);
@@ -282,7 +441,7 @@ int launch_gemm_batched(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_
         const double *Az = A + z0 * sA, *Bz = B + z0 * sB;
         double *Cz = C + z0 * sC;
         LaunchScope ls(ctx, name, 1, 2.0 * (double)K * (double)M * (double)N * (double)nz);
-#define GEMM_LAUNCH(TA_, TB_) gemm_dmma_kernel<TA_, TB_><<<grid, GEMM_THREADS, smem, ctx->stream>>>(Az, lda, Bz, ldb, Cz, ldc, M, N, K, alpha, accumulate, 0, 0, K, sC, 0, 1, sA, sB, 1)
+#define GEMM_LAUNCH(TA_, TB_) gemm_dmma_kernel<TA_, TB_><<<grid, GEMM_THREADS, smem, ctx->stream>>>(Az, lda, Bz, ldb, Cz, ldc, M, N, K, alpha, accumulate, 0, 0, K, sC, 0, 1, 1, sA, sB, 1)
         if (ta && tb) GEMM_LAUNCH(true, true);
         else if (!ta && !tb) GEMM_LAUNCH(false, false);
         else if (ta) GEMM_LAUNCH(true, false);
@@ -503,7 +662,9 @@ static int potrf_block(smcp_ctx *ctx, double *H, int64_t ld, int64_t mrows, int6
     return 0;
 }
 
-int d_potrf(smcp_ctx *ctx, double *H, int64_t ld, int64_t m, int64_t ncols, int32_t *info_dev, int rank, int nranks) {
+// Round-1 factorisation (launch chain: diagonal kernel + panel kernel + DMMA update per 64-column
+// panel, 128-column distribution blocks); kept behind SMCP_B200_POTRF_CHAIN=1 for A/B measurements.
+static int d_potrf_chain(smcp_ctx *ctx, double *H, int64_t ld, int64_t m, int64_t ncols, int32_t *info_dev, int rank, int nranks) {
     if (ncols > m) ncols = m;
     if (nranks < 1) nranks = 1;
     const size_t pp_smem = (size_t)(NB * LDT + NB * PP_ROWS) * sizeof(double);
@@ -570,6 +731,115 @@ int d_potrf(smcp_ctx *ctx, double *H, int64_t ld, int64_t m, int64_t ncols, int3
             const int jt0 = (int)(((rank - qb) % nranks + nranks) % nranks);
             if (launch_gemm_cyc(ctx, false, false, P2, ld, P2, ld, H + c2 + c2 * ld, ld, m - c2, m - c2, w, -1.0, 1, 1, 0,
                                 "potrf_syrk_dmma", jt0, nranks)) return -1;
+        }
+        if (two) CUDA_TRY(cudaEventRecord(F[q], sB));
+    }
+    if (two) {
+        CUDA_TRY(cudaEventRecord(join, sA));
+        CUDA_TRY(cudaStreamWaitEvent(sB, join, 0));
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// lapack.potrf (solvers.py:501, 1931) / partial factorisation of a frontal matrix.
+//  * L2-resident matrices (m <= SMCP_B200_POTRF_TILE_MAX = 2560) on one GPU: ONE cooperative launch
+//    (potrf_tile_kernel, dense_tile.cu).
+//  * larger m: right-looking over column blocks of `block` columns (512 on one GPU, the distribution
+//    block on several).  A block is factored by potrf_tile_kernel in panel mode (all rows of the
+//    block column, updates confined to the block) and applied to the trailing matrix by ONE DMMA
+//    GEMM with K = block, so C is re-read once per 512 columns instead of once per 64.
+//  * several GPUs (north star (3)): 1-D block-cyclic columns, owner(q) = q mod nranks.
+//    The owner of block q+1 applies panel q to it, factors it and broadcasts it (NCCL) on the
+//    look-ahead stream while every rank applies panel q to the other blocks it owns.  Every rank ends
+//    with the full factor, and the arithmetic per entry does not depend on the number of ranks.
+int d_potrf(smcp_ctx *ctx, double *H, int64_t ld, int64_t m, int64_t ncols, int32_t *info_dev, int rank, int nranks, int64_t block) {
+    static const bool chain = getenv("SMCP_B200_POTRF_CHAIN") && atoi(getenv("SMCP_B200_POTRF_CHAIN")) != 0;
+    if (chain && (block == 0 || block == OB)) return d_potrf_chain(ctx, H, ld, m, ncols, info_dev, rank, nranks);
+    if (ncols > m) ncols = m;
+    if (nranks < 1) nranks = 1;
+    if (m <= 0 || ncols <= 0) return 0;
+    static const int64_t tile_max = getenv("SMCP_B200_POTRF_TILE_MAX") ? atoll(getenv("SMCP_B200_POTRF_TILE_MAX")) : 2560;
+    if (nranks > 1 && (ld != m || ncols != m)) { smcp_set_error("d_potrf: the distributed factorisation needs a full square matrix"); return -2; }
+    LaunchScope outer(ctx, "potrf_dmma", 0, (double)ncols * ncols * ncols / 3.0 + (double)(m - ncols) * ncols * (double)m);
+    ctx->prof_mute++;
+    struct Unmute { smcp_ctx *c; ~Unmute() { c->prof_mute--; } } unmute{ctx};
+    CUDA_TRY(cudaMemsetAsync(info_dev, 0, sizeof(int), ctx->stream));
+    if (nranks == 1 && m <= tile_max && potrf_tile_fits(ctx, m, ncols, false))
+        return potrf_tile(ctx, H, ld, m, ncols, false, info_dev, 0);
+    if (block <= 0) block = nranks > 1 ? 256 : 512;
+    if (block % BN) { smcp_set_error("d_potrf: the column block must be a multiple of %d", BN); return -2; }
+    const int tpb = (int)(block / BN);
+    const int64_t nblocks = (ncols + block - 1) / block;
+    auto blk_w = [&](int64_t q) { return std::min<int64_t>(block, ncols - q * block); };
+    // panel q: all rows of block column q.  The last block of a PARTIAL factorisation whose width is
+    // not a multiple of the tile size is factored together with its trailing update (tile mode).
+    bool trailing_done = false;
+    auto factor_block = [&](int64_t q) -> int {
+        const int64_t c0 = q * block, w = blk_w(q);
+        const bool last = c0 + w >= ncols;
+        const bool full_mode = last && ncols < m && (w % 64) != 0;
+        if (full_mode) trailing_done = true;
+        if (!potrf_tile_fits(ctx, m - c0, w, !full_mode)) { smcp_set_error("d_potrf: panel too tall for the tile kernel"); return -2; }
+        return potrf_tile(ctx, H + c0 + c0 * ld, ld, m - c0, w, !full_mode, info_dev, (int)c0);
+    };
+    if (nranks == 1) {
+        for (int64_t q = 0; q < nblocks; ++q) {
+            const int64_t c0 = q * block, w = blk_w(q), c1 = c0 + w;
+            if (factor_block(q)) return -1;
+            if (c1 < m && !trailing_done) {
+                const double *P1 = H + c1 + c0 * ld;
+                if (launch_gemm(ctx, false, false, P1, ld, P1, ld, H + c1 + c1 * ld, ld, m - c1, m - c1, w, -1.0, 1, 1, 0, "potrf_syrk_dmma")) return -1;
+            }
+        }
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
+    // ---- block-cyclic over the ranks, look-ahead on the second stream
+    cudaStream_t sB = ctx->stream, sA = ctx->stream2 ? ctx->stream2 : ctx->stream;
+    const bool two = sA != sB;
+    while ((int64_t)ctx->potrf_ev.size() < 2 * nblocks + 2) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->potrf_ev.push_back(e);
+    }
+    cudaEvent_t *E = ctx->potrf_ev.data(), *F = ctx->potrf_ev.data() + nblocks;
+    cudaEvent_t fork = ctx->potrf_ev[2 * nblocks], join = ctx->potrf_ev[2 * nblocks + 1];
+    if (two) {
+        CUDA_TRY(cudaEventRecord(fork, sB));
+        CUDA_TRY(cudaStreamWaitEvent(sA, fork, 0));
+    }
+    {
+        StreamSwap sw(ctx, sA);
+        if (rank == 0 && factor_block(0)) return -1;
+        if (comm_bcast(ctx, H, (size_t)blk_w(0) * ld, 0, sA)) return -1;
+        if (two) CUDA_TRY(cudaEventRecord(E[0], sA));
+    }
+    for (int64_t q = 0; q < nblocks; ++q) {
+        const int64_t c0 = q * block, w = blk_w(q), c1 = c0 + w;
+        if (c1 >= m) break;
+        const double *P1 = H + c1 + c0 * ld;          // panel q, rows c1..
+        if (two) CUDA_TRY(cudaStreamWaitEvent(sB, E[q], 0));
+        int64_t c2 = c1;
+        if (q + 1 < nblocks) {
+            const int64_t w1 = blk_w(q + 1);
+            c2 = c1 + w1;
+            StreamSwap sw(ctx, sA);
+            if (two && q >= 1) CUDA_TRY(cudaStreamWaitEvent(sA, F[q - 1], 0));
+            if ((q + 1) % nranks == rank) {
+                if (launch_gemm(ctx, false, false, P1, ld, P1, ld, H + c1 + c1 * ld, ld, m - c1, w1, w, -1.0, 1, 1, 0, "potrf_syrk_dmma")) return -1;
+                if (factor_block(q + 1)) return -1;
+            }
+            if (comm_bcast(ctx, H + c1 * ld, (size_t)w1 * ld, (int)((q + 1) % nranks), sA)) return -1;
+            if (two) CUDA_TRY(cudaEventRecord(E[q + 1], sA));
+        }
+        if (c2 < m) {
+            // panel q applied to the blocks >= q+2 this rank owns
+            const double *P2 = H + c2 + c0 * ld;
+            const int64_t qb = c2 / block;
+            const int jb0 = (int)(((rank - qb) % nranks + nranks) % nranks);
+            if (launch_gemm_cyc(ctx, false, false, P2, ld, P2, ld, H + c2 + c2 * ld, ld, m - c2, m - c2, w, -1.0, 1, 1, 0,
+                                "potrf_syrk_dmma", jb0, nranks, tpb)) return -1;
         }
         if (two) CUDA_TRY(cudaEventRecord(F[q], sB));
     }

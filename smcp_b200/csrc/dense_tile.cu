@@ -1,0 +1,452 @@
+// Single-launch dense kernels for matrices that live in L2 (m up to a few thousand): the m x m
+// Schur complement H of the band configuration (m = 1000), and the frontal matrices of the
+// top set of the clique tree (rand_SDP n = 2000: a 1186-column root and 27 fronts of ~1130
+// rows).  They replace launch chains (lapack.potrf, src/python/solvers.py:501, 1931, was 52
+// launches at m = 1000; the blocked triangular solves of front.cu were ~38 launches per
+// solve at n = 1186):
+//
+//   potrf_tile_kernel  right-looking tile Cholesky (64 x 64 tiles) as ONE cooperative kernel:
+//                      every tile of the lower triangle is owned by a CTA; a step factors the
+//                      diagonal tile (redundantly in every CTA that owns a tile of that block
+//                      column: no broadcast round trip), solves the panel tiles, grid-syncs,
+//                      applies the panel to the trailing tiles with DMMA, grid-syncs.
+//                      `npiv` < m gives the partial factorisation of a frontal matrix (trailing
+//                      block = update matrix); `ntc` limits the updated tile columns (panel mode
+//                      of the blocked factorisation in dense.cu for large m).
+//   trsm_slab_kernel   X = L^{-1} B / L^{-T} B with a dense lower-triangular L: a CTA owns 8
+//                      right-hand sides for the whole solve and keeps them in shared memory
+//                      (no inter-CTA dependency at all); 64 x 64 diagonal blocks are solved by one
+//                      warp per right-hand side (shuffle substitution), the rest of each block
+//                      column is applied with m16n8k8 DMMA whose A fragments are read straight
+//                      from L in L2 (every entry of L is used exactly once per CTA).
+#include "internal.cuh"
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <cstdlib>
+#include <cstdio>
+#include <vector>
+
+namespace cg = cooperative_groups;
+
+#define TT 64          // tile size
+#define DLD 66         // leading dimension of the diagonal tile in shared memory (even: double2 loads)
+#define OLDT 68        // leading dimension of the [k][row] operand tiles: conflict-free DMMA fragment loads
+#define PT_THREADS 256
+#define PT_MAXOWN 64   // owned tiles per CTA (host checks)
+
+__device__ __forceinline__ void dmma16x8x8_t(double (&c)[4], const double (&a)[4], const double (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+                 : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
+}
+
+struct PotrfTileArgs {
+    double *H;
+    long long ld;
+    int mm;        // order of the (sub)matrix
+    int npiv;      // leading columns to factor
+    int ntc;       // tile columns that exist for this call (P: full trailing update; ceil(npiv/64): panel only)
+    int *info;     // dpotrf's info (first non-positive pivot, 1-based), written if still 0
+    int col_off;   // added to the local column index in info
+    long long *dbg; // SMCP_B200_PT_DEBUG: per-step phase timestamps of CTA 0 (ns), 6 per step
+};
+
+__device__ __forceinline__ long long gtimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define PT_STAMP(slot) do { if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[6 * k + (slot)] = gtimer(); } while (0)
+
+__global__ void __launch_bounds__(PT_THREADS, 1) potrf_tile_kernel(PotrfTileArgs a) {
+    extern __shared__ __align__(16) double ptsm[];
+    double *D = ptsm;                    // TT x DLD, D[c*DLD + r] = tile(r, c)
+    double *rs = D + TT * DLD;           // 1/sqrt(pivot)
+    double *dsv = rs + TT;               // pivots
+    double *W = dsv + TT;                // phase A: rows xs[c*256 + tid]; phase B: As | Bs
+    __shared__ short2 own[PT_MAXOWN];
+    __shared__ int nown_s;
+    cg::grid_group grid = cg::this_grid();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *H = a.H;
+    const long long ld = a.ld;
+    const int mm = a.mm;
+    const int P = (mm + TT - 1) / TT, Pc = (a.npiv + TT - 1) / TT;
+    if (tid == 0) {
+        const long long ntiles = (long long)a.ntc * P - (long long)a.ntc * (a.ntc - 1) / 2;
+        int cnt = 0, j = 0;
+        long long off = 0;
+        for (long long idx = blockIdx.x; idx < ntiles && cnt < PT_MAXOWN; idx += gridDim.x) {
+            while (idx >= off + (P - j)) { off += P - j; ++j; }
+            own[cnt++] = make_short2((short)(j + (int)(idx - off)), (short)j);
+        }
+        nown_s = cnt;
+    }
+    __syncthreads();
+    const int nown = nown_s;
+
+    for (int k = 0; k < Pc; ++k) {
+        const int kb = min(TT, a.npiv - TT * k);
+        const long long kc = (long long)TT * k;
+        bool workA = false, workB = false, diag_owner = false;
+        for (int q = 0; q < nown; ++q) {
+            const short2 t = own[q];
+            if (t.y == k) { workA = true; if (t.x == k) diag_owner = true; }
+            else if (t.y > k) workB = true;
+        }
+        PT_STAMP(0);
+        if (workA) {
+            // ---- diagonal tile: load (identity beyond the matrix), factor kb pivots right-looking
+            for (int idx = tid; idx < TT * TT; idx += PT_THREADS) {
+                const int r = idx & 63, c = idx >> 6;
+                double v = 0.0;
+                if (r >= c) {
+                    if (kc + r < mm && kc + c < mm) v = H[(kc + r) + (kc + c) * ld];
+                    else if (r == c) v = 1.0;
+                }
+                D[c * DLD + r] = v;
+            }
+            int bad = 0;
+            for (int c = 0; c < kb; ++c) {
+                __syncthreads();
+                double d = D[c * DLD + c];
+                if (!(d > 0.0)) {
+                    if (!bad) bad = c + 1;
+                    d = 1.0;
+                }
+                const double r = rsqrt(d), rinv = r * r;
+                if (tid == 0) { rs[c] = r; dsv[c] = d; }
+                const int i = tid & 63;
+                if (i > c) {
+                    // a_ij -= a_ic a_jc / d on the unscaled column c (scaled after the loop); four
+                    // independent load / fma / store chains in flight per thread
+                    const double t = D[c * DLD + i] * rinv;
+                    int j = c + 1 + (tid >> 6);
+                    for (; j + 12 <= i; j += 16) {
+                        const double l0 = D[c * DLD + j], l1 = D[c * DLD + j + 4], l2 = D[c * DLD + j + 8], l3 = D[c * DLD + j + 12];
+                        const double a0 = D[j * DLD + i], a1 = D[(j + 4) * DLD + i], a2 = D[(j + 8) * DLD + i], a3 = D[(j + 12) * DLD + i];
+                        D[j * DLD + i] = fma(-t, l0, a0);
+                        D[(j + 4) * DLD + i] = fma(-t, l1, a1);
+                        D[(j + 8) * DLD + i] = fma(-t, l2, a2);
+                        D[(j + 12) * DLD + i] = fma(-t, l3, a3);
+                    }
+                    for (; j <= i; j += 4) D[j * DLD + i] = fma(-t, D[c * DLD + j], D[j * DLD + i]);
+                }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < TT * kb; idx += PT_THREADS) {
+                const int r = idx & 63, c = idx >> 6;
+                if (r > c) D[c * DLD + r] *= rs[c];
+                else if (r == c) D[c * DLD + c] = dsv[c] * rs[c];
+            }
+            __syncthreads();
+            if (diag_owner && bad && tid == 0 && *a.info == 0) *a.info = a.col_off + (int)kc + bad;
+            PT_STAMP(1);
+            // ---- panel tiles (i, k), i > k: X L^T = B, one row per thread, up to 4 tiles at a time
+            int q = 0;
+            while (q < nown) {
+                int ti[4], nt = 0;
+                for (; q < nown && nt < 4; ++q)
+                    if (own[q].y == k && own[q].x != k) ti[nt++] = own[q].x;
+                if (!nt) break;
+                const int slot = tid >> 6, r = tid & 63;
+                const long long R = slot < nt ? (long long)TT * ti[slot < nt ? slot : 0] + r : mm;
+                const bool live = slot < nt && R < mm;
+                double *xs = W;
+                double *Pg = H + R + kc * ld;
+                for (int c = 0; c < TT; ++c) xs[c * PT_THREADS + tid] = (live && kc + c < mm) ? Pg[(long long)c * ld] : 0.0;
+                if (live) {
+                    for (int cb8 = 0; cb8 < TT; cb8 += 8) {
+                        double x8[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) x8[e] = xs[(cb8 + e) * PT_THREADS + tid];
+                        const int pmax = min(cb8, kb);
+                        for (int p = 0; p < pmax; ++p) {
+                            const double xp = xs[p * PT_THREADS + tid];
+                            const double2 *lp = reinterpret_cast<const double2 *>(D + p * DLD + cb8);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const double2 lv = lp[e];
+                                x8[2 * e] = fma(-xp, lv.x, x8[2 * e]);
+                                x8[2 * e + 1] = fma(-xp, lv.y, x8[2 * e + 1]);
+                            }
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            if (cb8 + e < kb) {
+                                const double xk = x8[e] * rs[cb8 + e];
+                                x8[e] = xk;
+#pragma unroll
+                                for (int e2 = e + 1; e2 < 8; ++e2) x8[e2] = fma(-xk, D[(cb8 + e) * DLD + cb8 + e2], x8[e2]);
+                            }
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            xs[(cb8 + e) * PT_THREADS + tid] = x8[e];
+                            if (kc + cb8 + e < mm) Pg[(long long)(cb8 + e) * ld] = x8[e];
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        PT_STAMP(2);
+        grid.sync();
+        PT_STAMP(3);
+        if (diag_owner) {
+            // written back only now: during phase A the other CTAs of this block column were still
+            // reading the unfactored tile; D is not touched by the trailing updates below
+            for (int idx = tid; idx < TT * TT; idx += PT_THREADS) {
+                const int r = idx & 63, c = idx >> 6;
+                if (r >= c && kc + r < mm) H[(kc + r) + (kc + c) * ld] = D[c * DLD + r];
+            }
+        }
+        if (workB) {
+            // ---- trailing tiles (i, j), j > k: C -= L(i,k) L(j,k)^T on the FP64 tensor cores
+            double *As = W, *Bs = W + TT * OLDT;
+            const int kb8 = (kb + 7) & ~7;
+            const int g = lane >> 2, t = lane & 3;
+            const int r0 = (warp & 3) * 16, c0w = (warp >> 2) * 32;
+            for (int q = 0; q < nown; ++q) {
+                const int ti = own[q].x, tj = own[q].y;
+                if (tj <= k) continue;
+                const long long ri = (long long)TT * ti, rj = (long long)TT * tj;
+                for (int idx = tid; idx < TT * kb8; idx += PT_THREADS) {
+                    const int r = idx & 63, c = idx >> 6;
+                    As[c * OLDT + r] = (c < kb && ri + r < mm) ? H[(ri + r) + (kc + c) * ld] : 0.0;
+                    if (ti != tj) Bs[c * OLDT + r] = (c < kb && rj + r < mm) ? H[(rj + r) + (kc + c) * ld] : 0.0;
+                }
+                __syncthreads();
+                const double *Bt = (ti != tj) ? Bs : As;
+                double acc[4][4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const long long row = ri + r0 + g + 8 * (v >> 1), col = rj + c0w + b * 8 + 2 * t + (v & 1);
+                        acc[b][v] = (row < mm && col < mm && row >= col) ? H[row + col * ld] : 0.0;
+                    }
+                for (int kk = 0; kk < kb8; kk += 8) {
+                    double af[4];
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) af[v] = -As[(kk + t + 4 * (v >> 1)) * OLDT + r0 + g + 8 * (v & 1)];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        double bf[2];
+#pragma unroll
+                        for (int v = 0; v < 2; ++v) bf[v] = Bt[(kk + t + 4 * v) * OLDT + c0w + b * 8 + g];
+                        dmma16x8x8_t(acc[b], af, bf);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const long long row = ri + r0 + g + 8 * (v >> 1), col = rj + c0w + b * 8 + 2 * t + (v & 1);
+                        if (row < mm && col < mm && row >= col) H[row + col * ld] = acc[b][v];
+                    }
+                __syncthreads();
+            }
+        }
+        PT_STAMP(4);
+        if (k + 1 < Pc) grid.sync();
+        PT_STAMP(5);
+    }
+}
+
+static size_t potrf_tile_smem() { return (size_t)(TT * DLD + 2 * TT + TT * PT_THREADS) * sizeof(double); }
+
+// Largest order handled by one launch (tiles per CTA bounded by PT_MAXOWN)
+bool potrf_tile_fits(const smcp_ctx *ctx, int64_t mm, int64_t npiv, bool panel_only) {
+    const int64_t P = (mm + TT - 1) / TT, Pc = (npiv + TT - 1) / TT, ntc = panel_only ? Pc : P;
+    const int64_t ntiles = ntc * P - ntc * (ntc - 1) / 2;
+    return P < 32000 && ntiles <= (int64_t)PT_MAXOWN * ctx->num_sms;
+}
+
+int potrf_tile(smcp_ctx *ctx, double *H, int64_t ld, int64_t mm, int64_t npiv, bool panel_only, int32_t *info_dev, int col_off) {
+    if (mm <= 0 || npiv <= 0) return 0;
+    if (npiv > mm) npiv = mm;
+    static bool attr = false;
+    const size_t smem = potrf_tile_smem();
+    if (!attr) {
+        CUDA_TRY(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    if (!potrf_tile_fits(ctx, mm, npiv, panel_only)) { smcp_set_error("potrf_tile: matrix too large for one launch"); return -2; }
+    PotrfTileArgs a;
+    a.H = H; a.ld = ld; a.mm = (int)mm; a.npiv = (int)npiv;
+    const int64_t P = (mm + TT - 1) / TT, Pc = (npiv + TT - 1) / TT;
+    a.ntc = (int)(panel_only ? Pc : P);
+    a.info = info_dev; a.col_off = col_off;
+    a.dbg = nullptr;
+    static const bool dbg_on = getenv("SMCP_B200_PT_DEBUG") != nullptr;
+    long long *dbg_dev = nullptr;
+    if (dbg_on) {
+        CUDA_TRY(cudaMalloc(&dbg_dev, (size_t)6 * Pc * sizeof(long long)));
+        CUDA_TRY(cudaMemsetAsync(dbg_dev, 0, (size_t)6 * Pc * sizeof(long long), ctx->stream));
+        a.dbg = dbg_dev;
+    }
+    const int64_t ntiles = (int64_t)a.ntc * P - (int64_t)a.ntc * (a.ntc - 1) / 2;
+    const unsigned grid = (unsigned)std::min<int64_t>(ctx->num_sms, ntiles);
+    void *args[] = {&a};
+    LaunchScope ls(ctx, "potrf_tile", 1, (double)npiv * npiv * npiv / 3.0);
+    CUDA_TRY(cudaLaunchCooperativeKernel((void *)potrf_tile_kernel, dim3(grid), dim3(PT_THREADS), args, smem, ctx->stream));
+    if (dbg_on) {
+        std::vector<long long> h((size_t)6 * Pc);
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaMemcpy(h.data(), dbg_dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(dbg_dev);
+        double ph[5] = {0, 0, 0, 0, 0};
+        for (int64_t k = 0; k < Pc; ++k) {
+            if (!h[6 * k + 1]) h[6 * k + 1] = h[6 * k];          // CTA 0 had no tile in this block column
+            for (int q = 0; q < 5; ++q) ph[q] += (double)(h[6 * k + q + 1] - h[6 * k + q]) * 1e-3;
+        }
+        fprintf(stderr, "[potrf_tile m=%lld npiv=%lld grid=%u] CTA0 us: diag %.1f panel %.1f sync1 %.1f update %.1f sync2 %.1f total %.1f (%lld steps)\n",
+                (long long)mm, (long long)npiv, grid, ph[0], ph[1], ph[2], ph[3], ph[4], (double)(h[6 * (Pc - 1) + 5] - h[0]) * 1e-3, (long long)Pc);
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// slab triangular solve
+// ---------------------------------------------------------------------------------------
+#define SL_NC 8
+#define SL_THREADS 256
+#define SL_DLD 65
+
+template <bool TRANS>
+__global__ void __launch_bounds__(SL_THREADS, 1)
+trsm_slab_kernel(const double *__restrict__ L, long long ldl, int n, double *__restrict__ B, long long ldb, long long nrhs, int ldS) {
+    extern __shared__ __align__(16) double slsm[];
+    double *D = slsm;                    // 64 x 65: D[c*65 + r] = L11(r, c)
+    double *rinv = D + TT * SL_DLD;      // 64
+    double *S = rinv + TT;               // 8 x ldS: S[c*ldS + r]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const long long c0 = (long long)blockIdx.x * SL_NC;
+    const int ncol = (int)min((long long)SL_NC, nrhs - c0);
+    {
+        double *s = S + warp * ldS;
+        const double *b = B + (c0 + warp) * ldb;
+        for (int r = lane; r < ldS; r += 32) s[r] = (warp < ncol && r < n) ? b[r] : 0.0;
+    }
+    const int nb = (n + TT - 1) / TT;
+    for (int bq = 0; bq < nb; ++bq) {
+        const int bi = TRANS ? nb - 1 - bq : bq;
+        const int k0 = bi * TT, kb = min(TT, n - k0);
+        __syncthreads();
+        for (int idx = tid; idx < TT * TT; idx += SL_THREADS) {
+            const int r = idx & 63, c = idx >> 6;
+            D[c * SL_DLD + r] = (r >= c && r < kb) ? L[(k0 + r) + (long long)(k0 + c) * ldl] : 0.0;
+        }
+        __syncthreads();
+        if (tid < TT) rinv[tid] = tid < kb ? 1.0 / D[tid * SL_DLD + tid] : 1.0;
+        __syncthreads();
+        {
+            // one warp per right-hand side: substitution inside the 64 x 64 block
+            double *x = S + warp * ldS + k0;
+            double x0 = x[lane], x1 = x[lane + 32];
+            if (!TRANS) {
+                for (int j = 0; j < kb; ++j) {
+                    const double xj = __shfl_sync(0xffffffffu, (j < 32) ? x0 : x1, j & 31) * rinv[j];
+                    if (lane == (j & 31)) { if (j < 32) x0 = xj; else x1 = xj; }
+                    if (lane > j) x0 = fma(-D[j * SL_DLD + lane], xj, x0);
+                    if (lane + 32 > j) x1 = fma(-D[j * SL_DLD + lane + 32], xj, x1);
+                }
+            } else {
+                for (int j = kb - 1; j >= 0; --j) {
+                    const double xj = __shfl_sync(0xffffffffu, (j < 32) ? x0 : x1, j & 31) * rinv[j];
+                    if (lane == (j & 31)) { if (j < 32) x0 = xj; else x1 = xj; }
+                    if (lane < j) x0 = fma(-D[lane * SL_DLD + j], xj, x0);
+                    if (lane + 32 < j) x1 = fma(-D[(lane + 32) * SL_DLD + j], xj, x1);
+                }
+            }
+            x[lane] = x0;
+            x[lane + 32] = x1;
+        }
+        __syncthreads();
+        // rest of the block column (forward: rows below; transposed: rows above) with DMMA
+        const int kb8 = (kb + 7) & ~7;
+        if (!TRANS) {
+            const int rbeg = k0 + TT;
+            if (rbeg < n) {
+                const int nstrips = (n - rbeg + 15) / 16;
+                for (int s = warp; s < nstrips; s += SL_THREADS / 32) {
+                    const int row0 = rbeg + 16 * s;
+                    double af[8][4];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const int row = row0 + g + 8 * (v & 1);
+                            af[q][v] = row < n ? -L[row + (long long)(k0 + 8 * q + t + 4 * (v >> 1)) * ldl] : 0.0;
+                        }
+                    double c[4];
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) c[v] = S[(2 * t + (v & 1)) * ldS + row0 + g + 8 * (v >> 1)];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        double bf[2];
+#pragma unroll
+                        for (int v = 0; v < 2; ++v) bf[v] = S[g * ldS + k0 + 8 * q + t + 4 * v];
+                        dmma16x8x8_t(c, af[q], bf);
+                    }
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) S[(2 * t + (v & 1)) * ldS + row0 + g + 8 * (v >> 1)] = c[v];
+                }
+            }
+        } else if (k0 > 0) {
+            const int nstrips = k0 / 16;
+            for (int s = warp; s < nstrips; s += SL_THREADS / 32) {
+                const int i0 = 16 * s;
+                double c[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) c[v] = S[(2 * t + (v & 1)) * ldS + i0 + g + 8 * (v >> 1)];
+                for (int kk = 0; kk < kb8; kk += 8) {
+                    double af[4], bf[2];
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const int kr = kk + t + 4 * (v >> 1);
+                        af[v] = kr < kb ? -L[(k0 + kr) + (long long)(i0 + g + 8 * (v & 1)) * ldl] : 0.0;
+                    }
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) bf[v] = S[g * ldS + k0 + kk + t + 4 * v];
+                    dmma16x8x8_t(c, af, bf);
+                }
+#pragma unroll
+                for (int v = 0; v < 4; ++v) S[(2 * t + (v & 1)) * ldS + i0 + g + 8 * (v >> 1)] = c[v];
+            }
+        }
+    }
+    __syncthreads();
+    if (warp < ncol) {
+        const double *s = S + warp * ldS;
+        double *b = B + (c0 + warp) * ldb;
+        for (int r = lane; r < n; r += 32) b[r] = s[r];
+    }
+}
+
+#define SL_NMAX 2816      // 8 x (2816 + 4) doubles of slab + the diagonal block = 214 KB of shared memory
+
+bool trsm_slab_fits(int64_t n) { return n <= SL_NMAX; }
+
+int trsm_slab(smcp_ctx *ctx, bool trans, const double *L, int64_t ldl, int64_t n, double *B, int64_t ldb, int64_t nrhs) {
+    if (n <= 0 || nrhs <= 0) return 0;
+    const int ldS = (int)(((n + 15) / 16) * 16 + 64 + 4);      // = 4 (mod 16); 64 extra rows: the last block reads x[lane + 32]
+    const size_t smem = (size_t)(TT * SL_DLD + TT + (size_t)SL_NC * ldS) * sizeof(double);
+    static size_t attr[2] = {0, 0};
+    if (smem > attr[trans]) {
+        if (trans) CUDA_TRY(cudaFuncSetAttribute(trsm_slab_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else CUDA_TRY(cudaFuncSetAttribute(trsm_slab_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr[trans] = smem;
+    }
+    const long long nct = (nrhs + SL_NC - 1) / SL_NC;
+    LaunchScope ls(ctx, "trsm_slab", 1, (double)n * n * nrhs);
+    for (long long b0 = 0; b0 < nct; b0 += 1 << 30) {
+        const unsigned grid = (unsigned)std::min<long long>(1 << 30, nct - b0);
+        if (trans) trsm_slab_kernel<true><<<grid, SL_THREADS, smem, ctx->stream>>>(L, ldl, (int)n, B + b0 * SL_NC * ldb, ldb, nrhs - b0 * SL_NC, ldS);
+        else trsm_slab_kernel<false><<<grid, SL_THREADS, smem, ctx->stream>>>(L, ldl, (int)n, B + b0 * SL_NC * ldb, ldb, nrhs - b0 * SL_NC, ldS);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}

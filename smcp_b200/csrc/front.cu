@@ -106,6 +106,10 @@ __global__ void __launch_bounds__(128) trsm_diag_kernel(const double *__restrict
 
 int d_trsm_left_lower(smcp_ctx *ctx, bool trans, const double *L, int64_t ldl, int64_t n, double *B, int64_t ldb, int64_t nrhs) {
     if (n <= 0 || nrhs <= 0) return 0;
+    // L2-resident factors: one launch, every CTA keeps 8 right-hand sides in shared memory for the whole
+    // solve (dense_tile.cu); SMCP_B200_TRSM_BLOCKED=1 keeps the launch chain below (A/B measurements)
+    static const bool blocked_only = getenv("SMCP_B200_TRSM_BLOCKED") && atoi(getenv("SMCP_B200_TRSM_BLOCKED")) != 0;
+    if (!blocked_only && trsm_slab_fits(n)) return trsm_slab(ctx, trans, L, ldl, n, B, ldb, nrhs);
     const size_t smem = (size_t)(FNB * FLDT + FNB * 128) * sizeof(double);
     static bool attr = false;
     if (!attr) {

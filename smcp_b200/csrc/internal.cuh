@@ -25,7 +25,17 @@ struct ProfEntry {
     double work = 0.0;      // matrices processed (chordal kernels) or algorithmic flops (GEMM)
 };
 
+// Device time of a whole API region (assembly, factorisation, solve of the Schur complement) without
+// synchronising: a pair of events per call, resolved when the accumulator is read.
+struct RegionAcc {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    double ms = 0.0;
+    int64_t calls = 0;
+};
+
 struct smcp_ctx {
+    std::map<std::string, RegionAcc> regions;
+    std::vector<cudaEvent_t> region_pool;
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
@@ -57,6 +67,14 @@ struct LaunchScope {
     int64_t launches0;       // ctx->launches after this scope's own n: nested launches are credited to it too
     LaunchScope(smcp_ctx *c, const char *nm, int nlaunch = 1, double work = 0.0);
     ~LaunchScope();
+};
+
+struct RegionScope {
+    smcp_ctx *ctx;
+    RegionAcc *acc;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    RegionScope(smcp_ctx *c, const char *name);
+    ~RegionScope();
 };
 
 // Device-side view of the symbolic object (int32 indices).
@@ -216,14 +234,19 @@ int d_trsm_left_lower(smcp_ctx *ctx, bool trans, const double *L, int64_t ldl, i
 // dense kernels (dense.cu)
 // factor the leading ncols columns of the m x m matrix H (leading dimension ld); ncols < m leaves the
 // Schur complement in the trailing block; nranks > 1: block-cyclic columns with NCCL panel broadcasts
-int d_potrf(smcp_ctx *ctx, double *H, int64_t ld, int64_t m, int64_t ncols, int32_t *info_dev, int rank, int nranks);
+int d_potrf(smcp_ctx *ctx, double *H, int64_t ld, int64_t m, int64_t ncols, int32_t *info_dev, int rank, int nranks, int64_t block = 0);
 int d_potrs(smcp_ctx *ctx, const double *H, int64_t m, double *y_dev);
 int launch_gemm_cyc(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
                     int64_t ldc, int64_t M, int64_t N, int64_t K, double alpha, int accumulate, int tri, int64_t tri_off,
-                    const char *name, int jt0, int jtstride);
+                    const char *name, int jb0, int jbstride, int tpb = 1);
 int launch_gemm_batched(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, int64_t sA, const double *B, int64_t ldb,
                         int64_t sB, double *C, int64_t ldc, int64_t sC, int64_t M, int64_t N, int64_t K, double alpha,
                         int accumulate, int64_t batch, const char *name);
+// single-launch tile Cholesky and slab triangular solves for L2-resident matrices (dense_tile.cu)
+bool potrf_tile_fits(const smcp_ctx *ctx, int64_t mm, int64_t npiv, bool panel_only);
+int potrf_tile(smcp_ctx *ctx, double *H, int64_t ld, int64_t mm, int64_t npiv, bool panel_only, int32_t *info_dev, int col_off);
+bool trsm_slab_fits(int64_t n);
+int trsm_slab(smcp_ctx *ctx, bool trans, const double *L, int64_t ldl, int64_t n, double *B, int64_t ldb, int64_t nrhs);
 // ncclBroadcast of `count` doubles in place on stream s (capi.cu)
 int comm_bcast(smcp_ctx *ctx, double *ptr, size_t count, int root, cudaStream_t s);
 int launch_gemm(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, const double *B, int64_t ldb, double *C,

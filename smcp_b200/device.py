@@ -44,6 +44,8 @@ API = {
     "smcp_prof_get_work": (_int, [_vp, C.c_char_p, C.POINTER(_dbl)]),
     "smcp_prof_list": (_int, [_vp, C.c_char_p, _i64]),
     "smcp_prof_reset": (_int, [_vp]),
+    "smcp_region_get": (_int, [_vp, C.c_char_p, C.POINTER(_dbl), C.POINTER(_i64)]),
+    "smcp_region_reset": (_int, [_vp]),
     "smcp_flush_l2": (_int, [_vp]),
     "smcp_sym_create": (_int, [_vp, C.POINTER(SymDesc), C.POINTER(_vp)]),
     "smcp_sym_destroy": (_int, [_vp]),
@@ -77,6 +79,11 @@ API = {
     "smcp_kkt_assemble_cyclic": (_int, [_vp, _vp, _i64, _int, _int]),
     "smcp_kkt_factor": (_int, [_vp, _i32p]),
     "smcp_kkt_factor_dist": (_int, [_vp, _int, _int, _i32p]),
+    "smcp_kkt_factor_block": (_int, [_vp, _i64, _int, _int, _i32p]),
+    "smcp_dense_potrf": (_int, [_vp, _f64p, _i64, _i64, _i64, _i32p, C.POINTER(_dbl)]),
+    "smcp_dense_trsm": (_int, [_vp, _int, _f64p, _i64, _i64, _f64p, _i64, _i64, C.POINTER(_dbl)]),
+    "smcp_dense_gemm": (_int, [_vp, _int, _int, _f64p, _i64, _f64p, _i64, _f64p, _i64, _i64, _i64, _i64, _dbl, _int, _int,
+                               C.POINTER(_dbl)]),
     "smcp_kkt_solve": (_int, [_vp, _f64p]),
     "smcp_kkt_get_H": (_int, [_vp, _f64p]),
     "smcp_kkt_set_H": (_int, [_vp, _f64p]),
@@ -198,6 +205,14 @@ class Context:
         s = buf.value.decode()
         return s.split(",") if s else []
 
+    def region_get(self, name):
+        ms, n = C.c_double(), C.c_int64()
+        _ck(self.lib, self.lib.smcp_region_get(self.h, name.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def region_reset(self):
+        _ck(self.lib, self.lib.smcp_region_reset(self.h))
+
     def flush_l2(self):
         _ck(self.lib, self.lib.smcp_flush_l2(self.h))
 
@@ -266,7 +281,9 @@ class DeviceBackend:
         fl = 4.0 * nn ** 3 + 6.0 * na * nn ** 2 + 6.0 * na ** 2 * nn
         thr_flops = float(os.environ.get("SMCP_B200_BIG_FLOPS", "2e6"))
         thr_nj = int(os.environ.get("SMCP_B200_BIG_NJ", "0"))
-        has_big = symb.nsn > 0 and ((thr_flops > 0 and fl.max() >= thr_flops) or (thr_nj > 0 and nj.max() >= thr_nj))
+        thr_compl = float(os.environ.get("SMCP_B200_BIG_COMPL_FLOPS", "6e6" if thr_flops > 0 else "0"))
+        has_big = symb.nsn > 0 and ((thr_flops > 0 and fl.max() >= thr_flops) or (thr_nj > 0 and nj.max() >= thr_nj)
+                                    or (thr_flops > 0 and thr_compl > 0 and (na ** 3).max() / 3.0 >= thr_compl))
         self.batched_probes = not (has_big and (nj.max() > 8 or thr_nj > 0))
         if self.batched_probes and symb.nblk * 255 * 8 <= (1 << 30):
             # workspaces of the batched line-search probes (255 candidates) sized at setup time
@@ -509,10 +526,10 @@ class DeviceBackend:
         else:
             rank, nranks, block = self.comm
             _ck(self.lib, self.lib.smcp_kkt_assemble_cyclic(self._op, tok, block, rank, nranks))
-            if block == 128:
-                # block-cyclic Cholesky: owners factor their 128-column blocks and broadcast the
+            if block % 128 == 0:
+                # block-cyclic Cholesky: owners factor their column blocks and broadcast the
                 # panels (NCCL); no gather of the unfactored H is needed
-                _ck(self.lib, self.lib.smcp_kkt_factor_dist(self._op, rank, nranks, info))
+                _ck(self.lib, self.lib.smcp_kkt_factor_block(self._op, block, rank, nranks, info))
             else:
                 _ck(self.lib, self.lib.smcp_kkt_allgather(self._op, block, rank, nranks))
                 _ck(self.lib, self.lib.smcp_kkt_factor(self._op, info))

@@ -44,6 +44,7 @@ options = {
 
 _backend_factory = None
 _iteration_hook = None      # optional callable(solver_name, iteration) used by bench.py for timing
+_last_problem = None        # the _Problem of the most recent driver call (instrumentation: pattern / flop statistics)
 
 
 def set_backend_factory(factory):
@@ -217,6 +218,8 @@ class _Problem:
         self.ops = ops = _make_backend(symb)
         ops.set_operator(self.Av, Ns)
         self.C = cspmatrix.from_vec(ops, c)
+        global _last_problem
+        _last_problem = self
 
     # operators (solvers.py:369-384)
     def Amap(self, X, i=None):

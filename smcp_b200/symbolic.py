@@ -24,6 +24,8 @@ the device copies are int32.
 from __future__ import annotations
 
 import heapq
+import os
+
 import numpy as np
 
 __all__ = ["maxcardsearch", "peo", "embed", "min_degree", "Symbolic", "lower_pattern",
@@ -193,7 +195,11 @@ def _py_min_degree(n, colptr, rowind):
 # The Python functions above are the specification; the drivers go through these dispatchers.
 # --------------------------------------------------------------------------------------
 def _native():
-    """The shared library if it is built (host symbolic code needs no GPU), else None."""
+    """The shared library if it is built (host symbolic code needs no GPU), else None.
+    ``SMCP_B200_NO_NATIVE_HOST=1`` forces the pure-NumPy specification (the CPU baseline of bench.py
+    uses it so that no library of this repository is mapped in the reference arm)."""
+    if os.environ.get("SMCP_B200_NO_NATIVE_HOST"):
+        return None
     try:
         from . import device
         return device.load_library()
