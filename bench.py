@@ -341,10 +341,14 @@ def measure_workload(workload, W, K, ctx, rank, world, pg, local, do_solve, hbm,
     h2d = (TRAFFIC["h2d"] - snap["traffic"]["h2d"]) // K
     d2h = (TRAFFIC["d2h"] - snap["traffic"]["d2h"]) // K
     n_launch = ctx.launch_count() - snap["launches"]
-    regions = {}
-    for nm in ("kkt_assemble", "kkt_factor", "kkt_solve", "kkt_allgather"):
+    regions = {nm: {"ms_per_step": 0.0, "calls_per_step": 0.0} for nm in ("kkt_assemble", "kkt_factor", "kkt_solve", "kkt_allgather")}
+    ops_ms = {}
+    for nm in ctx.region_names():
         ms, calls = ctx.region_get(nm)
-        regions[nm] = {"ms_per_step": ms / K, "calls_per_step": calls / K}
+        if nm.startswith("kkt_"):
+            regions[nm] = {"ms_per_step": ms / K, "calls_per_step": calls / K}
+        elif calls:
+            ops_ms[nm] = {"ms_per_step": ms / K, "calls_per_step": calls / K}
     prob = solvers._last_problem
     fm = flop_model(prob) if prob is not None else None
     nvp = prob.symb.nvp if prob is not None else 0
@@ -375,7 +379,7 @@ def measure_workload(workload, W, K, ctx, rank, world, pg, local, do_solve, hbm,
         pg.all_reduce(t, op=pg.ReduceOp.MAX)
         e2e_s, dev_s, sp_s = float(t[0]), float(t[1]), float(t[2])
 
-    out = {"e2e_s": e2e_s, "dev_s": dev_s, "h2d": int(h2d), "d2h": int(d2h), "launches": int(n_launch),
+    out = {"e2e_s": e2e_s, "dev_s": dev_s, "h2d": int(h2d), "d2h": int(d2h), "launches": int(n_launch), "ops": ops_ms,
            "clocks": clocks, "status": sol["status"], "iterations": int(iters), "n": n, "m": m, "nvp": int(nvp)}
     if rank != 0:
         return out
@@ -429,11 +433,15 @@ def measure_workload(workload, W, K, ctx, rank, world, pg, local, do_solve, hbm,
 
 def run_b200(args):
     rank, world, local, pg = dist_setup()
-    # NCCL's communicator lines stay visible (stderr), stdout carries only the JSON line
+    # NCCL's communicator lines stay visible: NCCL writes its INFO lines to stdout, so for N > 1 file
+    # descriptor 1 is pointed at stderr for the whole run and the one JSON line goes to the saved stdout
+    json_fd = None
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
     os.environ["LOCAL_RANK"] = str(local)
     from smcp_b200 import device
     from smcp_b200.device import Context
@@ -445,6 +453,8 @@ def run_b200(args):
             idt = torch.frombuffer(bytearray(device.comm_unique_id()), dtype=torch.uint8).clone()
         pg.broadcast(idt, src=0)
         device.init_comm(rank, world, bytes(idt.numpy().tobytes()), block=DIST_BLOCK, device=local)
+        print("smcp_b200: NCCL communicator ready: rank %d nranks %d (column blocks of %d)" % (rank, world, DIST_BLOCK),
+              file=sys.stderr, flush=True)
 
     W, K = args.warmup, args.steps
     hbm = load_peaks()
@@ -456,7 +466,7 @@ def run_b200(args):
         sec = measure_workload(sec_name, W, K, ctx, rank, world, pg, local, not args.no_solve, hbm, fp64_peak)
     if rank != 0:
         return
-    cpu = cpu_baseline(args.workload)
+    cpu = cpu_baseline(args.workload) if world == 1 else None       # host baseline: rank 0 at N = 1 only
     cfg = config_of(args.workload)
     cfg["l2"] = "working set > L2 per iteration (H alone is %d MB)" % (8 * main["m"] ** 2 // 2 ** 20)
     cfg["parallelism"] = "schur-columns block-cyclic x%d (blocks of %d columns)" % (world, DIST_BLOCK)
@@ -471,6 +481,7 @@ def run_b200(args):
         "roofline": main["roofline"],
         "cpu_baseline": cpu,
         "schur_potrf": main["schur_potrf"],
+        "chordal_ops_ms_per_step": main["ops"],
         "kernel_ms_per_step": main["kernel_ms_per_step"],
         "family_rooflines": main["family_rooflines"],
         "time_to_solve": main["time_to_solve"],
@@ -482,9 +493,14 @@ def run_b200(args):
             "config": config_of(sec_name), "e2e": {"value": sec["e2e_s"], "unit": "s/iter",
                                                    "h2d_bytes_per_step": sec["h2d"], "d2h_bytes_per_step": sec["d2h"]},
             "value": sec["dev_s"], "unit": "s/iter", "gpu_launches": sec["launches"], "roofline": sec["roofline"],
-            "schur_potrf": sec["schur_potrf"], "kernel_ms_per_step": sec["kernel_ms_per_step"],
+            "schur_potrf": sec["schur_potrf"], "chordal_ops_ms_per_step": sec["ops"], "kernel_ms_per_step": sec["kernel_ms_per_step"],
             "family_rooflines": sec["family_rooflines"], "time_to_solve": sec["time_to_solve"], "clocks": sec["clocks"]}
-    print(json.dumps(out))
+    line = json.dumps(out)
+    if json_fd is None:
+        print(line)
+    else:
+        sys.stdout.flush()
+        os.write(json_fd, (line + "\n").encode())
 
 
 # --------------------------------------------------------------------------------------

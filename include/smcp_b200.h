@@ -56,6 +56,9 @@ int smcp_prof_reset(smcp_ctx *ctx);
  * event pair per call on the context's stream, no synchronisation until read; ms and calls since reset */
 int smcp_region_get(smcp_ctx *ctx, const char *name, double *ms_out, int64_t *calls_out);
 int smcp_region_reset(smcp_ctx *ctx);
+/* comma-separated names of all regions seen so far: the kkt_* ones and one per chordal operation
+ * ("op_cholesky", "op_completion", "op_hessian", "op_hessian_inv", "op_hessian_batch", ...) */
+int smcp_region_list(smcp_ctx *ctx, char *buf, int64_t cap);
 /* write (flush) a buffer larger than L2 */
 int smcp_flush_l2(smcp_ctx *ctx);
 
@@ -134,6 +137,9 @@ int smcp_hess_create(smcp_sym *sym, const double *L, const double *Y, smcp_hess 
 int smcp_hess_destroy(smcp_hess *h);
 /* U <- P(S^-1 U S^-1) (inv=0) or its inverse map (inv=1) on `batch` matrices (stride nblk) */
 int smcp_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv);
+/* chompack.hessian(L, Y, U, adj=False/True, inv=...) (solvers.py:917, 978, 1121, 1126): the half factors
+ * G (adj=0, inv=0), G^adj (1, 0), G^-1 (0, 1), G^-adj (1, 1) with hessian = G^adj o G; in place on a batch */
+int smcp_hess_apply_half(smcp_hess *h, double *U_dev, int64_t batch, int inv, int adj);
 
 /* ---- constraint operator and Schur complement (kkt_chol, solvers.py:477-541) ------------
  * Av: |Vp| x m CCS, rows in vector-space order, columns already permuted so that the last

@@ -87,9 +87,11 @@ class OracleBackend:
         hf.Lbuf = Lbuf.copy()
         return hf
 
-    def hessian_apply(self, hf, bufs, inv):
+    def hessian_apply(self, hf, bufs, inv, adj=None):
         for b in bufs:
-            if inv:
+            if adj is not None:
+                sn.hessian_half(hf, b, bool(adj), bool(inv))
+            elif inv:
                 sn.hessian_inv(hf, b)
             else:
                 sn.hessian(hf, b)
@@ -116,30 +118,39 @@ class OracleBackend:
         return self.from_vec(self.Av @ np.asarray(y, dtype=np.float64).ravel())
 
     # -- Schur complement -------------------------------------------------------------
-    def schur_assemble(self, hf):
-        """Lower triangle of H, H_ij = A_i . Hess(A_j) (``solvers.py:479-497``)."""
+    def schur_assemble(self, hf, columns=None):
+        """Lower triangle of H, H_ij = A_i . Hess(A_j) (``solvers.py:479-497``).  ``columns``: list of
+        (j0, j1) column ranges to assemble (the blocks a rank owns); the other columns stay zero."""
         symb, Av, m, Ns = self.symb, self.Av, self.m, self.Ns
         H = self.H
         H[...] = 0.0
         md = m - Ns
         B = max(1, self.batch_columns)
+        own = np.ones(m, dtype=bool)
+        if columns is not None:
+            own[:] = False
+            for c0, c1 in columns:
+                own[c0:c1] = True
         # technique 1: one Hessian evaluation per "dense" constraint
-        for j0 in range(0, md, B):
-            j1 = min(md, j0 + B)
-            U = np.zeros((j1 - j0, symb.nblk))
-            for j in range(j0, j1):
+        dense_cols = [j for j in range(md) if own[j]]
+        for b0 in range(0, len(dense_cols), B):
+            batch = dense_cols[b0:b0 + B]
+            U = np.zeros((len(batch), symb.nblk))
+            for q, j in enumerate(batch):
                 c0, c1 = Av.indptr[j], Av.indptr[j + 1]
-                U[j - j0, symb.vec2blk[Av.indices[c0:c1]]] = Av.data[c0:c1]
+                U[q, symb.vec2blk[Av.indices[c0:c1]]] = Av.data[c0:c1]
             sn.hessian(hf, U)
-            self.stats["hessian_cols"] += j1 - j0
-            for j in range(j0, j1):
-                at = U[j - j0, symb.vec2blk] * self.halfdiag
+            self.stats["hessian_cols"] += len(batch)
+            for q, j in enumerate(batch):
+                at = U[q, symb.vec2blk] * self.halfdiag
                 H[j:, j] = 2.0 * (self.AvT[j:, :] @ at)
         # technique 2: sparse constraints through columns of S^{-1}
         if Ns:
             Ip, Jp = symb.Ip, symb.Jp
             for j in range(Ns):
                 jj = md + j
+                if not own[jj]:
+                    continue
                 c0, c1 = Av.indptr[jj], Av.indptr[jj + 1]
                 rows_j = Av.indices[c0:c1]
                 K = np.unique(np.concatenate([Ip[rows_j], Jp[rows_j]]))

@@ -292,6 +292,94 @@ def hessian_inv(hf, Z):
         _write_lower(blk, nn, 0.5 * (Fnn + Fnn.swapaxes(1, 2)), Fan)
 
 
+def hessian_half(hf, U, adj, inv):
+    """The half factors of the Hessian (``chompack.hessian(L, Y, U, adj=False/True, inv=...)``;
+    ``solvers.py:917, 978, 1121, 1126``).  With Y_aa = R R^T per supernode and pass 1 / pass 3 the two
+    congruence sweeps of ``hessian`` (App. A.4):
+        G        (adj=False, inv=False) = half scaling o pass 1   : (K_nn, K_an) -> (L^-1 K_nn L^-T, R^T K_an L^-T)
+        G^adj    (adj=True,  inv=False) = pass 3 o half scaling^adj: (V_nn, V_an) -> (L^-T V_nn L^-1, R V_an L^-1)
+        G^-1     (adj=False, inv=True)  and  G^-adj (adj=True, inv=True) are their inverses,
+    so that hessian = G^adj o G, hessian_inv = G^-1 o G^-adj and ||G(U)||^2 = U . hessian(U)."""
+    symb = hf.symb
+    U = _as2d(U)
+    T = lambda a: a.swapaxes(1, 2)
+    if not inv and not adj:
+        upd = [None] * symb.nsn
+        for k in range(symb.nsn):
+            nn, na = int(symb.nn[k]), int(symb.na[k])
+            F = _frontal(symb, U, k, upd)
+            Lnn, Lt = hf.Lnn[k], hf.Lt[k]
+            Knn = F[:, :nn, :nn]
+            X1 = sl.solve_triangular(Lnn, Knn, lower=True)                            # L^-1 K
+            Gnn = T(sl.solve_triangular(Lnn, T(X1), lower=True))                      # L^-1 K L^-T
+            if na:
+                Kan = F[:, nn:, :nn] - Lt @ Knn
+                upd[k] = F[:, nn:, nn:] - Lt @ F[:, :nn, nn:] - Kan @ Lt.T
+                Gan = hf.chol_Yaa(k).T @ T(sl.solve_triangular(Lnn, T(Kan), lower=True))   # R^T K_an L^-T
+            else:
+                Gan = F[:, nn:, :nn]
+            _write_lower(_blk(symb, U, k), nn, 0.5 * (Gnn + T(Gnn)), Gan)
+    elif not inv and adj:
+        for k in range(symb.nsn - 1, -1, -1):
+            nn, na = int(symb.nn[k]), int(symb.na[k])
+            blk = _blk(symb, U, k)
+            Lnn, Lt = hf.Lnn[k], hf.Lt[k]
+            Vnn = _sym(blk[:, :nn, :])
+            X1 = sl.solve_triangular(Lnn, Vnn, lower=True, trans='T')                  # L^-T V
+            Mnn = T(sl.solve_triangular(Lnn, T(X1), lower=True, trans='T'))           # L^-T V L^-1
+            if na:
+                Man = hf.chol_Yaa(k) @ T(sl.solve_triangular(Lnn, T(blk[:, nn:, :]), lower=True, trans='T'))   # R V_an L^-1
+                Zaa = _gather_aa(symb, U, k)
+                Zan = Man - Zaa @ Lt
+                Znn = Mnn - Lt.T @ Man - T(Zan) @ Lt
+            else:
+                Zan, Znn = blk[:, nn:, :], Mnn
+            _write_lower(blk, nn, 0.5 * (Znn + T(Znn)), Zan)
+    elif inv and adj:
+        for k in range(symb.nsn):
+            nn, na = int(symb.nn[k]), int(symb.na[k])
+            blk = _blk(symb, U, k)
+            Lnn, Lt = hf.Lnn[k], hf.Lt[k]
+            Znn = _sym(blk[:, :nn, :])
+            if na:
+                Zan = blk[:, nn:, :]
+                Zaa = _gather_aa(symb, U, k)
+                Man = Zan + Zaa @ Lt
+                Mnn = Znn + Lt.T @ Zan + T(Man) @ Lt
+                Van = sl.solve_triangular(hf.chol_Yaa(k), Man, lower=True) @ Lnn        # R^-1 M_an L
+            else:
+                Mnn, Van = Znn, blk[:, nn:, :]
+            Vnn = Lnn.T @ Mnn @ Lnn
+            _write_lower(blk, nn, 0.5 * (Vnn + T(Vnn)), Van)
+    else:
+        upd = [None] * symb.nsn
+        for k in range(symb.nsn):
+            nn, na = int(symb.nn[k]), int(symb.na[k])
+            blk = _blk(symb, U, k)
+            Lnn, Lt = hf.Lnn[k], hf.Lt[k]
+            Knn = Lnn @ _sym(blk[:, :nn, :]) @ Lnn.T
+            if na:
+                Kan = sl.solve_triangular(hf.chol_Yaa(k), blk[:, nn:, :], lower=True, trans='T') @ Lnn.T   # R^-T V_an L^T
+                Fan = Kan + Lt @ Knn
+                Faa = Lt @ T(Kan) + Fan @ Lt.T
+            else:
+                Fan, Faa = blk[:, nn:, :], None
+            Fnn = Knn.copy()
+            for c in _children(symb, k):
+                r = _rel(symb, c)
+                own = r < nn
+                ro, ra = r[own], r[~own] - nn
+                Uc = upd[c]
+                Fnn[:, ro[:, None], ro[None, :]] += Uc[:, own][:, :, own]
+                if na:
+                    Fan[:, ra[:, None], ro[None, :]] += Uc[:, ~own][:, :, own]
+                    Faa[:, ra[:, None], ra[None, :]] += Uc[:, ~own][:, :, ~own]
+                upd[c] = None
+            if na:
+                upd[k] = Faa
+            _write_lower(blk, nn, 0.5 * (Fnn + T(Fnn)), Fan)
+
+
 def trsm(symb, L, Bm, trans='N'):
     """Dense right-hand sides: Bm <- L^{-1} Bm ('N') or L^{-T} Bm ('T'), Bm is n x k with
     rows in the *internal* order of ``symb`` (App. A.8; ``chompack.trsm`` at

@@ -30,7 +30,7 @@ if world > 1:
     if rank == 0:
         idt = torch.frombuffer(bytearray(device.comm_unique_id()), dtype=torch.uint8).clone()
     dist.broadcast(idt, src=0)
-    device.init_comm(rank, world, bytes(idt.numpy().tobytes()), block=128, device=local)
+    device.init_comm(rank, world, bytes(idt.numpy().tobytes()), block=int(os.environ.get("SMCP_BLOCK", "256")), device=local)
 
 n = 8000
 I = np.concatenate([np.arange(n), np.arange(1, n), np.arange(2, n), np.arange(3, n)])
@@ -53,7 +53,7 @@ for m in [int(a) for a in sys.argv[1:]] or [1000, 4000]:
             dist.barrier()
         ctx.sync()
         t0 = time.perf_counter()
-        _ck(ops.lib, ops.lib.smcp_kkt_factor_dist(ops._op, rank, world, info))
+        _ck(ops.lib, ops.lib.smcp_kkt_factor_block(ops._op, int(os.environ.get("SMCP_BLOCK", "256")), rank, world, info))
         best = min(best, time.perf_counter() - t0)
         assert info[0] == 0
     rhs = rng.standard_normal(m)

@@ -35,8 +35,18 @@ BLOCK = int(os.environ.get("SMCP_BLOCK", "128"))
 device.init_comm(rank, world, bytes(idt.numpy().tobytes()), block=BLOCK, device=local)
 
 solvers.options["show_progress"] = False
-n, m, bw = (int(a) for a in (sys.argv[1:4] if len(sys.argv) > 3 else (600, 300, 5)))
-P = S.band_SDP(n, m, bw, seed=0)
+if len(sys.argv) > 1 and sys.argv[1] == "rand":
+    # sparse constraints (technique 2: dense inverse + position kernel per owned block)
+    import scipy.sparse as sp
+    n, m = int(sys.argv[2]), int(sys.argv[3])
+    r0 = np.random.default_rng(0)
+    e = r0.integers(0, n, size=(6 * n, 2))
+    V = sp.coo_matrix((np.ones(6 * n + 2 * n - 1), (np.concatenate([np.maximum(e[:, 0], e[:, 1]), np.arange(n), np.arange(1, n)]),
+                                                    np.concatenate([np.minimum(e[:, 0], e[:, 1]), np.arange(n), np.arange(0, n - 1)]))), shape=(n, n))
+    P = S.rand_SDP(V, m, density=0.005, seed=0)
+else:
+    n, m, bw = (int(a) for a in (sys.argv[1:4] if len(sys.argv) > 3 else (600, 300, 5)))
+    P = S.band_SDP(n, m, bw, seed=0)
 pr = _Problem(P.A, P.b, _read_options(P.n, True), "chol", None)
 ops, symb = pr.ops, pr.symb
 rng = np.random.default_rng(0)

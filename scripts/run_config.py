@@ -83,6 +83,11 @@ if full:
     raise SystemExit(0)
 for a, b in zip(its[:-1], its[1:]):
     print("  iteration %d: %.2f ms" % (a, 1e3 * (stamps[b] - stamps[a])))
+print("  API regions over the whole solve (device ms between event pairs, no synchronisation; calls):")
+for nm in sorted(ctx.region_names(), key=lambda k: -ctx.region_get(k)[0]):
+    ms, calls = ctx.region_get(nm)
+    if calls:
+        print("    %-24s %10.2f ms %6d calls %9.3f ms/call" % (nm, ms, calls, ms / calls))
 if os.environ.get("RUNCFG_NOPROF"):
     raise SystemExit(0)
 # pass 2: the same iterations with per-launch CUDA-event timing (serialises the launches)

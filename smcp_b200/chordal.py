@@ -167,13 +167,16 @@ def _factor_token(L, Y):
 def hessian(L, Y, U, inv=False, adj=None):
     """``chompack.hessian(L, Y, U, adj=None, inv=...)``: U <- P_V(S^{-1} U S^{-1}) with
     S = L L^T (``inv=False``) or its inverse map (``inv=True``).  U is a cspmatrix or a list
-    of them (evaluated as one device batch).  The half factors (``adj=True/False``) are only
-    used by the reference to form Newton decrements ``||G(u)||``; use ``hessian_norm``."""
-    if adj is not None:
-        raise NotImplementedError("half-factor application: use hessian_norm()")
+    of them (evaluated as one device batch).  ``adj=False`` / ``adj=True`` apply the half factors
+    G / G^adj (``inv=True``: G^-1 / G^-adj) with ``hessian = G^adj o G``, as chompack does
+    (``solvers.py:917, 978, 1121, 1126``).  The drivers only need ``||G(u)||`` and take the cheaper
+    ``hessian_norm``; the half factors themselves run through the generic supernodal sweeps."""
     Us = U if isinstance(U, (list, tuple)) else [U]
     tok = _factor_token(L, Y)
-    L.ops.hessian_apply(tok, [_inplace(u).buf for u in Us], bool(inv))
+    if adj is None:
+        L.ops.hessian_apply(tok, [_inplace(u).buf for u in Us], bool(inv))
+    else:
+        L.ops.hessian_apply(tok, [_inplace(u).buf for u in Us], bool(inv), bool(adj))
 
 
 def hessian_norm(L, Y, u, inv):

@@ -164,6 +164,23 @@ __global__ void big_reverse_kernel(const double *__restrict__ S, long long lds, 
     }
 }
 
+// completion: the clique matrix in the order [alpha; nu], lower triangle:
+//   T[0:na, 0:na] = X_aa (gathered from the ancestors), T[na:, 0:na] = X_an^T, T[na:, na:] = X_nn
+__global__ void big_compl_front_kernel(const int *__restrict__ aaidx, const double *__restrict__ Xb, const double *__restrict__ bin,
+                                       double *__restrict__ T, int nn, int na, int nj) {
+    BIG_LOOP((long long)nj * nj) {
+        const int i = (int)(idx % nj), j = (int)(idx / nj);
+        double v = 0.0;
+        if (j < na) {
+            if (i < na) v = Xb[aaidx[i + (long long)j * na]];
+            else v = bin[(nn + j) + (long long)(i - na) * nj];
+        } else if (i >= j) {
+            v = bin[(i - na) + (long long)(j - na) * nj];
+        }
+        T[idx] = v;
+    }
+}
+
 // inverse Hessian, final assembly: children (full) are added to (K_nn, F_an, F_aa)
 __global__ void big_hinv_store_kernel(BigArgs r, const double *__restrict__ Knn, const double *__restrict__ Fan, const double *__restrict__ Faa,
                                       double *__restrict__ blk, double *__restrict__ U) {
@@ -482,18 +499,18 @@ int big_completion(smcp_sym *s, const BigNode &q, double *X, const double *Xin, 
     const double *Xi = Xin + (size_t)b * s->d.nblk;
     const double *bin = Xi + q.boff;
     double *bout = X + (size_t)b * s->d.nblk + q.boff;
-    double *R = WS(0), *Z = WS(1), *Dl = WS(2), *T0 = WS(3), *M = WS(4), *Li = WS(5);
-    ELEM(big_sym_copy_kernel, (long long)nn * nn, bin, nj, Dl, nn, nn);
+    double *T = WS(0), *Z = WS(1), *T0 = WS(3), *M = WS(4), *Li = WS(5);
+    // The clique reordered as [alpha; nu]: ONE partial factorisation of T = [X_aa . ; X_na X_nn] with na
+    // pivots gives R = chol(X_aa), Z^T = X_na R^-T in the rows below it and Delta = X_nn - Z^T Z in
+    // the trailing block (instead of potrf + a forward solve + a rank-na product per supernode)
+    ELEM(big_compl_front_kernel, (long long)nj * nj, s->d.aaidx + q.uoff, Xi, bin, T, nn, na, nj);
     if (na) {
-        ELEM(big_gather_aa_kernel, (long long)na * na, s->d.aaidx + q.uoff, Xi, R, (long long)na * na);
-        if (d_potrf(ctx, R, na, na, na, s->big_info, 0, 1)) return -1;
+        if (d_potrf(ctx, T, nj, nj, na, s->big_info, 0, 1)) return -1;
         big_flag_kernel<<<1, 1, 0, ctx->stream>>>(s->big_info, s->fail + b);
-        ELEM(big_copy_mat_kernel, (long long)na * nn, bin + nn, nj, Z, na, na, nn, 0);
-        if (d_trsm_left_lower(ctx, false, R, na, na, Z, na, nn)) return -1;                         // Z = R^-1 X_an
-        if (G(s, true, true, Z, na, Z, na, Dl, nn, nn, nn, na, -1.0, 1)) return -1;                 // Delta = X_nn - Z^T Z
-        if (d_trsm_left_lower(ctx, true, R, na, na, Z, na, nn)) return -1;                          // W = X_aa^-1 X_an
+        big_transpose(s, T + na, nj, nn, na, Z, na);                                                // Z = R^-1 X_an
+        if (d_trsm_left_lower(ctx, true, T, nj, na, Z, na, nn)) return -1;                          // W = X_aa^-1 X_an
     }
-    ELEM(big_reverse_kernel, (long long)nn * nn, Dl, nn, T0, nn, 0);
+    ELEM(big_reverse_kernel, (long long)nn * nn, T + na + (size_t)na * nj, nj, T0, nn, 0);
     if (d_potrf(ctx, T0, nn, nn, nn, s->big_info, 0, 1)) return -1;
     big_flag_kernel<<<1, 1, 0, ctx->stream>>>(s->big_info, s->fail + b);
     ELEM(big_reverse_kernel, (long long)nn * nn, T0, nn, M, nn, 1);                                 // Delta = M^T M
@@ -530,6 +547,8 @@ int big_hess_prep_inv(smcp_sym *s, const BigNode &q, const double *Yaa_all, doub
     ELEM(big_copy_mat_kernel, (long long)na * na, Yaa_all + q.uoff, na, Raa_all + q.uoff, na, na, na, 0);
     if (d_potrf(ctx, Raa_all + q.uoff, na, na, na, s->big_info, 0, 1)) return -1;
     big_flag_kernel<<<1, 1, 0, ctx->stream>>>(s->big_info, s->fail);
+    // strictly upper part <- 0 (the factorisation leaves Y's entries there; the half factors use R as a dense block)
+    ELEM(big_copy_mat_kernel, (long long)na * na, Raa_all + q.uoff, na, Raa_all + q.uoff, na, na, na, 1);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

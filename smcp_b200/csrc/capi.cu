@@ -95,6 +95,16 @@ extern "C" int smcp_region_get(smcp_ctx *ctx, const char *name, double *ms_out, 
     *calls_out = it->second.calls;
     return 0;
 }
+extern "C" int smcp_region_list(smcp_ctx *ctx, char *buf, int64_t cap) {
+    std::string out;
+    for (auto &kv : ctx->regions) {
+        if (!out.empty()) out += ",";
+        out += kv.first;
+    }
+    if ((int64_t)out.size() + 1 > cap) { smcp_set_error("smcp_region_list: buffer too small"); return -2; }
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return 0;
+}
 extern "C" int smcp_region_reset(smcp_ctx *ctx) {
     for (auto &kv : ctx->regions) {
         region_resolve(ctx, kv.second);
@@ -472,6 +482,7 @@ extern "C" int smcp_hess_destroy(smcp_hess *h) {
     return 0;
 }
 extern "C" int smcp_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) { return k_hess_apply(h, U, batch, inv); }
+extern "C" int smcp_hess_apply_half(smcp_hess *h, double *U, int64_t batch, int inv, int adj) { return k_hess_apply_half(h, U, batch, inv, adj); }
 
 // ---------------------------------------------------------------------------------------
 // constraint operator, Schur complement

@@ -159,6 +159,7 @@ int fetch_fail(smcp_sym *s, int64_t batch, int32_t *info_host) {
 static bool use_big(const smcp_sym *s, int64_t batch) { return !s->big.empty() && batch <= 4; }
 
 int k_cholesky(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
+    RegionScope rs(s->ctx, batch > 1 ? "op_cholesky_batch" : "op_cholesky");
     if (s->small) return ks_cholesky(s, x, batch, info_host);
     if (sym_ensure(s, batch, false)) return -1;
     CUDA_TRY(cudaMemsetAsync(s->fail, 0, (size_t)batch * sizeof(int), s->ctx->stream));
@@ -177,6 +178,7 @@ int k_cholesky(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
 }
 
 int k_llt(smcp_sym *s, double *x, int64_t batch) {
+    RegionScope rs(s->ctx, "op_llt");
     if (s->small) return ks_llt(s, x, batch);
     if (sym_ensure(s, batch, false)) return -1;
     TreeArgs a = {};
@@ -193,6 +195,7 @@ int k_llt(smcp_sym *s, double *x, int64_t batch) {
 }
 
 int k_projinv(smcp_sym *s, double *x, int64_t batch) {
+    RegionScope rs(s->ctx, "op_projected_inverse");
     if (s->small) return ks_projinv(s, x, batch);
     if (sym_ensure(s, batch, false)) return -1;
     TreeArgs a = {};
@@ -210,6 +213,7 @@ int k_projinv(smcp_sym *s, double *x, int64_t batch) {
 static TaskSched flat_sched(const smcp_sym *s) { return s->flat; }
 
 int k_completion(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
+    RegionScope rs(s->ctx, batch > 1 ? "op_completion_batch" : "op_completion");
     if (s->small) return ks_completion(s, x, batch, info_host);
     if (sym_ensure(s, batch, true)) return -1;
     smcp_ctx *ctx = s->ctx;
@@ -230,6 +234,7 @@ int k_completion(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
 }
 
 int k_hess_prep(smcp_hess *h, const double *L, const double *Y) {
+    RegionScope rs(h->sym->ctx, "op_hessian_prep");
     if (h->sym->small) return ks_hess_prep(h, L, Y);
     smcp_sym *s = h->sym;
     if (sym_ensure(s, 1, false)) return -1;
@@ -248,6 +253,7 @@ int k_hess_prep(smcp_hess *h, const double *L, const double *Y) {
 }
 
 int k_hess_prep_inv(smcp_hess *h) {
+    RegionScope rs(h->sym->ctx, "op_hessian_prep_inv");
     if (h->sym->small) return ks_hess_prep_inv(h);
     smcp_sym *s = h->sym;
     if (sym_ensure(s, 1, false)) return -1;
@@ -265,6 +271,7 @@ int k_hess_prep_inv(smcp_hess *h) {
 }
 
 int k_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
+    RegionScope rs(h->sym->ctx, inv ? (batch > 4 ? "op_hessian_inv_batch" : "op_hessian_inv") : (batch > 4 ? "op_hessian_batch" : "op_hessian"));
     if (h->sym->small) return ks_hess_apply(h, U, batch, inv);
     smcp_sym *s = h->sym;
     if (sym_ensure(s, batch, false)) return -1;
@@ -303,6 +310,35 @@ int k_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
             for (const BigNode &q : s->big)
                 if (big_hess_inv(s, q, h->Lt, h->Raa, U, b)) return -1;
     return 0;
+}
+
+// Half factors of the Hessian (chompack.hessian(L, Y, U, adj=False/True, inv=...), reference call sites
+// src/python/solvers.py:917, 978, 1121, 1126): G, G^adj, G^-1, G^-adj with hessian = G^adj G.  The
+// drivers only need ||G(u)|| (smcp_b200.chordal.hessian_norm), so these run through the generic
+// CTA-per-supernode sweeps on every pattern (no chain / tiny-clique / dense top-set variants).
+int k_hess_apply_half(smcp_hess *h, double *U, int64_t batch, int inv, int adj) {
+    smcp_sym *s = h->sym;
+    RegionScope rs(s->ctx, "op_hessian_half");
+    if (sym_ensure(s, batch, false)) return -1;
+    if (grow((void **)&s->upd, &s->upd_cap, ((size_t)batch * (size_t)s->d.nupd + 1) * sizeof(double))) return -1;
+    if (!h->have_Raa) {
+        if (k_hess_prep_inv(h)) return -1;
+        h->have_Raa = true;
+    }
+    TreeArgs a = {};
+    a.X = U;
+    a.upd = s->upd;
+    a.Lt = h->Lt;
+    a.Yaa = h->Yaa;
+    a.Raa = h->Raa;
+    const int threads = pick_threads(s, false);
+    if (!inv) {
+        a.half = 1;
+        if (!adj) return launch_tree<OP_HFWD_UP>(s, a, s->up, batch, threads, "hessian_half");
+        return launch_tree<OP_HFWD_DOWN>(s, a, s->down, batch, threads, "hessian_half");
+    }
+    a.half = adj ? 1 : 2;
+    return launch_tree<OP_HINV>(s, a, s->up, batch, threads, "hessian_half");
 }
 
 // ---------------------------------------------------------------------------------------
@@ -370,6 +406,7 @@ __global__ void trsm_kernel(SymDev S, const double *L, double *B, long long ldb,
 }
 
 int k_trsm(smcp_sym *s, const double *L, double *B, int64_t ldb, int64_t nrhs, int trans) {
+    RegionScope rs(s->ctx, "op_trsm");
     smcp_ctx *ctx = s->ctx;
     int cols = 8;
     int grid = (int)((nrhs + cols - 1) / cols);

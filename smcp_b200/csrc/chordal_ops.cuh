@@ -31,6 +31,8 @@ struct TreeArgs {
     long long ws_stride;
     int use_smem;
     const int *skipflag; // per supernode: 1 = left to the dense top-set path (bigfront.cu); may be null
+    int half;            // half factors of the Hessian (chompack's adj=False/True): 0 = full map;
+                         // forward sweeps: 1 = G (up) / G^adj (down); inverse sweep: 1 = G^-adj, 2 = G^-1
 };
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
@@ -388,6 +390,9 @@ __device__ void op_hprep_inv(const TreeArgs &a, const Node &q) {
     for (int idx = TID; idx < na * na; idx += NT) R[idx] = Y[idx];
     SYNC();
     if (na) chol_panel<W>(R, na, na, na, a.fail);
+    for (int idx = TID; idx < na * na; idx += NT)
+        if (idx % na < idx / na) R[idx] = 0.0;          // strictly upper part: the half factors use R as a dense block
+    SYNC();
 }
 
 template <bool W>
@@ -453,16 +458,22 @@ __device__ void op_hfwd_up(const TreeArgs &a, const Node &q, int b, double *ws) 
         }
         SYNC();
     }
-    // M_nn = D^{-1} K_nn D^{-1}, D = L L^T
+    // M_nn = D^{-1} K_nn D^{-1}, D = L L^T   (half factor G: L^{-1} K_nn L^{-T})
     trsm_ll<W>(Lb, nj, nn, Fnn, nn, nn);
     trsm_rlt<W>(Lb, nj, nn, Fnn, nn, nn);
-    trsm_llt<W>(Lb, nj, nn, Fnn, nn, nn);
-    trsm_rl<W>(Lb, nj, nn, Fnn, nn, nn);
+    if (!a.half) {
+        trsm_llt<W>(Lb, nj, nn, Fnn, nn, nn);
+        trsm_rl<W>(Lb, nj, nn, Fnn, nn, nn);
+    }
     if (na) {
-        // M_an = Y_aa K_an D^{-1}
+        // M_an = Y_aa K_an D^{-1}   (half factor G: R^T K_an L^{-T}, Y_aa = R R^T)
         trsm_rlt<W>(Lb, nj, nn, Fan, na, na);
-        trsm_rl<W>(Lb, nj, nn, Fan, na, na);
-        mm<W>(blk + nn, nj, na, nn, na, 1.0, Yaa, 1, na, Fan, 1, na, false, false);
+        if (!a.half) {
+            trsm_rl<W>(Lb, nj, nn, Fan, na, na);
+            mm<W>(blk + nn, nj, na, nn, na, 1.0, Yaa, 1, na, Fan, 1, na, false, false);
+        } else {
+            mm<W>(blk + nn, nj, na, nn, na, 1.0, a.Raa + q.uoff, na, 1, Fan, 1, na, false, false);
+        }
     }
     for (int idx = TID; idx < nn * nn; idx += NT) {
         int i = idx % nn, j = idx / nn;
@@ -475,10 +486,34 @@ __device__ void op_hfwd_up(const TreeArgs &a, const Node &q, int b, double *ws) 
 template <bool W>
 __device__ void op_hfwd_down(const TreeArgs &a, const Node &q, int b, double *ws) {
     const int nn = q.nn, na = q.na, nj = q.nj;
-    if (!na) return;
     const SymDev &S = a.S;
     double *Xb = a.X + (long long)b * S.nblk;
     double *blk = Xb + q.boff;
+    if (a.half) {
+        // G^adj: the adjoint of the half scaling on this supernode's own block, then pass 3:
+        // M_nn = L^{-T} V_nn L^{-1}, M_an = R V_an L^{-1}
+        const double *Lb = a.Lt + q.boff;
+        double *Vnn = ws;                 // nn x nn full
+        double *Van = Vnn + nn * nn;      // na x nn
+        for (int idx = TID; idx < nn * nn; idx += NT) {
+            int i = idx % nn, j = idx / nn;
+            Vnn[idx] = (i >= j) ? blk[i + (long long)j * nj] : blk[j + (long long)i * nj];
+        }
+        for (int idx = TID; idx < na * nn; idx += NT) Van[idx] = blk[nn + idx % na + (long long)(idx / na) * nj];
+        SYNC();
+        trsm_llt<W>(Lb, nj, nn, Vnn, nn, nn);
+        trsm_rl<W>(Lb, nj, nn, Vnn, nn, nn);
+        for (int idx = TID; idx < nn * nn; idx += NT) {
+            int i = idx % nn, j = idx / nn;
+            blk[i + (long long)j * nj] = (i >= j) ? 0.5 * (Vnn[idx] + Vnn[j + i * nn]) : 0.0;
+        }
+        if (na) {
+            trsm_rl<W>(Lb, nj, nn, Van, na, na);
+            mm<W>(blk + nn, nj, na, nn, na, 1.0, a.Raa + q.uoff, 1, na, Van, 1, na, false, false);
+        }
+        SYNC();
+    }
+    if (!na) return;
     const double *Ltan = a.Lt + q.boff + nn;
     double *Zaa = ws;                 // na x na
     double *Mold = Zaa + na * na;     // na x nn
@@ -539,36 +574,72 @@ __device__ void op_hinv(const TreeArgs &a, const Node &q, int b, double *ws) {
         int kmax = i < j ? i : j;
         double s = 0.0;
         for (int r = 0; r <= kmax; ++r) s = fma(Lb[i + (long long)r * nj], Lb[j + (long long)r * nj], s);
-        T4[idx] = s;
+        // half factors use L itself (lower triangular, full storage) instead of D = L L^T
+        T4[idx] = a.half ? ((i >= j) ? Lb[i + (long long)j * nj] : 0.0) : s;
     }
     SYNC();
-    // M_an = Z_an + Z_aa Lt
-    for (int idx = TID; idx < na * nn; idx += NT) {
-        int i = idx % na, c = idx / na;
-        double s = 0.0;
-        for (int r = 0; r < na; ++r) s = fma(T3[i + r * na], Ltan[r + (long long)c * nj], s);
-        T1[idx] = blk[nn + i + (long long)c * nj] + s;
-    }
-    SYNC();
-    // M_nn = Z_nn + Lt^T Z_an + M_an^T Lt
-    for (int idx = TID; idx < nn * nn; idx += NT) {
-        int i = idx % nn, j = idx / nn;
-        double s = (i >= j) ? blk[i + (long long)j * nj] : blk[j + (long long)i * nj];
-        for (int r = 0; r < na; ++r) {
-            s = fma(Ltan[r + (long long)i * nj], blk[nn + r + (long long)j * nj], s);
-            s = fma(T1[r + i * na], Ltan[r + (long long)j * nj], s);
+    if (a.half != 2) {
+        // M_an = Z_an + Z_aa Lt
+        for (int idx = TID; idx < na * nn; idx += NT) {
+            int i = idx % na, c = idx / na;
+            double s = 0.0;
+            for (int r = 0; r < na; ++r) s = fma(T3[i + r * na], Ltan[r + (long long)c * nj], s);
+            T1[idx] = blk[nn + i + (long long)c * nj] + s;
         }
-        T2[idx] = s;
+        SYNC();
+        // M_nn = Z_nn + Lt^T Z_an + M_an^T Lt
+        for (int idx = TID; idx < nn * nn; idx += NT) {
+            int i = idx % nn, j = idx / nn;
+            double s = (i >= j) ? blk[i + (long long)j * nj] : blk[j + (long long)i * nj];
+            for (int r = 0; r < na; ++r) {
+                s = fma(Ltan[r + (long long)i * nj], blk[nn + r + (long long)j * nj], s);
+                s = fma(T1[r + i * na], Ltan[r + (long long)j * nj], s);
+            }
+            T2[idx] = s;
+        }
+        SYNC();
+    } else {
+        // G^-1: the block itself is (V_nn, V_an)
+        for (int idx = TID; idx < na * nn; idx += NT) T1[idx] = blk[nn + idx % na + (long long)(idx / na) * nj];
+        for (int idx = TID; idx < nn * nn; idx += NT) {
+            int i = idx % nn, j = idx / nn;
+            T2[idx] = (i >= j) ? blk[i + (long long)j * nj] : blk[j + (long long)i * nj];
+        }
+        SYNC();
     }
-    SYNC();
-    // K_nn = D M_nn D
-    mm<W>(T5, nn, nn, nn, nn, 1.0, T4, 1, nn, T2, 1, nn, false, false);
-    mm<W>(T2, nn, nn, nn, nn, 1.0, T5, 1, nn, T4, 1, nn, false, false);
+    if (a.half == 1) {
+        // G^-adj: V_nn = L^T M_nn L, V_an = R^-1 M_an L; written to the block, nothing is passed up
+        mm<W>(T5, nn, nn, nn, nn, 1.0, T4, nn, 1, T2, 1, nn, false, false);       // L^T M
+        mm<W>(T2, nn, nn, nn, nn, 1.0, T5, 1, nn, T4, 1, nn, false, false);       // (L^T M) L
+        if (na) {
+            mm<W>(T6, na, na, nn, nn, 1.0, T1, 1, na, T4, 1, nn, false, false);   // M_an L
+            trsm_ll<W>(a.Raa + q.uoff, na, na, T6, na, nn);
+        }
+        for (int idx = TID; idx < nn * nn; idx += NT) {
+            int i = idx % nn, j = idx / nn;
+            blk[i + (long long)j * nj] = (i >= j) ? 0.5 * (T2[idx] + T2[j + i * nn]) : 0.0;
+        }
+        for (int idx = TID; idx < na * nn; idx += NT) blk[nn + idx % na + (long long)(idx / na) * nj] = T6[idx];
+        SYNC();
+        return;
+    }
+    // K_nn = D M_nn D   (G^-1: L V_nn L^T)
+    if (a.half == 2) {
+        mm<W>(T5, nn, nn, nn, nn, 1.0, T4, 1, nn, T2, 1, nn, false, false);       // L V
+        mm<W>(T2, nn, nn, nn, nn, 1.0, T5, 1, nn, T4, nn, 1, false, false);       // (L V) L^T
+    } else {
+        mm<W>(T5, nn, nn, nn, nn, 1.0, T4, 1, nn, T2, 1, nn, false, false);
+        mm<W>(T2, nn, nn, nn, nn, 1.0, T5, 1, nn, T4, 1, nn, false, false);
+    }
     if (na) {
-        // K_an = Y_aa^{-1} M_an D
-        mm<W>(T6, na, na, nn, nn, 1.0, T1, 1, na, T4, 1, nn, false, false);
+        // K_an = Y_aa^{-1} M_an D   (G^-1: R^-T V_an L^T)
         const double *R = a.Raa + q.uoff;
-        trsm_ll<W>(R, na, na, T6, na, nn);
+        if (a.half == 2) {
+            mm<W>(T6, na, na, nn, nn, 1.0, T1, 1, na, T4, nn, 1, false, false);   // V_an L^T
+        } else {
+            mm<W>(T6, na, na, nn, nn, 1.0, T1, 1, na, T4, 1, nn, false, false);
+            trsm_ll<W>(R, na, na, T6, na, nn);
+        }
         trsm_llt<W>(R, na, na, T6, na, nn);
         // F_an = K_an + Lt K_nn
         for (int idx = TID; idx < na * nn; idx += NT) {

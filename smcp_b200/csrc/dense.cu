@@ -341,6 +341,9 @@ int launch_gemm(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, c
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
+    // K-major operands with 16-byte aligned columns: operand tiles fetched by TMA (gemm_tma.cu)
+    if (ta && tb && gemm_tma_eligible(A, lda, B, ldb, M, N, K))
+        return launch_gemm_tma_tn(ctx, A, lda, B, ldb, C, ldc, M, N, K, alpha, accumulate, tri, tri_off, name);
     return launch_gemm_cyc(ctx, ta, tb, A, lda, B, ldb, C, ldc, M, N, K, alpha, accumulate, tri, tri_off, name, 0, 1, 1);
 }
 

@@ -206,6 +206,7 @@ int k_llt(smcp_sym *s, double *x, int64_t batch);
 int k_hess_prep(smcp_hess *h, const double *L, const double *Y);
 int k_hess_prep_inv(smcp_hess *h);
 int k_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv);
+int k_hess_apply_half(smcp_hess *h, double *U, int64_t batch, int inv, int adj);
 int k_trsm(smcp_sym *s, const double *L, double *B, int64_t ldb, int64_t nrhs, int trans);
 int k_axpy(smcp_sym *s, double a, const double *x, double *y, int64_t len);
 int k_scal(smcp_sym *s, double a, double *x, int64_t len);
@@ -247,6 +248,10 @@ bool potrf_tile_fits(const smcp_ctx *ctx, int64_t mm, int64_t npiv, bool panel_o
 int potrf_tile(smcp_ctx *ctx, double *H, int64_t ld, int64_t mm, int64_t npiv, bool panel_only, int32_t *info_dev, int col_off);
 bool trsm_slab_fits(int64_t n);
 int trsm_slab(smcp_ctx *ctx, bool trans, const double *L, int64_t ldl, int64_t n, double *B, int64_t ldb, int64_t nrhs);
+// TMA-fed DMMA GEMM for K-major operands (gemm_tma.cu)
+bool gemm_tma_eligible(const double *A, int64_t lda, const double *B, int64_t ldb, int64_t M, int64_t N, int64_t K);
+int launch_gemm_tma_tn(smcp_ctx *ctx, const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc,
+                       int64_t M, int64_t N, int64_t K, double alpha, int accumulate, int tri, int64_t tri_off, const char *name);
 // ncclBroadcast of `count` doubles in place on stream s (capi.cu)
 int comm_bcast(smcp_ctx *ctx, double *ptr, size_t count, int root, cudaStream_t s);
 int launch_gemm(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, const double *B, int64_t ldb, double *C,

@@ -46,6 +46,7 @@ API = {
     "smcp_prof_reset": (_int, [_vp]),
     "smcp_region_get": (_int, [_vp, C.c_char_p, C.POINTER(_dbl), C.POINTER(_i64)]),
     "smcp_region_reset": (_int, [_vp]),
+    "smcp_region_list": (_int, [_vp, C.c_char_p, _i64]),
     "smcp_flush_l2": (_int, [_vp]),
     "smcp_sym_create": (_int, [_vp, C.POINTER(SymDesc), C.POINTER(_vp)]),
     "smcp_sym_destroy": (_int, [_vp]),
@@ -70,6 +71,7 @@ API = {
     "smcp_hess_create": (_int, [_vp, _dp, _dp, C.POINTER(_vp)]),
     "smcp_hess_destroy": (_int, [_vp]),
     "smcp_hess_apply": (_int, [_vp, _dp, _i64, _int]),
+    "smcp_hess_apply_half": (_int, [_vp, _dp, _i64, _int, _int]),
     "smcp_op_create": (_int, [_vp, _i64, _i64, _i64p, _i64p, _f64p, C.POINTER(_vp)]),
     "smcp_op_destroy": (_int, [_vp]),
     "smcp_op_set_entry_coords": (_int, [_vp, _i64p, _i64p]),
@@ -209,6 +211,12 @@ class Context:
         ms, n = C.c_double(), C.c_int64()
         _ck(self.lib, self.lib.smcp_region_get(self.h, name.encode(), C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def region_names(self):
+        buf = C.create_string_buffer(8192)
+        _ck(self.lib, self.lib.smcp_region_list(self.h, buf, 8192))
+        s = buf.value.decode()
+        return s.split(",") if s else []
 
     def region_reset(self):
         _ck(self.lib, self.lib.smcp_region_reset(self.h))
@@ -476,9 +484,12 @@ class DeviceBackend:
         self._tok = h
         return h
 
-    def hessian_apply(self, tok, bufs, inv):
+    def hessian_apply(self, tok, bufs, inv, adj=None):
         for b in bufs:
-            _ck(self.lib, self.lib.smcp_hess_apply(tok, b, 1, int(bool(inv))))
+            if adj is None:
+                _ck(self.lib, self.lib.smcp_hess_apply(tok, b, 1, int(bool(inv))))
+            else:
+                _ck(self.lib, self.lib.smcp_hess_apply_half(tok, b, 1, int(bool(inv)), int(bool(adj))))
 
     # -- operator ---------------------------------------------------------------------
     def set_operator(self, Av, Ns):

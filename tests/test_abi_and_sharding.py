@@ -68,9 +68,18 @@ def test_block_cyclic_ownership(m, nranks, block):
 
 
 _WORKER = r"""
+# One process per rank (gloo): the host-side logic of the N > 1 path on the CPU oracle.
+#  1. every rank assembles ONLY the column blocks of H it owns (1-D block-cyclic, like
+#     smcp_kkt_assemble_cyclic): dense-technique and sparse-technique columns;
+#  2. the blocks are factored with the schedule of d_potrf (csrc/dense.cu): the owner of block q
+#     factors its panel and broadcasts it, every rank applies it to the blocks it owns;
+#  3. every rank must end with the factor of the H a single process assembles -- and the exchange
+#     of the UNFACTORED blocks (smcp_kkt_allgather) must reproduce that H bit for bit.
 import os, sys
 sys.path.insert(0, %(root)r)
 import numpy as np
+import scipy.linalg as sl
+import scipy.sparse as sp
 import torch, torch.distributed as dist
 from smcp_b200.device import owned_column_blocks
 from smcp_b200 import solvers
@@ -81,26 +90,57 @@ rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
 solvers.options["show_progress"] = False
 solvers.set_backend_factory(lambda symb: OracleBackend(symb, batch_columns=8))
-P = S.band_SDP(30, 21, 2, seed=3)
-pr = _Problem(P.A, P.b, _read_options(P.n, False), "chol", None)
-ob, symb, m = pr.ops, pr.symb, pr.m
-s = np.zeros(symb.nvp); s[symb.diag_vec] = 2.0
-s += 0.05 * np.random.default_rng(0).standard_normal(symb.nvp)
-L = ob.from_vec(s); ob.cholesky(L); Y = ob.clone(L); ob.projected_inverse(Y)
-hf = ob.hessian_factor(L, Y)
-Hfull = np.tril(ob.schur_assemble(hf)).copy()
-# sharded: this rank keeps only its own column blocks, then the blocks are exchanged exactly
-# like smcp_kkt_allgather does (owner broadcasts whole columns)
-block = 4
-Hloc = np.zeros((m, m))
-for c0, c1 in owned_column_blocks(m, rank, world, block):
-    Hloc[:, c0:c1] = Hfull[:, c0:c1]
-for q, c0 in enumerate(range(0, m, block)):
-    c1 = min(m, c0 + block)
-    t = torch.from_numpy(np.ascontiguousarray(Hloc[:, c0:c1]))
-    dist.broadcast(t, src=q %% world)
-    Hloc[:, c0:c1] = t.numpy()
-assert np.array_equal(Hloc, Hfull), "sharded exchange does not reproduce H"
+rng = np.random.default_rng(7)
+e = rng.integers(0, 40, size=(50, 2))
+V = sp.coo_matrix((np.ones(50 + 40), (np.concatenate([e[:, 0], np.arange(40)]), np.concatenate([e[:, 1], np.arange(40)]))), shape=(40, 40))
+cases = [("band-dense", S.band_SDP(30, 21, 2, seed=3), 4), ("rand-sparse", S.rand_SDP(V, 23, density=0.04, seed=4), 3)]
+for name, P, block in cases:
+    pr = _Problem(P.A, P.b, _read_options(P.n, False), "chol", None)
+    ob, symb, m = pr.ops, pr.symb, pr.m
+    s = np.zeros(symb.nvp); s[symb.diag_vec] = 2.0
+    s += 0.05 * np.random.default_rng(0).standard_normal(symb.nvp)
+    L = ob.from_vec(s); ob.cholesky(L); Y = ob.clone(L); ob.projected_inverse(Y)
+    hf = ob.hessian_factor(L, Y)
+    mine = owned_column_blocks(m, rank, world, block)
+    cols0 = ob.stats["hessian_cols"]
+    Hloc = np.tril(ob.schur_assemble(hf, columns=mine)).copy()          # this rank's blocks only
+    done = ob.stats["hessian_cols"] - cols0
+    assert done == sum(min(c1, m - pr.Ns) - min(c0, m - pr.Ns) for c0, c1 in mine), (name, "assembled foreign columns")
+    for c0, c1 in owned_column_blocks(m, (rank + 1) %% world, world, block):
+        assert not Hloc[:, c0:c1].any(), (name, "foreign block is not empty")
+    Href = np.tril(ob.schur_assemble(hf)).copy()                          # single-process reference
+    # (3) exchange of the unfactored blocks
+    Hx = Hloc.copy()
+    for q, c0 in enumerate(range(0, m, block)):
+        c1 = min(m, c0 + block)
+        t = torch.from_numpy(np.ascontiguousarray(Hx[:, c0:c1]))
+        dist.broadcast(t, src=q %% world)
+        Hx[:, c0:c1] = t.numpy()
+    assert np.array_equal(Hx, Href), (name, "sharded assembly + exchange does not reproduce H")
+    # (2) block-cyclic right-looking Cholesky with panel broadcasts
+    Hd = Hloc.copy()
+    nb = (m + block - 1) // block
+    for q in range(nb):
+        c0, c1 = q * block, min(m, (q + 1) * block)
+        if q %% world == rank:
+            Hd[c0:c1, c0:c1] = np.linalg.cholesky(Hd[c0:c1, c0:c1] + np.tril(Hd[c0:c1, c0:c1], -1).T)
+            if c1 < m:
+                Hd[c1:, c0:c1] = sl.solve_triangular(Hd[c0:c1, c0:c1], Hd[c1:, c0:c1].T, lower=True).T
+        t = torch.from_numpy(np.ascontiguousarray(Hd[:, c0:c1]))
+        dist.broadcast(t, src=q %% world)
+        Hd[:, c0:c1] = t.numpy()
+        for q2 in range(q + 1, nb):
+            if q2 %% world != rank:
+                continue
+            d0, d1 = q2 * block, min(m, (q2 + 1) * block)
+            Hd[d0:, d0:d1] -= Hd[d0:, c0:c1] @ Hd[d0:d1, c0:c1].T
+    Lref = np.linalg.cholesky(Href + np.tril(Href, -1).T)
+    assert np.linalg.norm(np.tril(Hd) - Lref) <= 1e-12 * np.linalg.norm(Lref), (name, "distributed factor differs")
+    # every rank holds the same factor bit for bit
+    t = torch.from_numpy(np.ascontiguousarray(np.tril(Hd)))
+    t0 = t.clone()
+    dist.broadcast(t0, src=0)
+    assert torch.equal(t, t0), (name, "ranks disagree on the factor")
 dist.barrier()
 if rank == 0:
     print("OK")

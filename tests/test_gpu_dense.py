@@ -125,7 +125,9 @@ def test_trsm(n, nrhs, trans):
 @pytest.mark.parametrize("M,N,K,tri", [(300, 300, 4000, 1), (257, 130, 64, 0), (1000, 1000, 512, 1), (128, 128, 8, 1), (90, 700, 33, 0),
                                        # N <= 16 with K > 16: matrix times a few vectors (gemm_thin_kernel); K <= 16: rank-k kernel
                                        (1131, 1, 1131, 0), (700, 9, 300, 0), (5, 16, 1000, 0), (40, 3, 17, 0), (1131, 1131, 1, 1),
-                                       (333, 200, 16, 0)])
+                                       (333, 200, 16, 0),
+                                       # K-major operands (ta = tb = 1) with even leading dimensions: TMA-fed kernel, with split-K
+                                       (1000, 1000, 30000, 1), (77, 513, 2050, 0), (130, 257, 1001, 0), (129, 129, 256, 1)])
 def test_gemm(ta, tb, M, N, K, tri):
     from smcp_b200.device import _ck
     ctx = _ctx()
