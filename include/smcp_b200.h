@@ -160,6 +160,14 @@ int smcp_op_aadj(smcp_op *op, const double *host_y, double *X);
 int smcp_kkt_assemble(smcp_op *op, smcp_hess *h, int64_t j0, int64_t j1);
 /* multi-GPU: assemble the column blocks q = rank (mod nranks) of `block` columns as one batch */
 int smcp_kkt_assemble_cyclic(smcp_op *op, smcp_hess *h, int64_t block, int rank, int nranks);
+/* kktsolver='qr' (solvers.py:413-475, 1843-1904) in SYRK form: Z = [G(A_1) ... G(A_m)] with the half factor
+ * G of the Hessian, H = Z^T Z in the trace inner product by one triangular DMMA product (then smcp_kkt_factor /
+ * smcp_kkt_solve as usual); z_tmul: out[j] = <G(A_j), X>; z_mul: X = sum_j y[j] G(A_j).  Needs Ns = 0.
+ * h = NULL takes G = identity: H is then the Gram matrix <A_i, A_j> of the constraints, whose Cholesky solve
+ * gives the least-norm start of SDP.solve_phase1 (base.py:383-396: syrk + CHOLMOD in the reference). */
+int smcp_kkt_assemble_syrk(smcp_op *op, smcp_hess *h);
+int smcp_kkt_z_tmul(smcp_op *op, const double *X_dev, double *host_out);
+int smcp_kkt_z_mul(smcp_op *op, const double *host_y, double *X_dev);
 /* lapack.potrf(H): info_host = 0 ok, k > 0 if the leading minor of order k is not PD        */
 int smcp_kkt_factor(smcp_op *op, int32_t *info_host);
 /* lapack.potrs(H, y) in place on a host m-vector */

@@ -173,6 +173,38 @@ class OracleBackend:
         if not np.all(np.isfinite(self.Hf)):
             raise ArithmeticError("Schur complement is not positive definite")
 
+    # -- kktsolver='qr' (solvers.py:413-475): Z = [G(A_1) ... G(A_m)], Householder QR like the reference
+    def schur_factor_qr(self, hf):
+        symb, Av, m = self.symb, self.Av, self.m
+        Z = np.zeros((m, symb.nblk))
+        for j in range(m):
+            c0, c1 = Av.indptr[j], Av.indptr[j + 1]
+            Z[j, symb.vec2blk[Av.indices[c0:c1]]] = Av.data[c0:c1]
+        sn.hessian_half(hf, Z, False, False)
+        self.Zw = (Z * np.sqrt(symb.wdot)[None, :]).T.copy()          # nblk x m, weighted: Z^T Z = trace inner products
+        R = np.linalg.qr(self.Zw, mode="r")
+        d = np.abs(np.diag(R))
+        if not np.all(np.isfinite(R)) or d.min() <= 1e-14 * d.max():
+            raise ArithmeticError("Z is rank deficient")
+        Ru = R * np.sign(np.diag(R))[:, None]
+        self.Hf = np.ascontiguousarray(Ru.T)                            # lower factor of Z^T Z
+        self.H = None
+
+    def gram_factor(self):
+        G = 2.0 * (self.AvT @ sp.diags(self.halfdiag) @ self.Av).toarray()      # <A_i, A_j>, trace inner product
+        try:
+            self.Hf = sl.cholesky(G, lower=True, check_finite=False)
+        except sl.LinAlgError:
+            raise ArithmeticError("the constraint matrices are linearly dependent")
+
+    def z_tmul(self, buf):
+        return self.Zw.T @ (buf * np.sqrt(self.symb.wdot))
+
+    def z_mul(self, y):
+        w = np.sqrt(self.symb.wdot)
+        out = self.Zw @ np.asarray(y, dtype=np.float64).ravel()
+        return np.divide(out, w, out=np.zeros_like(out), where=w > 0)
+
     def schur_solve(self, y):
         return sl.cho_solve((self.Hf, True), np.asarray(y, dtype=np.float64).ravel(),
                             check_finite=False)

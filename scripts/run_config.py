@@ -72,7 +72,7 @@ def hook(name, it):
 solvers._iteration_hook = hook
 # pass 1: wall clock per iteration, no per-launch timing (launches overlap with the host)
 t0 = time.time()
-sol = getattr(P, "solve_" + method)(kktsolver="chol", **kw)
+sol = getattr(P, "solve_" + method)(kktsolver=os.environ.get("RUNCFG_KKT", "chol"), **kw)
 print("solve_%s: status %s, %d iterations, %.2f s total (incl. setup)" % (method, sol["status"], sol["iterations"], time.time() - t0))
 its = sorted(stamps)
 if full:
@@ -94,7 +94,7 @@ if os.environ.get("RUNCFG_NOPROF"):
 stamps.clear()
 ctx.prof_reset()
 ctx.prof_enable(True)
-sol = getattr(P, "solve_" + method)(kktsolver="chol", **kw)
+sol = getattr(P, "solve_" + method)(kktsolver=os.environ.get("RUNCFG_KKT", "chol"), **kw)
 ctx.prof_enable(False)
 rows = []
 for nm in ctx.prof_names():

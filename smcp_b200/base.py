@@ -194,44 +194,39 @@ class SDP(object):
 
     def solve_phase1(self, kktsolver="chol", MM=1e5):
         """Primal Phase I with the feasible-start solver; returns ``(X0, sol)`` with a primal
-        feasible ``X0`` (``base.py:370-470``).  The least-norm start (a sparse normal-equations
-        solve, CHOLMOD in the reference) is once-per-solve host work done with SciPy."""
+        feasible ``X0`` (``base.py:370-470``).  The least-norm start (``base.py:383-396``: sparse
+        ``syrk`` + CHOLMOD in the reference) runs on the backend: Gram matrix of the constraints by one
+        triangular product, dense Cholesky, ``A^adj``."""
         from .chordal import cspmatrix, completion
         n, m = self.n, self.m
         k = 1e-3
         A = self._need()
         Id = np.arange(n, dtype=np.int64) * (n + 1)
-        As = A[:, 1:].tocsc().copy()
-        scale = np.ones(A.shape[0])
-        scale[Id] = 1.0 / np.sqrt(2.0)
-        As = (sp.diags(scale) @ As).tocsc()
-        # least-norm start: (As^T As) u = b.  Dense constraint matrices (mtxnorm: every A_i fills the
-        # same 40 400 rows) go through BLAS on the non-empty rows; sparse ones through SciPy's solver
-        rows = np.unique(As.indices)
-        if As.nnz > 0.2 * len(rows) * max(1, m) and len(rows) * m * 8 <= (2 << 30):
-            D = np.asarray(As[rows, :].todense())
-            u = np.linalg.solve(D.T @ D, self.b)
+        # least-norm start X0 = sum_j u_j A_j with G u = b, G_ij = <A_i, A_j> (base.py:383-396: the reference
+        # forms As^T As with syrk and solves with CHOLMOD).  On the backend: G as ONE triangular product of
+        # the constraint vectors (DMMA / TMA on the device), the dense Cholesky of the Schur complement, and
+        # A^adj for the combination -- on the same embedding the completability test below needs.
+        opt = solvers._read_options(n, True)
+        prob = solvers._Problem(A, self.b, opt, "qr", None)          # 'qr': no constraint reordering (Ns = 0)
+        ops, symb, pm = prob.ops, prob.symb, prob.p
+        dense_bytes = 8.0 * symb.nblk * m
+        if dense_bytes <= (16 << 30):
+            ops.gram_factor()
+            u = ops.schur_solve(prob.b)
+            Xc = prob.Aadj(u)
+            X0 = sp.tril(prob.to_original(Xc), format="csc")
+            X0.eliminate_zeros()
         else:
-            M = (As.T @ As).tocsc()
-            u = spla.spsolve(M, self.b)
-        x = 0.5 * (A[:, 1:] @ u)
-        I, J = misc.ind2sub(n, self.I)
-        X0 = sp.csc_matrix((x[self.I], (I, J)), shape=(n, n))
-
-        # completability test on the embedding of V (base.py:398-412)
-        keep = I >= J
-        cp, ri = lower_pattern(n, I[keep], J[keep])
-        pm = maxcardsearch(n, cp, ri)
-        fc, fr, _ = embed(n, cp, ri, pm)
-        if fc[-1] != cp[-1]:
-            pm = min_degree(n, cp, ri)
-            fc, fr, _ = embed(n, cp, ri, pm)
-        symb = Symbolic(n, fc, fr)
-        ops = solvers._make_backend(symb)
-        lo = sp.tril(X0, format="csc")
-        full = (lo + sp.tril(lo, -1).T).tocsr()
-        xv = np.asarray(full[pm[symb.Ip], pm[symb.Jp]]).ravel()
-        Xc = cspmatrix.from_vec(ops, xv)
+            # constraint vectors too large for the dense product: sparse normal equations on the host
+            As = A[:, 1:].tocsc().copy()
+            scale = np.ones(A.shape[0])
+            scale[Id] = 1.0 / np.sqrt(2.0)
+            As = (sp.diags(scale) @ As).tocsc()
+            u = spla.spsolve((As.T @ As).tocsc(), self.b)
+            x = 0.5 * (A[:, 1:] @ u)
+            I, J = misc.ind2sub(n, self.I)
+            X0 = sp.csc_matrix((x[self.I], (I, J)), shape=(n, n))
+            Xc = prob.from_original(X0)
 
         def completable(Z):
             L = Z.copy()

@@ -267,6 +267,8 @@ int big_setup(smcp_sym *s, const smcp_sym_desc *D) {
         b.nch = (int)(D->chptr[k + 1] - D->chptr[k]);
         b.boff = D->blkptr[k];
         b.uoff = D->updptr[k];
+        b.rowoff = D->rowptr[k];
+        b.r0 = (int)D->rowidx[D->rowptr[k]];
         b.inv_off = (long long)io;
         b.ch_off = (long long)co;
         for (int q = 0; q < b.nch; ++q) {
@@ -518,6 +520,53 @@ int big_completion(smcp_sym *s, const BigNode &q, double *X, const double *Xin, 
     if (d_trsm_left_lower(ctx, false, M, nn, nn, Li, nn, nn)) return -1;                            // L_nn = M^-1
     ELEM(big_copy_mat_kernel, (long long)nn * nn, Li, nn, bout, nj, nn, nn, 1);
     if (na && G(s, false, true, Z, na, Li, nn, bout + nn, nj, na, nn, nn, -1.0, 0)) return -1;      // L_an = -W L_nn
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ---- chordal trsm with many right-hand sides: one supernode of the top set ------------------------
+// forward : B_nu <- L_nn^-1 B_nu ; B_alpha -= L_an B_nu          (rows alpha scattered: rowidx)
+// backward: B_nu -= L_an^T B_alpha ; B_nu <- L_nn^-T B_nu
+__global__ void big_rows_gather_kernel(const double *__restrict__ B, long long ldb, const int *__restrict__ rows, int na, long long nrhs,
+                                       double *__restrict__ G) {
+    BIG_LOOP((long long)na * nrhs) {
+        const int i = (int)(idx % na);
+        const long long c = idx / na;
+        G[idx] = B[rows[i] + c * ldb];
+    }
+}
+__global__ void big_rows_sub_kernel(double *__restrict__ B, long long ldb, const int *__restrict__ rows, int na, long long nrhs,
+                                    const double *__restrict__ T) {
+    BIG_LOOP((long long)na * nrhs) {
+        const int i = (int)(idx % na);
+        const long long c = idx / na;
+        B[rows[i] + c * ldb] -= T[idx];
+    }
+}
+
+int big_trsm_node(smcp_sym *s, const BigNode &q, const double *L, double *B, int64_t ldb, int64_t nrhs, int trans) {
+    smcp_ctx *ctx = s->ctx;
+    const int nn = q.nn, na = q.na, nj = q.nj;
+    const double *blk = L + q.boff;
+    const int r0 = q.r0;                                  // first row of the supernode (its columns are contiguous)
+    const int *rows = s->d.rowidx + q.rowoff + nn;        // the separator rows
+    if (na && grow((void **)&s->big_cat, &s->big_cat_cap, (size_t)na * nrhs * sizeof(double))) return -1;
+    double *T = s->big_cat;
+    if (!trans) {
+        if (d_trsm_left_lower(ctx, false, blk, nj, nn, B + r0, ldb, nrhs)) return -1;
+        if (na) {
+            // T(i, c) = sum_k L_an(i, k) B_nu(k, c)
+            if (launch_gemm(ctx, false, true, blk + nn, nj, B + r0, ldb, T, na, na, nrhs, nn, 1.0, 0, 0, 0, "front_gemm_dmma")) return -1;
+            ELEM(big_rows_sub_kernel, (long long)na * nrhs, B, ldb, rows, na, nrhs, T);
+        }
+    } else {
+        if (na) {
+            ELEM(big_rows_gather_kernel, (long long)na * nrhs, B, ldb, rows, na, nrhs, T);
+            // B_nu(i, c) -= sum_k L_an(k, i) B_alpha(k, c)
+            if (launch_gemm(ctx, true, true, blk + nn, nj, T, na, B + r0, ldb, nn, nrhs, na, -1.0, 1, 0, 0, "front_gemm_dmma")) return -1;
+        }
+        if (d_trsm_left_lower(ctx, true, blk, nj, nn, B + r0, ldb, nrhs)) return -1;
+    }
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

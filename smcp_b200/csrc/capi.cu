@@ -149,6 +149,7 @@ extern "C" int smcp_ctx_destroy(smcp_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);
+    if (ctx->gridbar) cudaFree(ctx->gridbar);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
@@ -513,6 +514,8 @@ struct smcp_op {
     double *Ub = nullptr;
     size_t Ub_cap = 0;
     double *Zinv = nullptr;       // n x n dense inverse for the sparse-constraint technique
+    double *Zq = nullptr;         // kktsolver='qr': Z = [G(A_1) ... G(A_m)] weighted by sqrt(wdot), nblk x m
+    double *sqrtw = nullptr;      // sqrt of the trace inner-product weights (nblk)
     double *Dinv = nullptr;       // inverses of the 64 x 64 diagonal blocks of chol(H) (potrs)
     std::vector<long long> h_colptr;
     void *allocs[16] = {0};
@@ -690,6 +693,8 @@ extern "C" int smcp_op_destroy(smcp_op *op) {
     if (op->AvW) cudaFree(op->AvW);
     if (op->Ub) cudaFree(op->Ub);
     if (op->Zinv) cudaFree(op->Zinv);
+    if (op->Zq) cudaFree(op->Zq);
+    if (op->sqrtw) cudaFree(op->sqrtw);
     if (op->Dinv) cudaFree(op->Dinv);
     cudaFree(op->H); cudaFree(op->info_dev); cudaFree(op->yv);
     delete op;
@@ -959,11 +964,132 @@ extern "C" int smcp_kkt_assemble_cyclic(smcp_op *op, smcp_hess *h, int64_t block
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// kktsolver='qr' in SYRK form (solvers.py:413-475): Z = [G(A_1) ... G(A_m)] with the
+// half factor G of the Hessian, H = Z^T Z (trace inner product) by one triangular DMMA product.
+// ---------------------------------------------------------------------------------------
+__global__ void sqrtw_kernel(const double *__restrict__ w, double *__restrict__ out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = sqrt(w[i]);
+}
+// Z[r + j*nblk] *= sw[r]  (mode 0);  x[r] = sw[r] > 0 ? x[r] / sw[r] : 0 (mode 1, one column);  x[r] *= sw[r] (mode 2)
+__global__ void rowscale_kernel(double *__restrict__ Z, const double *__restrict__ sw, long long nblk, long long ncols, int mode) {
+    const long long total = nblk * ncols;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const double s = sw[idx % nblk];
+        if (mode == 1) Z[idx] = s > 0.0 ? Z[idx] / s : 0.0;
+        else Z[idx] *= s;
+    }
+}
+// x[r] = sum_j Z[r + j*nblk] y[j]: thread per row, coalesced over rows, y staged in shared memory
+__global__ void __launch_bounds__(256) zmul_kernel(const double *__restrict__ Z, long long nblk, long long m, const double *__restrict__ y,
+                                                   double *__restrict__ x) {
+    __shared__ double ys[256];
+    const long long r = (long long)blockIdx.x * 256 + threadIdx.x;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (long long j0 = 0; j0 < m; j0 += 256) {
+        __syncthreads();
+        if (j0 + threadIdx.x < m) ys[threadIdx.x] = y[j0 + threadIdx.x];
+        __syncthreads();
+        const int nj = (int)min((long long)256, m - j0);
+        if (r < nblk) {
+            const double *z = Z + r + j0 * nblk;
+            int j = 0;
+            for (; j + 3 < nj; j += 4) {
+                s0 = fma(z[(long long)j * nblk], ys[j], s0);
+                s1 = fma(z[(long long)(j + 1) * nblk], ys[j + 1], s1);
+                s2 = fma(z[(long long)(j + 2) * nblk], ys[j + 2], s2);
+                s3 = fma(z[(long long)(j + 3) * nblk], ys[j + 3], s3);
+            }
+            for (; j < nj; ++j) s0 = fma(z[(long long)j * nblk], ys[j], s0);
+        }
+    }
+    if (r < nblk) x[r] = (s0 + s1) + (s2 + s3);
+}
+
+extern "C" int smcp_kkt_assemble_syrk(smcp_op *op, smcp_hess *h) {
+    smcp_sym *s = op->sym;
+    smcp_ctx *ctx = s->ctx;
+    RegionScope rs(ctx, "kkt_assemble");
+    const int64_t m = op->m;
+    const long long nblk = s->d.nblk;
+    if (op->Ns) { smcp_set_error("smcp_kkt_assemble_syrk: the sparse-constraint technique does not apply (Ns must be 0)"); return -2; }
+    const size_t bytes = (size_t)nblk * (size_t)m * sizeof(double);
+    if (bytes > ((size_t)96 << 30)) { smcp_set_error("kktsolver='qr' needs m*|blkval| doubles (%.1f GB)", bytes / 1073741824.0); return -2; }
+    if (!op->Zq) CUDA_TRY(cudaMalloc(&op->Zq, bytes ? bytes : 8));
+    if (!op->sqrtw) {
+        CUDA_TRY(cudaMalloc(&op->sqrtw, (size_t)nblk * sizeof(double)));
+        sqrtw_kernel<<<(unsigned)((nblk + 255) / 256), 256, 0, ctx->stream>>>(s->d.wdot, op->sqrtw, nblk);
+    }
+    CUDA_TRY(cudaMemsetAsync(op->Zq, 0, bytes, ctx->stream));
+    {
+        LaunchScope ls(ctx, "scatter_cols");
+        scatter_cols_kernel<<<(unsigned)m, 128, 0, ctx->stream>>>(op->colptr, op->rowblk, op->vals, op->Zq, nblk, 0, (int)m);
+    }
+    if (h) {
+        // G on all columns, in chunks that keep the update-matrix workspace (chunk x nupd doubles) below 4 GB
+        const size_t per = ((size_t)s->d.nupd + 1) * sizeof(double);
+        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(m, (int64_t)(((size_t)4 << 30) / per)));
+        for (int64_t c0 = 0; c0 < m; c0 += chunk)
+            if (k_hess_apply_half(h, op->Zq + (size_t)c0 * nblk, std::min(chunk, m - c0), 0, 0)) return -1;
+    }
+    {
+        LaunchScope ls(ctx, "level1");
+        rowscale_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(op->Zq, op->sqrtw, nblk, m, 0);
+    }
+    if (launch_gemm(ctx, true, true, op->Zq, nblk, op->Zq, nblk, op->H, m, m, m, nblk, 1.0, 0, 1, 0, "schur_syrk_dmma")) return -1;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// out[j] = <G(A_j), X> in the trace inner product  (X: a chordal matrix on the device)
+extern "C" int smcp_kkt_z_tmul(smcp_op *op, const double *X, double *host_out) {
+    smcp_sym *s = op->sym;
+    smcp_ctx *ctx = s->ctx;
+    if (!op->Zq) { smcp_set_error("smcp_kkt_z_tmul: no SYRK-form assembly yet"); return -2; }
+    const long long nblk = s->d.nblk;
+    if (grow((void **)&s->tmp, &s->tmp_cap, (size_t)nblk * sizeof(double))) return -1;
+    CUDA_TRY(cudaMemcpyAsync(s->tmp, X, (size_t)nblk * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    {
+        LaunchScope ls(ctx, "level1");
+        rowscale_kernel<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(s->tmp, op->sqrtw, nblk, 1, 2);
+    }
+    {
+        LaunchScope ls(ctx, "amap_dense", 1, 8.0 * (double)nblk * (double)op->m);
+        amap_dense_kernel<<<(unsigned)op->m, 256, 0, ctx->stream>>>(op->Zq, nblk, s->tmp, op->yv, 0);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(host_out, op->yv, (size_t)op->m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// X = sum_j y_j G(A_j)
+extern "C" int smcp_kkt_z_mul(smcp_op *op, const double *host_y, double *X) {
+    smcp_sym *s = op->sym;
+    smcp_ctx *ctx = s->ctx;
+    if (!op->Zq) { smcp_set_error("smcp_kkt_z_mul: no SYRK-form assembly yet"); return -2; }
+    const long long nblk = s->d.nblk;
+    CUDA_TRY(cudaMemcpyAsync(op->yv, host_y, (size_t)op->m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        LaunchScope ls(ctx, "aadj", 1, 8.0 * (double)nblk * (double)op->m);
+        zmul_kernel<<<(unsigned)((nblk + 255) / 256), 256, 0, ctx->stream>>>(op->Zq, nblk, op->m, op->yv, X);
+    }
+    {
+        LaunchScope ls(ctx, "level1");
+        rowscale_kernel<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(X, op->sqrtw, nblk, 1, 1);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));       // host_y may be reused by the caller
+    return 0;
+}
+
 extern "C" int smcp_kkt_factor(smcp_op *op, int32_t *info_host) {
     smcp_ctx *ctx = op->sym->ctx;
     {
         RegionScope rs(ctx, "kkt_factor");
         if (d_potrf(ctx, op->H, op->m, op->m, op->m, op->info_dev, 0, 1)) return -1;
+        if (potrs_cluster_enabled() && d_potrs_prepare(ctx, op->H, op->m, op->Dinv)) return -1;
     }
     CUDA_TRY(cudaMemcpyAsync(info_host, op->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -981,6 +1107,7 @@ extern "C" int smcp_kkt_factor_dist(smcp_op *op, int rank, int nranks, int32_t *
     {
         RegionScope rs(ctx, "kkt_factor");
         if (d_potrf(ctx, op->H, op->m, op->m, op->m, op->info_dev, rank, nranks)) return -1;
+        if (potrs_cluster_enabled() && d_potrs_prepare(ctx, op->H, op->m, op->Dinv)) return -1;
     }
     CUDA_TRY(cudaMemcpyAsync(info_host, op->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -996,6 +1123,7 @@ extern "C" int smcp_kkt_factor_block(smcp_op *op, int64_t block, int rank, int n
     {
         RegionScope rs(ctx, "kkt_factor");
         if (d_potrf(ctx, op->H, op->m, op->m, op->m, op->info_dev, rank, nranks, block)) return -1;
+        if (potrs_cluster_enabled() && d_potrs_prepare(ctx, op->H, op->m, op->Dinv)) return -1;
     }
     CUDA_TRY(cudaMemcpyAsync(info_host, op->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1088,7 +1216,7 @@ extern "C" int smcp_kkt_solve(smcp_op *op, double *host_y) {
     CUDA_TRY(cudaMemcpyAsync(op->yv, host_y, (size_t)op->m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     {
         RegionScope rs(ctx, "kkt_solve");
-        if (d_potrs(ctx, op->H, op->m, op->yv)) return -1;
+        if (potrs_cluster_enabled() ? d_potrs_cluster(ctx, op->H, op->m, op->Dinv, op->yv) : d_potrs(ctx, op->H, op->m, op->yv)) return -1;
     }
     CUDA_TRY(cudaMemcpyAsync(host_y, op->yv, (size_t)op->m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));

@@ -23,6 +23,7 @@
 #include "internal.cuh"
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 
 #include "chordal_ops.cuh"
 
@@ -345,13 +346,27 @@ int k_hess_apply_half(smcp_hess *h, double *U, int64_t batch, int inv, int adj) 
 // chordal trsm: B <- L^{-1} B / L^{-T} B, B dense n x nrhs (rows in internal order)
 // One CTA per block of right-hand sides walks the whole tree (columns are independent).
 // ---------------------------------------------------------------------------------------
-__global__ void trsm_kernel(SymDev S, const double *L, double *B, long long ldb, int nrhs, int trans, int cols_per_cta) {
+__global__ void trsm_kernel(SymDev S, const double *L, double *B, long long ldb, int nrhs, int trans, int cols_per_cta, const int *skipflag,
+                            int use_smem) {
     int c0 = blockIdx.x * cols_per_cta;
     int nc = min(cols_per_cta, nrhs - c0);
     if (nc <= 0) return;
-    double *Bc = B + (long long)c0 * ldb;
+    // the block of right-hand sides lives in shared memory for the whole sweep when it fits: the
+    // separator rows of a supernode are scattered, and read-modify-write round trips to L2 per supernode
+    // made this kernel a latency chain (14 ms per sweep on the n = 2000 rand_SDP pattern)
+    extern __shared__ double trsm_sm[];
+    double *Bg = B + (long long)c0 * ldb;
+    double *Bc = Bg;
+    const long long ldg = ldb;
+    if (use_smem) {
+        for (long long idx = TID; idx < (long long)S.n * nc; idx += NT) trsm_sm[idx] = Bg[idx % S.n + (idx / S.n) * ldg];
+        __syncthreads();
+        Bc = trsm_sm;
+        ldb = S.n;
+    }
     if (!trans) {
         for (int k = 0; k < S.nsn; ++k) {
+            if (skipflag && skipflag[k]) continue;       // top set: dense kernels (big_trsm_node)
             int nn = S.nn[k], na = S.na[k], nj = nn + na;
             const double *blk = L + S.blkptr[k];
             const int *rows = S.rowidx + S.rowptr[k];
@@ -379,6 +394,7 @@ __global__ void trsm_kernel(SymDev S, const double *L, double *B, long long ldb,
         }
     } else {
         for (int k = S.nsn - 1; k >= 0; --k) {
+            if (skipflag && skipflag[k]) continue;
             int nn = S.nn[k], na = S.na[k], nj = nn + na;
             const double *blk = L + S.blkptr[k];
             const int *rows = S.rowidx + S.rowptr[k];
@@ -403,18 +419,52 @@ __global__ void trsm_kernel(SymDev S, const double *L, double *B, long long ldb,
             }
         }
     }
+    if (use_smem) {
+        __syncthreads();
+        for (long long idx = TID; idx < (long long)S.n * nc; idx += NT) Bg[idx % S.n + (idx / S.n) * ldg] = trsm_sm[idx];
+    }
 }
 
 int k_trsm(smcp_sym *s, const double *L, double *B, int64_t ldb, int64_t nrhs, int trans) {
     RegionScope rs(s->ctx, "op_trsm");
     smcp_ctx *ctx = s->ctx;
     int cols = 8;
+    // right-hand sides staged in shared memory (up to 200 KB per CTA): n x cols doubles
+    const size_t smem_cap = 200 * 1024;
+    int use_smem = 0;
+    size_t smem = 0;
+    {
+        int fit = (int)(smem_cap / ((size_t)s->d.n * sizeof(double)));
+        if (fit >= 1) {
+            cols = std::min(cols, fit);
+            // keep enough CTAs in flight: at least ~2 per SM when there are that many right-hand sides
+            while (cols > 1 && (nrhs + cols - 1) / cols < 2 * ctx->num_sms && nrhs >= 2 * ctx->num_sms) --cols;
+            use_smem = 1;
+            smem = (size_t)s->d.n * cols * sizeof(double);
+            static size_t attr = 0;
+            if (smem > attr) {
+                CUDA_TRY(cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+                attr = smem_cap;
+            }
+        }
+    }
     int grid = (int)((nrhs + cols - 1) / cols);
     if (grid < 1) return 0;
+    // many right-hand sides (the dense inverse of the sparse-constraint technique: n of them) on a
+    // pattern with a dense top set: the top supernodes -- where the flops are -- go through the slab
+    // solves and DMMA products of bigfront.cu; the top set is closed under ancestors, so in the forward
+    // sweep it comes after everything else and in the backward sweep before
+    const bool big = !s->big.empty() && nrhs >= 32;
+    if (big && trans)
+        for (auto it = s->big.rbegin(); it != s->big.rend(); ++it)
+            if (big_trsm_node(s, *it, L, B, ldb, nrhs, 1)) return -1;
     {
         LaunchScope ls(ctx, "chordal_trsm");
-        trsm_kernel<<<grid, 128, 0, ctx->stream>>>(s->d, L, B, ldb, (int)nrhs, trans, cols);
+        trsm_kernel<<<grid, 128, smem, ctx->stream>>>(s->d, L, B, ldb, (int)nrhs, trans, cols, big ? s->big_flag : nullptr, use_smem);
     }
+    if (big && !trans)
+        for (const BigNode &q : s->big)
+            if (big_trsm_node(s, q, L, B, ldb, nrhs, 0)) return -1;
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -48,6 +48,7 @@ struct PotrfTileArgs {
     int ntc;       // tile columns that exist for this call (P: full trailing update; ceil(npiv/64): panel only)
     int *info;     // dpotrf's info (first non-positive pivot, 1-based), written if still 0
     int col_off;   // added to the local column index in info
+    unsigned *bar; // grid barrier counter (zeroed before the launch)
     long long *dbg; // SMCP_B200_PT_DEBUG: per-step phase timestamps of CTA 0 (ns), 6 per step
 };
 
@@ -58,20 +59,108 @@ __device__ __forceinline__ long long gtimer() {
 }
 #define PT_STAMP(slot) do { if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[6 * k + (slot)] = gtimer(); } while (0)
 
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Barrier over the (co-resident: cooperative launch) grid: one arrival per CTA on a monotone counter.
+// cooperative_groups' grid.sync() costs ~4-5 us on 148 CTAs, this one ~2.
+__device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned &target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        while (ld_acquire_u32(ctr) < target) { }
+    }
+    __syncthreads();
+}
+
+// Cholesky of the 64 x 64 tile in D (kb pivots; the trailing part of the tile receives the Schur
+// complement), all 256 threads: thread (i, jq) keeps the entries (i, 16 jq .. 16 jq + 15) of the lower
+// triangle in REGISTERS; per pivot the (unscaled) pivot column goes through a double-buffered 64-entry
+// column in shared memory and the thread that owns the next diagonal entry computes 1/sqrt(pivot) for the
+// NEXT step before the barrier: one barrier per pivot, a_ij -= a_ic a_jc / d_c on registers.
+// Returns the 1-based index of the first non-positive pivot (0 = none) in *bad_s.
+__device__ __forceinline__ void tile_chol64(double *D, double *rs, double *rinv_s, double *dsv, double *colbuf, int *bad_s, int kb, int tid) {
+    const int i = tid & 63, jq = tid >> 6;
+    double a[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int j = 16 * jq + q;
+        a[q] = (j <= i) ? D[j * DLD + i] : 0.0;
+    }
+    if (tid == 0) *bad_s = 0;
+    if (jq == 0) {
+        colbuf[i] = a[0];
+        if (i == 0) {
+            double d = a[0];
+            if (!(d > 0.0)) { *bad_s = 1; d = 1.0; }
+            const double r = rsqrt(d);
+            rs[0] = r; rinv_s[0] = r * r; dsv[0] = d;
+        }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int cb = 0; cb < 4; ++cb) {
+#pragma unroll
+        for (int cq = 0; cq < 16; ++cq) {
+            const int c = 16 * cb + cq;
+            if (c < kb) {
+                const double *col = colbuf + (c & 1) * 64;
+                if (i > c && 16 * jq + 15 > c) {
+                    const double t = col[i] * rinv_s[c];
+                    const double2 *c2 = reinterpret_cast<const double2 *>(col + 16 * jq);
+#pragma unroll
+                    for (int q2 = 0; q2 < 8; ++q2) {
+                        const double2 lv = c2[q2];
+                        const int j = 16 * jq + 2 * q2;
+                        if (j > c && j <= i) a[2 * q2] = fma(-t, lv.x, a[2 * q2]);
+                        if (j + 1 > c && j + 1 <= i) a[2 * q2 + 1] = fma(-t, lv.y, a[2 * q2 + 1]);
+                    }
+                }
+                // publish column c + 1 (final after this update) and its pivot
+                if (c + 1 < kb && jq == ((c + 1) >> 4)) {
+                    const double v = a[(cq + 1) & 15];
+                    colbuf[((c + 1) & 1) * 64 + i] = v;
+                    if (i == c + 1) {
+                        double d = v;
+                        if (!(d > 0.0)) { if (!*bad_s) *bad_s = c + 2; d = 1.0; }
+                        const double r = rsqrt(d);
+                        rs[c + 1] = r; rinv_s[c + 1] = r * r; dsv[c + 1] = d;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    // scaled factor (columns < kb) and the untouched-scale trailing part back to D
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int j = 16 * jq + q;
+        if (j <= i) D[j * DLD + i] = (j < kb) ? ((i == j) ? dsv[j] * rs[j] : a[q] * rs[j]) : a[q];
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(PT_THREADS, 1) potrf_tile_kernel(PotrfTileArgs a) {
     extern __shared__ __align__(16) double ptsm[];
     double *D = ptsm;                    // TT x DLD, D[c*DLD + r] = tile(r, c)
     double *rs = D + TT * DLD;           // 1/sqrt(pivot)
     double *dsv = rs + TT;               // pivots
-    double *W = dsv + TT;                // phase A: rows xs[c*256 + tid]; phase B: As | Bs
+    double *rinv_s = dsv + TT;           // 1/pivot
+    double *colbuf = rinv_s + TT;        // 2 x 64
+    double *Dp = colbuf + 2 * TT;        // TT x 72: the factored tile with its four 16-row groups 18 apart (panel solve)
+    double *W = Dp + TT * 72;            // phase B: As | Bs
     __shared__ short2 own[PT_MAXOWN];
-    __shared__ int nown_s;
-    cg::grid_group grid = cg::this_grid();
+    __shared__ int nown_s, bad_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double *H = a.H;
     const long long ld = a.ld;
     const int mm = a.mm;
     const int P = (mm + TT - 1) / TT, Pc = (a.npiv + TT - 1) / TT;
+    unsigned bar_target = 0;
     if (tid == 0) {
         const long long ntiles = (long long)a.ntc * P - (long long)a.ntc * (a.ntc - 1) / 2;
         int cnt = 0, j = 0;
@@ -96,7 +185,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) potrf_tile_kernel(PotrfTileArgs
         }
         PT_STAMP(0);
         if (workA) {
-            // ---- diagonal tile: load (identity beyond the matrix), factor kb pivots right-looking
+            // ---- diagonal tile: load (identity beyond the matrix), factor kb pivots
             for (int idx = tid; idx < TT * TT; idx += PT_THREADS) {
                 const int r = idx & 63, c = idx >> 6;
                 double v = 0.0;
@@ -106,92 +195,58 @@ __global__ void __launch_bounds__(PT_THREADS, 1) potrf_tile_kernel(PotrfTileArgs
                 }
                 D[c * DLD + r] = v;
             }
-            int bad = 0;
-            for (int c = 0; c < kb; ++c) {
-                __syncthreads();
-                double d = D[c * DLD + c];
-                if (!(d > 0.0)) {
-                    if (!bad) bad = c + 1;
-                    d = 1.0;
-                }
-                const double r = rsqrt(d), rinv = r * r;
-                if (tid == 0) { rs[c] = r; dsv[c] = d; }
-                const int i = tid & 63;
-                if (i > c) {
-                    // a_ij -= a_ic a_jc / d on the unscaled column c (scaled after the loop); four
-                    // independent load / fma / store chains in flight per thread
-                    const double t = D[c * DLD + i] * rinv;
-                    int j = c + 1 + (tid >> 6);
-                    for (; j + 12 <= i; j += 16) {
-                        const double l0 = D[c * DLD + j], l1 = D[c * DLD + j + 4], l2 = D[c * DLD + j + 8], l3 = D[c * DLD + j + 12];
-                        const double a0 = D[j * DLD + i], a1 = D[(j + 4) * DLD + i], a2 = D[(j + 8) * DLD + i], a3 = D[(j + 12) * DLD + i];
-                        D[j * DLD + i] = fma(-t, l0, a0);
-                        D[(j + 4) * DLD + i] = fma(-t, l1, a1);
-                        D[(j + 8) * DLD + i] = fma(-t, l2, a2);
-                        D[(j + 12) * DLD + i] = fma(-t, l3, a3);
-                    }
-                    for (; j <= i; j += 4) D[j * DLD + i] = fma(-t, D[c * DLD + j], D[j * DLD + i]);
-                }
-            }
             __syncthreads();
-            for (int idx = tid; idx < TT * kb; idx += PT_THREADS) {
+            tile_chol64(D, rs, rinv_s, dsv, colbuf, &bad_s, kb, tid);
+            if (diag_owner && bad_s && tid == 0 && *a.info == 0) *a.info = a.col_off + (int)kc + bad_s;
+            // copy for the panel solve: four lanes read four different 16-row groups of a column at once;
+            // 18 doubles apart they fall into different banks (in D they are 128 bytes apart: 4-way conflicts)
+            for (int idx = tid; idx < TT * TT; idx += PT_THREADS) {
                 const int r = idx & 63, c = idx >> 6;
-                if (r > c) D[c * DLD + r] *= rs[c];
-                else if (r == c) D[c * DLD + c] = dsv[c] * rs[c];
+                Dp[c * 72 + 18 * (r >> 4) + (r & 15)] = D[c * DLD + r];
             }
             __syncthreads();
-            if (diag_owner && bad && tid == 0 && *a.info == 0) *a.info = a.col_off + (int)kc + bad;
             PT_STAMP(1);
-            // ---- panel tiles (i, k), i > k: X L^T = B, one row per thread, up to 4 tiles at a time
-            int q = 0;
-            while (q < nown) {
-                int ti[4], nt = 0;
-                for (; q < nown && nt < 4; ++q)
-                    if (own[q].y == k && own[q].x != k) ti[nt++] = own[q].x;
-                if (!nt) break;
-                const int slot = tid >> 6, r = tid & 63;
-                const long long R = slot < nt ? (long long)TT * ti[slot < nt ? slot : 0] + r : mm;
-                const bool live = slot < nt && R < mm;
-                double *xs = W;
-                double *Pg = H + R + kc * ld;
-                for (int c = 0; c < TT; ++c) xs[c * PT_THREADS + tid] = (live && kc + c < mm) ? Pg[(long long)c * ld] : 0.0;
-                if (live) {
-                    for (int cb8 = 0; cb8 < TT; cb8 += 8) {
-                        double x8[8];
+            // ---- panel tiles (i, k), i > k: X L^T = B.  Four consecutive lanes share a row (16 columns
+            // each in registers); the pivot column's x is broadcast by a shuffle inside the lane group.
+            for (int q = 0; q < nown; ++q) {
+                if (own[q].y != k || own[q].x == k) continue;
+                const int r = tid >> 2, p = tid & 3;
+                const long long R = (long long)TT * own[q].x + r;
+                const bool live = R < mm;
+                double *Pg = H + R + (kc + 16 * p) * ld;
+                double x[16];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) x8[e] = xs[(cb8 + e) * PT_THREADS + tid];
-                        const int pmax = min(cb8, kb);
-                        for (int p = 0; p < pmax; ++p) {
-                            const double xp = xs[p * PT_THREADS + tid];
-                            const double2 *lp = reinterpret_cast<const double2 *>(D + p * DLD + cb8);
+                for (int e = 0; e < 16; ++e) x[e] = (live && kc + 16 * p + e < mm) ? Pg[(long long)e * ld] : 0.0;
+                const int gbase = lane & ~3;
+#pragma unroll 1
+                for (int pc = 0; pc < 4; ++pc) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const double2 lv = lp[e];
-                                x8[2 * e] = fma(-xp, lv.x, x8[2 * e]);
-                                x8[2 * e + 1] = fma(-xp, lv.y, x8[2 * e + 1]);
+                    for (int e = 0; e < 16; ++e) {
+                        const int c = 16 * pc + e;
+                        if (c < kb) {
+                            const double xc = __shfl_sync(0xffffffffu, x[e] * rs[c], gbase + pc);
+                            if (p == pc) x[e] = xc;
+                            if (p >= pc) {
+                                const double2 *lc = reinterpret_cast<const double2 *>(Dp + c * 72 + 18 * p);
+#pragma unroll
+                                for (int e2 = 0; e2 < 8; ++e2) {
+                                    const double2 lv = lc[e2];
+                                    if (16 * p + 2 * e2 > c) x[2 * e2] = fma(-xc, lv.x, x[2 * e2]);
+                                    if (16 * p + 2 * e2 + 1 > c) x[2 * e2 + 1] = fma(-xc, lv.y, x[2 * e2 + 1]);
+                                }
                             }
-                        }
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            if (cb8 + e < kb) {
-                                const double xk = x8[e] * rs[cb8 + e];
-                                x8[e] = xk;
-#pragma unroll
-                                for (int e2 = e + 1; e2 < 8; ++e2) x8[e2] = fma(-xk, D[(cb8 + e) * DLD + cb8 + e2], x8[e2]);
-                            }
-                        }
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            xs[(cb8 + e) * PT_THREADS + tid] = x8[e];
-                            if (kc + cb8 + e < mm) Pg[(long long)(cb8 + e) * ld] = x8[e];
                         }
                     }
                 }
-                __syncthreads();
+                if (live) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (kc + 16 * p + e < mm) Pg[(long long)e * ld] = x[e];
+                }
             }
         }
         PT_STAMP(2);
-        grid.sync();
+        grid_barrier(a.bar, bar_target);
         PT_STAMP(3);
         if (diag_owner) {
             // written back only now: during phase A the other CTAs of this block column were still
@@ -249,12 +304,12 @@ __global__ void __launch_bounds__(PT_THREADS, 1) potrf_tile_kernel(PotrfTileArgs
             }
         }
         PT_STAMP(4);
-        if (k + 1 < Pc) grid.sync();
+        if (k + 1 < Pc) grid_barrier(a.bar, bar_target);
         PT_STAMP(5);
     }
 }
 
-static size_t potrf_tile_smem() { return (size_t)(TT * DLD + 2 * TT + TT * PT_THREADS) * sizeof(double); }
+static size_t potrf_tile_smem() { return (size_t)(TT * DLD + 5 * TT + TT * 72 + 2 * TT * OLDT) * sizeof(double); }
 
 // Largest order handled by one launch (tiles per CTA bounded by PT_MAXOWN)
 bool potrf_tile_fits(const smcp_ctx *ctx, int64_t mm, int64_t npiv, bool panel_only) {
@@ -279,6 +334,13 @@ int potrf_tile(smcp_ctx *ctx, double *H, int64_t ld, int64_t mm, int64_t npiv, b
     a.ntc = (int)(panel_only ? Pc : P);
     a.info = info_dev; a.col_off = col_off;
     a.dbg = nullptr;
+    // grid-barrier counter: a ring of 64 counters so that launches in flight on different streams never share one
+    if (!ctx->gridbar) {
+        CUDA_TRY(cudaMalloc(&ctx->gridbar, 64 * 64));
+        CUDA_TRY(cudaMemset(ctx->gridbar, 0, 64 * 64));
+    }
+    a.bar = ctx->gridbar + 16 * (ctx->gridbar_next++ & 63);
+    CUDA_TRY(cudaMemsetAsync(a.bar, 0, sizeof(unsigned), ctx->stream));
     static const bool dbg_on = getenv("SMCP_B200_PT_DEBUG") != nullptr;
     long long *dbg_dev = nullptr;
     if (dbg_on) {

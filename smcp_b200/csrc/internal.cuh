@@ -52,6 +52,8 @@ struct smcp_ctx {
     double *gemm_ws = nullptr;          // split-K partial results
     size_t gemm_ws_cap = 0;
     void *nccl_comm = nullptr;
+    unsigned *gridbar = nullptr;        // counters of the hand-rolled grid barrier (potrf_tile_kernel)
+    unsigned gridbar_next = 0;
     // pinned staging for small host<->device transfers
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
@@ -117,6 +119,8 @@ struct BigNode {
     int k, nn, na, nj, nch;
     long long boff, uoff;        // offsets of its block in blkval and of its update matrix
     long long inv_off, ch_off;   // offsets into big_inv (nch x nj) and big_ch (nch)
+    long long rowoff;            // offset of its row list in rowidx
+    int r0;                      // its first row / column (the columns of a supernode are contiguous)
 };
 #define BIG_NWS 6                // nj x nj workspaces of the dense path
 
@@ -227,6 +231,7 @@ int big_projinv(smcp_sym *s, const BigNode &q, double *X, int64_t b);
 int big_completion(smcp_sym *s, const BigNode &q, double *X, const double *Xin, int64_t b);
 int big_hess_prep(smcp_sym *s, const BigNode &q, const double *L0, const double *Y0, double *Lt_out, double *Yaa_out);
 int big_hess_prep_inv(smcp_sym *s, const BigNode &q, const double *Yaa_all, double *Raa_all);
+int big_trsm_node(smcp_sym *s, const BigNode &q, const double *L, double *B, int64_t ldb, int64_t nrhs, int trans);
 int big_hess_fwd_batched(smcp_sym *s, const double *Lt, const double *Yaa_all, double *U, int64_t batch);
 
 // blocked triangular solves (front.cu)
@@ -237,6 +242,10 @@ int d_trsm_left_lower(smcp_ctx *ctx, bool trans, const double *L, int64_t ldl, i
 // Schur complement in the trailing block; nranks > 1: block-cyclic columns with NCCL panel broadcasts
 int d_potrf(smcp_ctx *ctx, double *H, int64_t ld, int64_t m, int64_t ncols, int32_t *info_dev, int rank, int nranks, int64_t block = 0);
 int d_potrs(smcp_ctx *ctx, const double *H, int64_t m, double *y_dev);
+// potrs as one thread-block-cluster launch on the inverted 64 x 64 diagonal blocks (potrs_cluster.cu)
+bool potrs_cluster_enabled();
+int d_potrs_prepare(smcp_ctx *ctx, const double *H, int64_t m, double *Dinv);
+int d_potrs_cluster(smcp_ctx *ctx, const double *H, int64_t m, const double *Dinv, double *y_dev);
 int launch_gemm_cyc(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
                     int64_t ldc, int64_t M, int64_t N, int64_t K, double alpha, int accumulate, int tri, int64_t tri_off,
                     const char *name, int jb0, int jbstride, int tpb = 1);

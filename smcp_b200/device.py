@@ -79,6 +79,9 @@ API = {
     "smcp_op_aadj": (_int, [_vp, _f64p, _dp]),
     "smcp_kkt_assemble": (_int, [_vp, _vp, _i64, _i64]),
     "smcp_kkt_assemble_cyclic": (_int, [_vp, _vp, _i64, _int, _int]),
+    "smcp_kkt_assemble_syrk": (_int, [_vp, _vp]),
+    "smcp_kkt_z_tmul": (_int, [_vp, _dp, _f64p]),
+    "smcp_kkt_z_mul": (_int, [_vp, _f64p, _dp]),
     "smcp_kkt_factor": (_int, [_vp, _i32p]),
     "smcp_kkt_factor_dist": (_int, [_vp, _int, _int, _i32p]),
     "smcp_kkt_factor_block": (_int, [_vp, _i64, _int, _int, _i32p]),
@@ -546,6 +549,35 @@ class DeviceBackend:
                 _ck(self.lib, self.lib.smcp_kkt_factor(self._op, info))
         if info[0]:
             raise ArithmeticError("Schur complement is not positive definite (info=%d)" % info[0])
+
+    # -- kktsolver='qr' in SYRK form (solvers.py:413-475) ---------------------------------------
+    def schur_factor_qr(self, tok):
+        info = np.zeros(1, dtype=np.int32)
+        _ck(self.lib, self.lib.smcp_kkt_assemble_syrk(self._op, tok))
+        _ck(self.lib, self.lib.smcp_kkt_factor(self._op, info))
+        if info[0]:
+            raise ArithmeticError("Z = G(A) is rank deficient (info=%d)" % info[0])
+
+    def gram_factor(self):
+        """Cholesky factor of the Gram matrix <A_i, A_j> (trace inner product) of the constraints: the
+        normal equations of the least-norm start of ``SDP.solve_phase1`` (``base.py:383-396``)."""
+        info = np.zeros(1, dtype=np.int32)
+        _ck(self.lib, self.lib.smcp_kkt_assemble_syrk(self._op, None))
+        _ck(self.lib, self.lib.smcp_kkt_factor(self._op, info))
+        if info[0]:
+            raise ArithmeticError("the constraint matrices are linearly dependent (info=%d)" % info[0])
+
+    def z_tmul(self, buf):
+        TRAFFIC["d2h"] += 8 * self.m
+        out = np.empty(self.m)
+        _ck(self.lib, self.lib.smcp_kkt_z_tmul(self._op, buf, out))
+        return out
+
+    def z_mul(self, y):
+        TRAFFIC["h2d"] += 8 * self.m
+        p = self._alloc(False)
+        _ck(self.lib, self.lib.smcp_kkt_z_mul(self._op, np.ascontiguousarray(y, dtype=np.float64), p))
+        return p
 
     def schur_solve(self, y):
         TRAFFIC["h2d"] += 8 * self.m

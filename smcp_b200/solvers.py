@@ -7,7 +7,7 @@ Public surface (drop-in for ``smcp.solvers``, reference ``src/python/solvers.py`
 * ``chordalsolver_esd(A, b, ...)``  – extended self-dual embedding (``solvers.py:1330-2467``)
 * ``conelp(c, G, h, dims)``         – CVXOPT-style cone-LP front end (``solvers.py:2470-2599``)
 
-Only ``kktsolver='chol'`` is provided (the north-star path); ``'qr'`` raises.
+``kktsolver='chol'`` is the north-star path; ``'qr'`` is provided in its SYRK form (``_KKTqr``).
 
 The numerical work of every iteration — chordal Cholesky / completion / projected inverse,
 the barrier Hessian, the dense Schur complement and its Cholesky, step-length probes and
@@ -141,10 +141,9 @@ class _Problem:
     """Ordering, chordal embedding, vector-space layout and the operators A / A^adj."""
 
     def __init__(self, A, b, opt, kktsolver, p):
-        if kktsolver != "chol":
-            if kktsolver == "qr":
-                raise NotImplementedError("kktsolver='qr' is outside the B200 hot path; use 'chol'")
+        if kktsolver not in ("chol", "qr"):
             raise ValueError("Unknown 'kktsolver'.")
+        self.kktsolver = kktsolver
         A = misc.as_csc(A)
         self.m = m = A.shape[1] - 1
         self.n = n = int(math.sqrt(A.shape[0]))
@@ -159,13 +158,17 @@ class _Problem:
 
         # constraint permutation: "dense" constraints first, "sparse" ones last; each group by
         # decreasing nnz, ties by decreasing index (solvers.py:246-268)
-        Nz = misc.nzcolumns(A)
-        pm, Ns = misc.matperm(Nz, opt.tnzcols)
-        nnz_col = np.diff(A.indptr)[1:]
-        for lo, hi in ((0, m - Ns), (m - Ns, m)):
-            if hi > lo:
-                grp = sorted(((int(nnz_col[j]), int(j)) for j in pm[lo:hi]), reverse=True)
-                pm[lo:hi] = [j for _, j in grp]
+        if kktsolver == "chol":
+            Nz = misc.nzcolumns(A)
+            pm, Ns = misc.matperm(Nz, opt.tnzcols)
+            nnz_col = np.diff(A.indptr)[1:]
+            for lo, hi in ((0, m - Ns), (m - Ns, m)):
+                if hi > lo:
+                    grp = sorted(((int(nnz_col[j]), int(j)) for j in pm[lo:hi]), reverse=True)
+                    pm[lo:hi] = [j for _, j in grp]
+        else:
+            # kktsolver='qr': no sparse-constraint technique, constraints keep their order (solvers.py:269-271)
+            pm, Ns = np.arange(m, dtype=np.int64), 0
         self.pm, self.Ns = pm, Ns
         self.b = b = b[pm].copy()
         if m:
@@ -278,6 +281,36 @@ class _KKT:
         hessian(self.L, self.Y, [x], inv=False, adj=None)
         x.scale(1.0 / kk)
         return x, y
+
+
+class _KKTqr:
+    """``kkt_qr`` (solvers.py:413-475 == 1843-1904): with the half factor G of the Hessian
+    (``hessian = G^adj o G``) and Z = [G(A_1) ... G(A_m)], the Schur complement is H = Z^T Z in the trace
+    inner product.  The reference takes the QR factorisation of Z (``lapack.geqrf``); here H = Z^T Z is
+    formed by one triangular DMMA product (SYRK form, SURVEY 8f rank 3: half the Hessian work of
+    ``kkt_chol``, H positive semidefinite by construction) and factored by the same Cholesky, i.e. R of
+    Z = Q R without Q (Q is only ever applied as Z R^-1):
+        y = H^{-1}(kk*by + Z^T G(bx)),   x = (1/kk) G^adj(Z y - G(bx))."""
+
+    def __init__(self, prob, L, Y, scaling):
+        self.prob, self.L, self.Y, self.scaling = prob, L, Y, scaling
+        prob.ops.schur_factor_qr(schur_token(L, Y))      # raises ArithmeticError if Z is rank deficient
+
+    def solve(self, bx, by, t):
+        kk = 1.0 / t if self.scaling == "primal" else t
+        ops = self.prob.ops
+        r1 = bx.copy()
+        hessian(self.L, self.Y, [r1], inv=False, adj=False)
+        y = ops.schur_solve(kk * by + ops.z_tmul(r1.buf))
+        x = cspmatrix(ops, ops.z_mul(np.ascontiguousarray(y, dtype=np.float64)))
+        x -= r1
+        hessian(self.L, self.Y, [x], inv=False, adj=True)
+        x.scale(1.0 / kk)
+        return x, y
+
+
+def _make_kkt(prob, L, Y, scaling):
+    return (_KKTqr if prob.kktsolver == "qr" else _KKT)(prob, L, Y, scaling)
 
 
 def _nrm2(v):
@@ -498,7 +531,7 @@ def chordalsolver_feas(A, b, primalstart=None, dualstart=None, scaling="primal",
         Xt = prob.identity()
         Lt = Xt.copy()
         completion(Lt)
-        fI = _KKT(prob, Lt, Xt, st.scaling)
+        fI = _make_kkt(prob, Lt, Xt, st.scaling)
         X0, _nu = fI.solve(prob.zeros(), b, st.t)
         if _in_cone(X0, completion) is not None:
             X = X0
@@ -615,7 +648,7 @@ def chordalsolver_feas(A, b, primalstart=None, dualstart=None, scaling="primal",
             projected_inverse(Y)
 
         try:
-            f = _KKT(prob, L, Y, st.scaling)
+            f = _make_kkt(prob, L, Y, st.scaling)
         except ArithmeticError:
             # reference: "*** Factorization failed" and a dict that makes the next call fail
             print("*** Factorization failed")
@@ -1088,7 +1121,7 @@ def chordalsolver_esd(A, b, primalstart=None, dualstart=None, scaling="primal",
             projected_inverse(st.Y)
 
         try:
-            st.f = _KKT(prob, st.L, st.Y, scaling)
+            st.f = _make_kkt(prob, st.L, st.Y, scaling)
         except ArithmeticError:
             print("*** Factorization failed")
             status = "unknown"

@@ -222,8 +222,14 @@ def test_C5_maxcut_n5000():
     ob = _oracle_for(pr)
     symb = pr.symb
     w = symb.wdot > 0
-    # X = I + small chordal perturbation: strictly inside the cone, not a trivial diagonal
-    x = 0.02 * np.random.default_rng(1).standard_normal(symb.nblk) * w
-    x[symb.diag_blk] = 1.0 + 0.1 * np.random.default_rng(2).random(symb.n)
+    # a diagonally dominant chordal matrix on the filled pattern: strictly inside the cone, not a trivial diagonal
+    v = 0.05 * np.random.default_rng(1).standard_normal(symb.nvp)
+    off = symb.Ip != symb.Jp
+    rowsum = np.zeros(symb.n)
+    np.add.at(rowsum, symb.Ip[off], np.abs(v[off]))
+    np.add.at(rowsum, symb.Jp[off], np.abs(v[off]))
+    v[~off] = 1.0 + rowsum[symb.Ip[~off]]
+    x = np.zeros(symb.nblk)
+    x[symb.vec2blk] = v
     e0 = _check_point(pr, ob, x, 1e-9, (2500, 2516), scaling="dual")
     print("C5 n=5000:", {k: "%.1e" % v for k, v in e0.items()})

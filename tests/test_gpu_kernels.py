@@ -175,6 +175,35 @@ def test_hessian_forward_inverse(setup, batch):
     assert relerr(back, U) < 1e-8
 
 
+@pytest.mark.parametrize("inv,adj", [(False, False), (False, True), (True, True), (True, False)])
+def test_hessian_half_factors(setup, inv, adj):
+    """chompack.hessian(L, Y, U, adj=False/True, inv=...) (solvers.py:917, 978, 1121, 1126): the half
+    factors G, G^adj, G^-adj, G^-1 against the oracle, the identity hessian = G^adj o G, and the Newton
+    decrement ||G(u)||^2 = u . hessian(u) that the drivers evaluate through hessian_norm()."""
+    from oracle import supernodal as sn
+    symb, dev, s, l, y = setup
+    rng = np.random.default_rng(13)
+    hf = sn.HessianFactor(symb, l, y)
+    tok = dev.hessian_factor(dev.set_blk(l), dev.set_blk(y))
+    U = rng.standard_normal((2, symb.nblk)) * (symb.wdot > 0)
+    W = U.copy()
+    sn.hessian_half(hf, W, adj, inv)
+    bufs = [dev.set_blk(u) for u in U]
+    dev.hessian_apply(tok, bufs, inv, adj)
+    got = np.array([dev.get_blk(b) for b in bufs])
+    assert relerr(got * (symb.wdot > 0), W * (symb.wdot > 0)) < 1e-10
+    # second half: the composition is the full (inverse) Hessian
+    dev.hessian_apply(tok, bufs, inv, not adj)
+    full = np.array([dev.get_blk(b) for b in bufs])
+    F = U.copy()
+    (sn.hessian_inv if inv else sn.hessian)(hf, F)
+    if adj == inv:      # forward: G then G^adj; inverse: G^-adj then G^-1
+        assert relerr(full * (symb.wdot > 0), F * (symb.wdot > 0)) < 1e-9
+        for k in range(2):
+            n2 = sn.dot(symb, got[k], got[k])
+            assert abs(n2 - sn.dot(symb, U[k], F[k])) <= 1e-9 * abs(n2)
+
+
 def test_probe_batch(setup):
     symb, dev, s, l, y = setup
     rng = np.random.default_rng(5)

@@ -209,6 +209,29 @@ def test_driver_parity(kind, method, scaling):
                     assert abs(ra[key] - rb[key]) <= 1e-8 * max(1.0, abs(ra[key])), (key, ra, rb)
 
 
+@pytest.mark.parametrize("kind,method", [("band", "feas"), ("band", "esd"), ("mtxnorm", "esd")])
+def test_kktsolver_qr_gpu(kind, method):
+    """kktsolver='qr' on the device (half factors, Z^T Z by one triangular DMMA product, Cholesky) against the
+    oracle's Householder-QR version of the same solver."""
+    from smcp_b200 import solvers
+    fo, fd = _factories()
+    P = _make(kind)
+    out = []
+    for fac in (fo, fd):
+        solvers.options["show_progress"] = False
+        solvers.set_backend_factory(fac)
+        if method == "feas":
+            out.append(P.solve_feas(kktsolver="qr", primalstart={"x": P._X0} if P._X0 is not None else None))
+        else:
+            out.append(P.solve_esd(kktsolver="qr"))
+    a, b = out
+    assert a["status"] == b["status"] == "optimal", (a["status"], b["status"])
+    if method == "feas":       # the self-dual embedding's exit iteration is not reproducible (tests/test_golden.py)
+        assert abs(a["iterations"] - b["iterations"]) <= 1
+    for key in ("primal objective", "dual objective"):
+        assert abs(a[key] - b[key]) <= 1e-7 * max(1.0, abs(a[key])), (key, a[key], b[key])
+
+
 def test_conelp_known_answer_gpu():
     """The reference's only test problem (tests/test_basic.py:9-19): CVXOPT's cone-LP example,
     optimum x = (-1.22, 0.0966, 3.58)."""

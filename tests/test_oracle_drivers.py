@@ -76,6 +76,23 @@ def test_esd_band(oracle_backend):
     assert abs(sol["primal objective"] - 3.1762985) < 1e-5
 
 
+def test_kktsolver_qr_matches_chol(oracle_backend):
+    """kktsolver='qr' (solvers.py:413-475; here in SYRK form on the half factors, Householder QR in the
+    oracle): the same Newton systems as 'chol', hence the same iterates to solver accuracy."""
+    import smcp_b200 as S
+    P = S.band_SDP(40, 12, 3, seed=2)
+    a = P.solve_feas(kktsolver="chol", primalstart={"x": P._X0})
+    b = P.solve_feas(kktsolver="qr", primalstart={"x": P._X0})
+    assert a["status"] == b["status"] == "optimal"
+    assert abs(a["iterations"] - b["iterations"]) <= 1
+    for key in ("primal objective", "dual objective"):
+        assert abs(a[key] - b[key]) <= 1e-8 * max(1.0, abs(a[key]))
+    # the self-dual embedding, whose exit is fragile with 'chol' (see tests/test_golden.py), converges with 'qr'
+    c = S.band_SDP(30, 10, 2, seed=1).solve_esd(kktsolver="qr")
+    assert c["status"] == "optimal" and c["iterations"] <= 25
+    assert abs(c["primal objective"] - 3.17629856) <= 1e-6
+
+
 def test_phase1_then_feas(oracle_backend):
     """example.py:22-35 flow: mtxnorm problem, phase 1 for a primal start, then solve_feas."""
     import smcp_b200 as S
@@ -100,8 +117,8 @@ def test_options_validation(oracle_backend):
     solvers.options["maxiters"] = 100
     with pytest.raises(ValueError):
         P.solve_feas(scaling="both")
-    with pytest.raises(NotImplementedError):
-        P.solve_feas(kktsolver="qr")
+    with pytest.raises(ValueError):
+        P.solve_feas(kktsolver="lu")
 
 
 def test_product_backend_fails_loudly_without_cuda():
