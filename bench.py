@@ -437,8 +437,10 @@ def run_b200(args):
     # descriptor 1 is pointed at stderr for the whole run and the one JSON line goes to the saved stdout
     json_fd = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.pop("NCCL_DEBUG_FILE", None)
         sys.stdout.flush()
         json_fd = os.dup(1)
         os.dup2(2, 1)

@@ -1,0 +1,19 @@
+mkdir -p gpurun_out
+(timeout 900 python -m pytest tests/test_gpu_solver.py -q --maxfail=10 2>&1 | tail -30) > gpurun_out/r02_v9_pytest_solver.log
+(timeout 300 python scripts/bench_dense.py 1000 2500 10000 2>&1 | grep -E "^m=|rror" ) > gpurun_out/r02_v9_dense.log
+(RUNCFG_METHOD=feas RUNCFG_NOPROF=1 timeout 600 python scripts/run_config.py C4 full 2>&1 | tail -8) > gpurun_out/r02_v9_C4_feas.log
+(timeout 900 python bench.py 2>gpurun_out/r02_v9_bench.err | tail -1) > gpurun_out/r02_v9_bench.json
+tail -n 12 gpurun_out/r02_v9_pytest_solver.log; cat gpurun_out/r02_v9_dense.log; cat gpurun_out/r02_v9_C4_feas.log; tail -3 gpurun_out/r02_v9_bench.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r02_v9_bench.json'))
+print("C3 e2e", d["e2e"], "value", d["value"], "launches", d["gpu_launches"])
+print("roofline", d["roofline"])
+print("schur_potrf", {k:v for k,v in d["schur_potrf"].items() if k not in ("note","flop_model")})
+print("tts", d["time_to_solve"])
+print("ops", {k: round(v["ms_per_step"],1) for k,v in d["chordal_ops_ms_per_step"].items()})
+print("kern", {k: round(v,1) for k,v in list(d["kernel_ms_per_step"].items())[:12]})
+s=d.get("secondary")
+if s:
+    print("C2 e2e", s["e2e"], "value", s["value"], "roofline", s["roofline"]); print({k: round(v,3) for k,v in list(s["kernel_ms_per_step"].items())[:12]}); print("tts", s["time_to_solve"])
+PY

@@ -835,10 +835,6 @@ scm_position_kernel(const long long *__restrict__ colptr, const double *__restri
     }
 }
 
-__global__ void set_identity_kernel(double *Z, long long n) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) Z[i + i * n] = 1.0;
-}
 
 // technique 1 on a set of column ranges: ONE batched Hessian over all of them (the chordal kernels
 // are latency/issue bound, small batches waste the machine), then one DMMA contraction per range
@@ -886,6 +882,39 @@ static int assemble_dense_ranges(smcp_op *op, smcp_hess *h, const std::vector<st
 }
 
 // technique 2: sparse constraints through the dense inverse of S (columns [s0, s1))
+__global__ void set_identity_cols_kernel(double *Z, long long n, long long c0, long long c1) {
+    long long i = c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < c1) Z[i + i * n] = 1.0;
+}
+__global__ void set_identity_kernel(double *Z, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) Z[i + i * n] = 1.0;
+}
+
+// dense inverse of S (internal order) for the sparse-constraint technique.  Several ranks: every rank solves
+// for its slice of the columns (equal chunks; the buffer is padded to nranks * chunk columns) and the slices
+// are all-gathered over NVLink -- a collective: every rank of the communicator must call it.
+static int build_zinv(smcp_op *op, smcp_hess *h, bool sharded) {
+    smcp_sym *s = op->sym;
+    smcp_ctx *ctx = s->ctx;
+    const long long n = s->d.n;
+    const int nr = sharded ? ctx->comm_nranks : 1, rk = sharded ? ctx->comm_rank : 0;
+    const long long chunk = (n + nr - 1) / nr;
+    if (!op->Zinv) CUDA_TRY(cudaMalloc(&op->Zinv, (size_t)n * (size_t)std::max<long long>(chunk * ctx->comm_nranks + 1, n) * sizeof(double)));
+    const long long c0 = std::min<long long>(n, rk * chunk), c1 = std::min<long long>(n, c0 + chunk);
+    CUDA_TRY(cudaMemsetAsync(op->Zinv + (size_t)rk * chunk * n, 0, (size_t)chunk * n * sizeof(double), ctx->stream));
+    if (c1 > c0) {
+        {
+            LaunchScope ls(ctx, "setup");
+            set_identity_cols_kernel<<<(unsigned)((c1 - c0 + 255) / 256), 256, 0, ctx->stream>>>(op->Zinv, n, c0, c1);
+        }
+        if (k_trsm(s, h->L, op->Zinv + (size_t)c0 * n, n, c1 - c0, 0)) return -1;
+        if (k_trsm(s, h->L, op->Zinv + (size_t)c0 * n, n, c1 - c0, 1)) return -1;
+    }
+    if (nr > 1 && comm_allgather(ctx, op->Zinv, (size_t)chunk * n, ctx->stream)) return -1;
+    return 0;
+}
+
 static int assemble_sparse_range(smcp_op *op, smcp_hess *h, int64_t s0, int64_t s1, bool fresh_inverse) {
     smcp_sym *s = op->sym;
     smcp_ctx *ctx = s->ctx;
@@ -893,16 +922,7 @@ static int assemble_sparse_range(smcp_op *op, smcp_hess *h, int64_t s0, int64_t 
     if (s1 <= s0) return 0;
     if (!op->ent_r) { smcp_set_error("entry coordinates not set (smcp_op_set_entry_coords)"); return -2; }
     const long long n = s->d.n;
-    if (fresh_inverse) {
-        if (!op->Zinv) CUDA_TRY(cudaMalloc(&op->Zinv, (size_t)n * n * sizeof(double)));
-        CUDA_TRY(cudaMemsetAsync(op->Zinv, 0, (size_t)n * n * sizeof(double), ctx->stream));
-        {
-            LaunchScope ls(ctx, "setup");
-            set_identity_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(op->Zinv, n);
-        }
-        if (k_trsm(s, h->L, op->Zinv, n, n, 0)) return -1;
-        if (k_trsm(s, h->L, op->Zinv, n, n, 1)) return -1;
-    }
+    if (fresh_inverse && build_zinv(op, h, false)) return -1;
     // position form when the staged columns of Z fit in shared memory and the constraints are not
     // (almost) single entries; otherwise the pairwise form of the reference
     const long long cap = 25600;                 // doubles of dynamic shared memory (200 KB)
@@ -953,12 +973,15 @@ extern "C" int smcp_kkt_assemble_cyclic(smcp_op *op, smcp_hess *h, int64_t block
         if (c0 < md) dense.push_back({c0, std::min(c1, md)});
     }
     if (assemble_dense_ranges(op, h, dense)) return -1;
+    if (op->Ns > 0) {
+        // the dense inverse is shared by all sparse columns: built once, collectively when the communicator spans the ranks
+        smcp_ctx *ctx = op->sym->ctx;
+        if (build_zinv(op, h, nranks > 1 && ctx->nccl_comm && ctx->comm_nranks == nranks && ctx->comm_rank == rank)) return -1;
+        fresh = false;
+    }
     for (int64_t c0 = (int64_t)rank * block; c0 < m; c0 += (int64_t)nranks * block) {
         const int64_t c1 = std::min(m, c0 + block);
-        if (c1 > md) {
-            if (assemble_sparse_range(op, h, std::max(c0, md), c1, fresh)) return -1;
-            fresh = false;
-        }
+        if (c1 > md && assemble_sparse_range(op, h, std::max(c0, md), c1, fresh)) return -1;
     }
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -1089,7 +1112,7 @@ extern "C" int smcp_kkt_factor(smcp_op *op, int32_t *info_host) {
     {
         RegionScope rs(ctx, "kkt_factor");
         if (d_potrf(ctx, op->H, op->m, op->m, op->m, op->info_dev, 0, 1)) return -1;
-        if (potrs_cluster_enabled() && d_potrs_prepare(ctx, op->H, op->m, op->Dinv)) return -1;
+        if (potrs_cluster_for(op->m) && d_potrs_prepare(ctx, op->H, op->m, op->Dinv)) return -1;
     }
     CUDA_TRY(cudaMemcpyAsync(info_host, op->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1107,7 +1130,7 @@ extern "C" int smcp_kkt_factor_dist(smcp_op *op, int rank, int nranks, int32_t *
     {
         RegionScope rs(ctx, "kkt_factor");
         if (d_potrf(ctx, op->H, op->m, op->m, op->m, op->info_dev, rank, nranks)) return -1;
-        if (potrs_cluster_enabled() && d_potrs_prepare(ctx, op->H, op->m, op->Dinv)) return -1;
+        if (potrs_cluster_for(op->m) && d_potrs_prepare(ctx, op->H, op->m, op->Dinv)) return -1;
     }
     CUDA_TRY(cudaMemcpyAsync(info_host, op->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1123,7 +1146,7 @@ extern "C" int smcp_kkt_factor_block(smcp_op *op, int64_t block, int rank, int n
     {
         RegionScope rs(ctx, "kkt_factor");
         if (d_potrf(ctx, op->H, op->m, op->m, op->m, op->info_dev, rank, nranks, block)) return -1;
-        if (potrs_cluster_enabled() && d_potrs_prepare(ctx, op->H, op->m, op->Dinv)) return -1;
+        if (potrs_cluster_for(op->m) && d_potrs_prepare(ctx, op->H, op->m, op->Dinv)) return -1;
     }
     CUDA_TRY(cudaMemcpyAsync(info_host, op->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1216,7 +1239,7 @@ extern "C" int smcp_kkt_solve(smcp_op *op, double *host_y) {
     CUDA_TRY(cudaMemcpyAsync(op->yv, host_y, (size_t)op->m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     {
         RegionScope rs(ctx, "kkt_solve");
-        if (potrs_cluster_enabled() ? d_potrs_cluster(ctx, op->H, op->m, op->Dinv, op->yv) : d_potrs(ctx, op->H, op->m, op->yv)) return -1;
+        if (potrs_cluster_for(op->m) ? d_potrs_cluster(ctx, op->H, op->m, op->Dinv, op->yv) : d_potrs(ctx, op->H, op->m, op->yv)) return -1;
     }
     CUDA_TRY(cudaMemcpyAsync(host_y, op->yv, (size_t)op->m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1249,6 +1272,10 @@ typedef int (*fn_init)(void **, int, nccl_uid, int);
 typedef int (*fn_destroy)(void *);
 typedef int (*fn_bcast)(const void *, void *, size_t, int, int, void *, cudaStream_t);
 typedef int (*fn_group)(void);
+typedef int (*fn_allreduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*fn_allgather)(const void *, void *, size_t, int, void *, cudaStream_t);
+static fn_allreduce p_allreduce;
+static fn_allgather p_allgather;
 static void *g_nccl = nullptr;
 static fn_getuid p_getuid;
 static fn_init p_init;
@@ -1267,7 +1294,9 @@ static int load_nccl() {
     p_bcast = (fn_bcast)dlsym(g_nccl, "ncclBroadcast");
     p_gstart = (fn_group)dlsym(g_nccl, "ncclGroupStart");
     p_gend = (fn_group)dlsym(g_nccl, "ncclGroupEnd");
-    if (!p_getuid || !p_init || !p_destroy || !p_bcast || !p_gstart || !p_gend) {
+    p_allreduce = (fn_allreduce)dlsym(g_nccl, "ncclAllReduce");
+    p_allgather = (fn_allgather)dlsym(g_nccl, "ncclAllGather");
+    if (!p_getuid || !p_init || !p_destroy || !p_bcast || !p_gstart || !p_gend || !p_allreduce || !p_allgather) {
         smcp_set_error("libnccl is missing required symbols");
         return -1;
     }
@@ -1289,11 +1318,33 @@ extern "C" int smcp_comm_init(smcp_ctx *ctx, int rank, int nranks, const char *i
     memcpy(id.internal, id_128, 128);
     int rc = p_init(&ctx->nccl_comm, nranks, id, rank);
     if (rc) { smcp_set_error("ncclCommInitRank failed (%d)", rc); return -1; }
+    ctx->comm_rank = rank;
+    ctx->comm_nranks = nranks;
     return 0;
 }
 extern "C" int smcp_comm_destroy(smcp_ctx *ctx) {
     if (ctx->nccl_comm) p_destroy(ctx->nccl_comm);
     ctx->nccl_comm = nullptr;
+    ctx->comm_rank = 0;
+    ctx->comm_nranks = 1;
+    return 0;
+}
+
+int comm_group_start() { return p_gstart ? p_gstart() : -1; }
+int comm_group_end() { return p_gend ? p_gend() : -1; }
+int comm_allreduce_max_i32(smcp_ctx *ctx, int *ptr, size_t count, cudaStream_t s) {
+    if (!ctx->nccl_comm) { smcp_set_error("NCCL communicator not initialised"); return -2; }
+    int rc = p_allreduce(ptr, ptr, count, 2 /* ncclInt32 */, 2 /* ncclMax */, ctx->nccl_comm, s);
+    if (rc) { smcp_set_error("ncclAllReduce failed (%d)", rc); return -1; }
+    ctx->launches += 1;
+    return 0;
+}
+// every rank contributes `chunk` doubles at base + rank*chunk; all ranks end with nranks*chunk doubles
+int comm_allgather(smcp_ctx *ctx, double *base, size_t chunk, cudaStream_t s) {
+    if (!ctx->nccl_comm) { smcp_set_error("NCCL communicator not initialised"); return -2; }
+    int rc = p_allgather(base + (size_t)ctx->comm_rank * chunk, base, chunk, 8 /* ncclFloat64 */, ctx->nccl_comm, s);
+    if (rc) { smcp_set_error("ncclAllGather failed (%d)", rc); return -1; }
+    ctx->launches += 1;
     return 0;
 }
 

@@ -159,6 +159,16 @@ int fetch_fail(smcp_sym *s, int64_t batch, int32_t *info_host) {
 // bigfront.cu (after the tree kernel in leaves-to-root sweeps, before it in root-to-leaves sweeps)
 static bool use_big(const smcp_sym *s, int64_t batch) { return !s->big.empty() && batch <= 4; }
 
+// Number of ranks that share the per-supernode-independent operations on the top set (completion, the
+// Cholesky factors of Y_aa): all ranks of the communicator when the library runs as N replicas of one
+// solve (bench / drivers under torchrun); 1 otherwise.  SMCP_B200_DIST_OPS=0 keeps every rank on its own.
+static int dist_ops(const smcp_sym *s, int64_t batch) {
+    static const bool off = getenv("SMCP_B200_DIST_OPS") && atoi(getenv("SMCP_B200_DIST_OPS")) == 0;
+    const smcp_ctx *ctx = s->ctx;
+    if (off || !ctx->nccl_comm || ctx->comm_nranks < 2 || batch != 1 || s->big.size() < 2) return 1;
+    return ctx->comm_nranks;
+}
+
 int k_cholesky(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
     RegionScope rs(s->ctx, batch > 1 ? "op_cholesky_batch" : "op_cholesky");
     if (s->small) return ks_cholesky(s, x, batch, info_host);
@@ -226,10 +236,31 @@ int k_completion(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
     const bool big = use_big(s, batch);
     if (big) a.skipflag = s->big_flag;
     if (launch_tree<OP_COMPL>(s, a, flat_sched(s), batch, pick_threads(s, big), batch > 1 ? "completion_batch" : "completion")) return -1;
-    if (big)
-        for (int64_t b = 0; b < batch; ++b)
-            for (const BigNode &q : s->big)
-                if (big_completion(s, q, x, s->tmp, b)) return -1;
+    if (big) {
+        // The completion of a supernode depends on the INPUT matrix only, so with several
+        // ranks (replicas of the same solve) the supernodes of the top set are shared out round-robin and
+        // every owner broadcasts its block of L: the 27 factorisations of ~1100-row separators of the
+        // rand_SDP pattern run 27/N per rank.  All ranks end with bitwise identical data and verdicts.
+        const int nr = dist_ops(s, batch), rk = ctx->comm_rank;
+        for (int64_t b = 0; b < batch; ++b) {
+            int idx = 0;
+            for (const BigNode &q : s->big) {
+                if (nr == 1 || idx % nr == rk)
+                    if (big_completion(s, q, x, s->tmp, b)) return -1;
+                ++idx;
+            }
+        }
+        if (nr > 1) {
+            if (comm_group_start()) return -1;
+            int idx = 0;
+            for (const BigNode &q : s->big) {
+                if (comm_bcast(ctx, x + q.boff, (size_t)q.nj * q.nn, idx % nr, ctx->stream)) { comm_group_end(); return -1; }
+                ++idx;
+            }
+            if (comm_group_end()) return -1;
+            if (comm_allreduce_max_i32(ctx, s->fail, 1, ctx->stream)) return -1;
+        }
+    }
     if (info_host) return fetch_fail(s, batch, info_host);
     return 0;
 }
@@ -265,9 +296,27 @@ int k_hess_prep_inv(smcp_hess *h) {
     const bool big = use_big(s, 1);
     if (big) a.skipflag = s->big_flag;
     if (launch_tree<OP_HPREP_INV>(s, a, flat_sched(s), 1, pick_threads(s, big), "hessian_prep_inv")) return -1;
-    if (big)
-        for (const BigNode &q : s->big)
-            if (big_hess_prep_inv(s, q, h->Yaa, h->Raa)) return -1;
+    if (big) {
+        // independent per supernode as well: chol(Y_aa) of the top set shared out over the ranks
+        smcp_ctx *ctx = s->ctx;
+        const int nr = dist_ops(s, 1), rk = ctx->comm_rank;
+        int idx = 0;
+        for (const BigNode &q : s->big) {
+            if (nr == 1 || idx % nr == rk)
+                if (big_hess_prep_inv(s, q, h->Yaa, h->Raa)) return -1;
+            ++idx;
+        }
+        if (nr > 1) {
+            if (comm_group_start()) return -1;
+            idx = 0;
+            for (const BigNode &q : s->big) {
+                if (q.na && comm_bcast(ctx, h->Raa + q.uoff, (size_t)q.na * q.na, idx % nr, ctx->stream)) { comm_group_end(); return -1; }
+                ++idx;
+            }
+            if (comm_group_end()) return -1;
+            if (comm_allreduce_max_i32(ctx, s->fail, 1, ctx->stream)) return -1;
+        }
+    }
     return 0;
 }
 

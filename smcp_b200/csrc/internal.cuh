@@ -52,6 +52,7 @@ struct smcp_ctx {
     double *gemm_ws = nullptr;          // split-K partial results
     size_t gemm_ws_cap = 0;
     void *nccl_comm = nullptr;
+    int comm_rank = 0, comm_nranks = 1;   // set by smcp_comm_init
     unsigned *gridbar = nullptr;        // counters of the hand-rolled grid barrier (potrf_tile_kernel)
     unsigned gridbar_next = 0;
     // pinned staging for small host<->device transfers
@@ -244,6 +245,7 @@ int d_potrf(smcp_ctx *ctx, double *H, int64_t ld, int64_t m, int64_t ncols, int3
 int d_potrs(smcp_ctx *ctx, const double *H, int64_t m, double *y_dev);
 // potrs as one thread-block-cluster launch on the inverted 64 x 64 diagonal blocks (potrs_cluster.cu)
 bool potrs_cluster_enabled();
+bool potrs_cluster_for(int64_t m);
 int d_potrs_prepare(smcp_ctx *ctx, const double *H, int64_t m, double *Dinv);
 int d_potrs_cluster(smcp_ctx *ctx, const double *H, int64_t m, const double *Dinv, double *y_dev);
 int launch_gemm_cyc(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
@@ -261,6 +263,12 @@ int trsm_slab(smcp_ctx *ctx, bool trans, const double *L, int64_t ldl, int64_t n
 bool gemm_tma_eligible(const double *A, int64_t lda, const double *B, int64_t ldb, int64_t M, int64_t N, int64_t K);
 int launch_gemm_tma_tn(smcp_ctx *ctx, const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc,
                        int64_t M, int64_t N, int64_t K, double alpha, int accumulate, int tri, int64_t tri_off, const char *name);
+// NCCL helpers on the library's communicator (capi.cu): grouped broadcasts, max-reduction of an int32 flag,
+// in-place all-gather of equal chunks of doubles
+int comm_group_start();
+int comm_group_end();
+int comm_allreduce_max_i32(smcp_ctx *ctx, int *ptr, size_t count, cudaStream_t s);
+int comm_allgather(smcp_ctx *ctx, double *base, size_t chunk, cudaStream_t s);
 // ncclBroadcast of `count` doubles in place on stream s (capi.cu)
 int comm_bcast(smcp_ctx *ctx, double *ptr, size_t count, int root, cudaStream_t s);
 int launch_gemm(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, const double *B, int64_t ldb, double *C,

@@ -203,6 +203,10 @@ bool potrs_cluster_enabled() {
     static const bool off = getenv("SMCP_B200_POTRS_SUBST") && atoi(getenv("SMCP_B200_POTRS_SUBST")) != 0;
     return !off;
 }
+// One cluster (16 SMs at most) streams the whole factor: fine while it sits in L2 and the solve is a
+// latency chain (m = 1000: 0.09 ms against 0.24), slower than the many-SM streamed updates of dense.cu
+// once the factor is hundreds of MB (m = 10^4: 5.1 ms against 3.6)
+bool potrs_cluster_for(int64_t m) { return potrs_cluster_enabled() && m <= 4096; }
 
 int d_potrs_cluster(smcp_ctx *ctx, const double *H, int64_t m, const double *Dinv, double *y_dev) {
     if (m <= 0) return 0;
