@@ -4,8 +4,8 @@ reference ``src/python/base.py``).
 ``SDP`` keeps the reference's data layout — ``A`` CCS ``n^2 x (m+1)`` with column 0 = vec(C)
 and lower-triangular entries only, ``b`` dense — and its three solve entry points on the
 hot path: ``solve_feas`` (``base.py:346-368``), ``solve_esd`` (``316-344``) and
-``solve_phase1`` (``370-470``).  SDPA / pickle I/O, ``solve_cvxopt`` and the robust-LS
-converters are outside the path and not provided.
+``solve_phase1`` (``370-470``), plus SDPA (dat-s) / pickle I/O with the reference's signatures.
+``solve_cvxopt`` and the robust-LS converters are outside the path and not provided.
 
 The generators restate ``band_SDP`` (``base.py:598-636``), ``mtxnorm_SDP`` (``707-778``),
 ``rand_SDP`` (``879-949``) and ``mk_rand`` (``514-560``) with NumPy's ``default_rng``:
@@ -28,9 +28,14 @@ __all__ = ["SDP", "band_SDP", "mtxnorm_SDP", "rand_SDP", "maxcut_SDP", "mk_rand"
 class SDP(object):
     """SDP object: ``n``, ``m``, ``A`` (CCS n^2 x (m+1)), ``b``, aggregate sparsity ``I``."""
 
-    def __init__(self, A=None, b=None, name=None):
-        """``SDP(A, b)`` from problem data, or ``SDP(filename)`` from a sparse SDPA (dat-s) file
-        (``base.py:60-95, 177-195``: the file's primal is negated into SMCP's standard form)."""
+    def __init__(self, A=None, b=None, name=None, filename=None):
+        """``SDP(A, b)`` from problem data, or ``SDP(filename)`` / ``SDP(filename='x.dat-s')`` from a sparse
+        SDPA (dat-s) or pickle file (``base.py:62-85, 177-195``: the file's primal is negated into SMCP's
+        standard form)."""
+        if filename is not None:
+            if A is not None and not isinstance(A, str):
+                raise TypeError("give either problem data or a file name")
+            A = filename
         self._I = None
         self._ischordal = None
         self._blockstruct = None
@@ -87,11 +92,29 @@ class SDP(object):
             f.write(bz2.compress(raw) if compress else raw)
         return fname
 
-    def write_sdpa(self, fname):
-        """Writes the problem as a sparse SDPA file (``base.py:197-215``; one block unless the
-        object was read from a file with a block structure)."""
+    def write_sdpa(self, fname=None, compress=False):
+        """Writes the problem to the sparse SDPA file ``<fname>.dat-s`` (``<fname>`` defaults to the problem
+        name; ``compress=True``: ``<fname>.dat-s.bz2``), refusing to overwrite an existing file
+        (``base.py:197-217``; one block unless the object was read from a file with a block structure).
+        Returns the name of the file written."""
+        import bz2, os
         bs = self._blockstruct if self._blockstruct is not None else np.array([self.n], dtype=np.int64)
+        if fname is None:
+            fname = self._pname
+        if fname is None:
+            raise ValueError("the problem has no name: give a file name")
+        fname += ".dat-s"
+        if os.path.isfile(fname):
+            raise IOError("file %s already exists" % fname)
+        if compress and os.path.isfile(fname + ".bz2"):
+            raise IOError("file %s already exists" % (fname + ".bz2"))
         misc.sdpa_write(fname, self._need(), self.b, bs, neg=True)
+        if compress:
+            with open(fname, "rb") as fi, open(fname + ".bz2", "wb") as fo:
+                fo.write(bz2.compress(fi.read()))
+            os.remove(fname)
+            fname += ".bz2"
+        return fname
 
     def __str__(self):
         return "<SDP: n=%i, m=%i, nnz=%i> %s" % (self.n, self.m, self.nnz, self._pname)
@@ -380,19 +403,24 @@ class mtxnorm_SDP(SDP):
         SDP.__init__(self)
         if type(seed) is not int:
             raise ValueError("seed must be an integer")
-        if not (type(density) is float and 0.0 < density <= 1.0):
-            raise TypeError("density must be a float between 0 and 1")
+        # density: one float for all F_i or a list with one float per F_i (base.py:718-760)
+        if type(density) is float and 0.0 < density <= 1.0:
+            dens = [density] * r
+        elif isinstance(density, (list, tuple)) and len(density) == r and all(0.0 < float(v) <= 1.0 for v in density):
+            dens = [float(v) for v in density]
+        else:
+            raise TypeError("density must be a float between 0 and 1 or a list of r such floats")
         rng = np.random.default_rng(seed)
         n = p + q
         self._p, self._q = p, q
         I1 = np.tile(np.arange(q, n, dtype=np.int64), q)
         J1 = np.repeat(np.arange(q, dtype=np.int64), p)
         Il = misc.sub2ind((n, n), I1, J1)
-        nz = min(max(1, int(round(density * p * q))), p * q)
         rows = [Il]
         cols = [np.zeros(p * q, dtype=np.int64)]
         vals = [rng.standard_normal(p * q)]
         for j in range(1, r + 1):
+            nz = min(max(1, int(round(dens[j - 1] * p * q))), p * q)
             sel = Il if nz == p * q else rng.choice(Il, size=nz, replace=False)
             rows.append(sel)
             cols.append(np.full(nz, j, dtype=np.int64))
@@ -404,7 +432,7 @@ class mtxnorm_SDP(SDP):
                                             shape=(n * n, r + 2)))
         self._b = np.zeros(r + 1)
         self._b[-1] = -1.0
-        self._pname = "mtxnorm_p%i_q%i_r%i_d%s" % (p, q, r, density)
+        self._pname = "mtxnorm_p%i_q%i_r%i_d%s" % (p, q, r, density if type(density) is float else "list")
 
 
 class rand_SDP(SDP):

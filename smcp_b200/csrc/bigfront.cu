@@ -434,14 +434,19 @@ int big_hess_down(smcp_sym *s, const BigNode &q, const double *Lt, double *X, in
 }
 
 // ---- inverse Hessian ----------------------------------------------------------------------
-int big_hess_inv(smcp_sym *s, const BigNode &q, const double *Lt, const double *Raa_all, double *X, int64_t b) {
+// Two phases (every stage but the final extend-add is independent per supernode):
+//   local: reads the supernode's own block and the still-untouched alpha x alpha entries of its ancestors,
+//          leaves K_nn = D M_nn D and K_an = Y_aa^-1 M_an D in the scratch block KS (nn^2 | na x nn);
+//          all supernodes at once, in any order -- with several ranks they are shared out (chordal.cu);
+//   sweep: F_an = K_an + Lt K_nn, F_aa = Lt K_an^T + F_an Lt^T, children's update matrices added, leaves to root.
+int big_hess_inv_local(smcp_sym *s, const BigNode &q, const double *Lt, const double *Raa_all, const double *X, int64_t b, double *KS) {
     smcp_ctx *ctx = s->ctx;
     const int nn = q.nn, na = q.na, nj = q.nj;
-    double *Xb = X + (size_t)b * s->d.nblk;
-    double *blk = Xb + q.boff;
-    double *Uk = s->upd + (size_t)b * s->d.nupd + q.uoff;
+    const double *Xb = X + (size_t)b * s->d.nblk;
+    const double *blk = Xb + q.boff;
     const double *Lb = Lt + q.boff, *Ltan = Lb + nn, *R = Raa_all + q.uoff;
-    double *D = WS(0), *Zaa = WS(1), *Man = WS(2), *Mnn = WS(3), *T = WS(4), *Kan = WS(5);
+    double *D = WS(0), *Zaa = WS(1), *Man = WS(2), *T = WS(4);
+    double *Mnn = KS + q.boff, *Kan = Mnn + (size_t)nn * nn;
     if (G(s, false, false, Lb, nj, Lb, nj, D, nn, nn, nn, nn, 1.0, 0)) return -1;                 // D = L L^T (full)
     ELEM(big_sym_copy_kernel, (long long)nn * nn, blk, nj, Mnn, nn, nn);                          // Z_nn (full)
     if (na) {
@@ -457,6 +462,20 @@ int big_hess_inv(smcp_sym *s, const BigNode &q, const double *Lt, const double *
         if (G(s, false, true, Man, na, D, nn, Kan, na, na, nn, nn, 1.0, 0)) return -1;             // M_an D
         if (d_trsm_left_lower(ctx, false, R, na, na, Kan, na, nn)) return -1;                      // K_an = Y_aa^-1 M_an D
         if (d_trsm_left_lower(ctx, true, R, na, na, Kan, na, nn)) return -1;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int big_hess_inv_sweep(smcp_sym *s, const BigNode &q, const double *Lt, double *X, int64_t b, const double *KS) {
+    smcp_ctx *ctx = s->ctx;
+    const int nn = q.nn, na = q.na, nj = q.nj;
+    double *blk = X + (size_t)b * s->d.nblk + q.boff;
+    double *Uk = s->upd + (size_t)b * s->d.nupd + q.uoff;
+    const double *Ltan = Lt + q.boff + nn;
+    const double *Mnn = KS + q.boff, *Kan = Mnn + (size_t)nn * nn;
+    double *Zaa = WS(1), *Man = WS(2);
+    if (na) {
         ELEM(big_copy_mat_kernel, (long long)na * nn, Kan, na, Man, na, na, nn, 0);
         if (G(s, false, true, Ltan, nj, Mnn, nn, Man, na, na, nn, nn, 1.0, 1)) return -1;          // F_an = K_an + Lt K_nn
         if (G(s, false, false, Ltan, nj, Kan, na, Zaa, na, na, na, nn, 1.0, 0)) return -1;         // F_aa = Lt K_an^T

@@ -150,6 +150,7 @@ extern "C" int smcp_ctx_destroy(smcp_ctx *ctx) {
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);
     if (ctx->gridbar) cudaFree(ctx->gridbar);
+    if (ctx->trs_dinv) cudaFree(ctx->trs_dinv);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
@@ -346,7 +347,9 @@ extern "C" int smcp_sym_destroy(smcp_sym *s) {
     if (s->red) cudaFree(s->red);
     if (s->fbuf) cudaFree(s->fbuf);
     if (s->ch_state) cudaFree(s->ch_state);
+    if (s->probe_buf) cudaFree(s->probe_buf);
     if (s->big_bws) cudaFree(s->big_bws);
+    if (s->big_hinv) cudaFree(s->big_hinv);
     if (s->big_cat) cudaFree(s->big_cat);
     for (auto &b : s->hess_pool) {
         cudaFree(b.Lt); cudaFree(b.Yaa); cudaFree(b.Raa);
@@ -417,13 +420,11 @@ extern "C" int smcp_csp_completion(smcp_sym *s, double *x, int64_t batch, int32_
 extern "C" int smcp_csp_projected_inverse(smcp_sym *s, double *x, int64_t batch) { return k_projinv(s, x, batch); }
 extern "C" int smcp_csp_llt(smcp_sym *s, double *x, int64_t batch) { return k_llt(s, x, batch); }
 
-static double *g_probe_buf = nullptr;
-static size_t g_probe_cap = 0;
 
 extern "C" int smcp_sym_reserve(smcp_sym *s, int64_t batch) {
     if (batch < 1) return 0;
     if (sym_ensure(s, batch, true)) return -1;
-    if (grow((void **)&g_probe_buf, &g_probe_cap, ((size_t)batch * s->d.nblk + batch + 16) * sizeof(double))) return -1;
+    if (grow((void **)&s->probe_buf, &s->probe_cap, ((size_t)batch * s->d.nblk + batch + 16) * sizeof(double))) return -1;
     if (grow((void **)&s->red, &s->red_cap, ((size_t)batch * 40 + 1024) * sizeof(double) + (size_t)s->d.nvp * sizeof(double) + 4096)) return -1;
     return 0;
 }
@@ -432,13 +433,13 @@ extern "C" int smcp_csp_probe(smcp_sym *s, int kind, const double *x, const doub
                               int64_t count, int32_t *info_host, double *sumlogdiag_host) {
     smcp_ctx *ctx = s->ctx;
     if (count <= 0) return 0;
-    if (grow((void **)&g_probe_buf, &g_probe_cap, ((size_t)count * s->d.nblk + count + 16) * sizeof(double))) return -1;
-    double *gam = g_probe_buf + (size_t)count * s->d.nblk;
+    if (grow((void **)&s->probe_buf, &s->probe_cap, ((size_t)count * s->d.nblk + count + 16) * sizeof(double))) return -1;
+    double *gam = s->probe_buf + (size_t)count * s->d.nblk;
     CUDA_TRY(cudaMemcpyAsync(gam, gammas_host, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    if (k_axpy_batch(s, x, dx, gam, g_probe_buf, count)) return -1;
-    int rc = kind == 0 ? k_cholesky(s, g_probe_buf, count, info_host) : k_completion(s, g_probe_buf, count, info_host);
+    if (k_axpy_batch(s, x, dx, gam, s->probe_buf, count)) return -1;
+    int rc = kind == 0 ? k_cholesky(s, s->probe_buf, count, info_host) : k_completion(s, s->probe_buf, count, info_host);
     if (rc) return rc;
-    if (sumlogdiag_host) return k_sumlogdiag(s, g_probe_buf, count, sumlogdiag_host);
+    if (sumlogdiag_host) return k_sumlogdiag(s, s->probe_buf, count, sumlogdiag_host);
     return 0;
 }
 
@@ -1112,7 +1113,7 @@ extern "C" int smcp_kkt_factor(smcp_op *op, int32_t *info_host) {
     {
         RegionScope rs(ctx, "kkt_factor");
         if (d_potrf(ctx, op->H, op->m, op->m, op->m, op->info_dev, 0, 1)) return -1;
-        if (potrs_cluster_for(op->m) && d_potrs_prepare(ctx, op->H, op->m, op->Dinv)) return -1;
+        if (potrs_cluster_for(op->m) && d_potrs_prepare(ctx, op->H, op->m, op->m, op->Dinv)) return -1;
     }
     CUDA_TRY(cudaMemcpyAsync(info_host, op->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1130,7 +1131,7 @@ extern "C" int smcp_kkt_factor_dist(smcp_op *op, int rank, int nranks, int32_t *
     {
         RegionScope rs(ctx, "kkt_factor");
         if (d_potrf(ctx, op->H, op->m, op->m, op->m, op->info_dev, rank, nranks)) return -1;
-        if (potrs_cluster_for(op->m) && d_potrs_prepare(ctx, op->H, op->m, op->Dinv)) return -1;
+        if (potrs_cluster_for(op->m) && d_potrs_prepare(ctx, op->H, op->m, op->m, op->Dinv)) return -1;
     }
     CUDA_TRY(cudaMemcpyAsync(info_host, op->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1146,7 +1147,7 @@ extern "C" int smcp_kkt_factor_block(smcp_op *op, int64_t block, int rank, int n
     {
         RegionScope rs(ctx, "kkt_factor");
         if (d_potrf(ctx, op->H, op->m, op->m, op->m, op->info_dev, rank, nranks, block)) return -1;
-        if (potrs_cluster_for(op->m) && d_potrs_prepare(ctx, op->H, op->m, op->Dinv)) return -1;
+        if (potrs_cluster_for(op->m) && d_potrs_prepare(ctx, op->H, op->m, op->m, op->Dinv)) return -1;
     }
     CUDA_TRY(cudaMemcpyAsync(info_host, op->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));

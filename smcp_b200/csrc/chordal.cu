@@ -355,10 +355,32 @@ int k_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
         h->have_Raa = true;
     }
     if (launch_tree<OP_HINV>(s, a, s->up, batch, threads, batch >= 32 ? "hessian_inv_batch" : "hessian_inv")) return -1;
-    if (big)
-        for (int64_t b = 0; b < batch; ++b)
+    if (big) {
+        // top set: the per-supernode part first (independent: shared out over the ranks of a replicated solve,
+        // results exchanged by grouped broadcasts of nj x nn doubles per supernode), then the leaves-to-root sweep
+        smcp_ctx *ctx = s->ctx;
+        if (grow((void **)&s->big_hinv, &s->big_hinv_cap, (size_t)s->d.nblk * sizeof(double))) return -1;
+        const int nr = dist_ops(s, batch), rk = ctx->comm_rank;
+        for (int64_t b = 0; b < batch; ++b) {
+            int idx = 0;
+            for (const BigNode &q : s->big) {
+                if (nr == 1 || idx % nr == rk)
+                    if (big_hess_inv_local(s, q, h->Lt, h->Raa, U, b, s->big_hinv)) return -1;
+                ++idx;
+            }
+            if (nr > 1) {
+                if (comm_group_start()) return -1;
+                idx = 0;
+                for (const BigNode &q : s->big) {
+                    if (comm_bcast(ctx, s->big_hinv + q.boff, (size_t)q.nj * q.nn, idx % nr, ctx->stream)) { comm_group_end(); return -1; }
+                    ++idx;
+                }
+                if (comm_group_end()) return -1;
+            }
             for (const BigNode &q : s->big)
-                if (big_hess_inv(s, q, h->Lt, h->Raa, U, b)) return -1;
+                if (big_hess_inv_sweep(s, q, h->Lt, U, b, s->big_hinv)) return -1;
+        }
+    }
     return 0;
 }
 

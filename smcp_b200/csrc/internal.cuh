@@ -53,6 +53,8 @@ struct smcp_ctx {
     size_t gemm_ws_cap = 0;
     void *nccl_comm = nullptr;
     int comm_rank = 0, comm_nranks = 1;   // set by smcp_comm_init
+    double *trs_dinv = nullptr;         // inverted diagonal blocks for the few-right-hand-side triangular solves (front.cu)
+    size_t trs_dinv_cap = 0;
     unsigned *gridbar = nullptr;        // counters of the hand-rolled grid barrier (potrf_tile_kernel)
     unsigned gridbar_next = 0;
     // pinned staging for small host<->device transfers
@@ -145,6 +147,8 @@ struct smcp_sym {
     size_t cta_ws_cap = 0;
     double *tmp = nullptr;           // batch x nblk temporary (out-of-place ops)
     size_t tmp_cap = 0;
+    double *probe_buf = nullptr;     // candidates of the batched line-search probes (smcp_csp_probe)
+    size_t probe_cap = 0;
     double *red = nullptr;           // reduction scratch
     size_t red_cap = 0;
     // tiny-clique path (max_nj <= 8): warp-per-chain sweeps, see chordal_small.cu
@@ -164,6 +168,8 @@ struct smcp_sym {
     size_t big_ws_stride = 0;
     int *big_info = nullptr;
     int max_nj_small = 0;        // largest frontal matrix left to the tree kernels when the top set is skipped
+    double *big_hinv = nullptr;                         // inverse Hessian: K_nn | K_an of every top-set supernode (blkval layout)
+    size_t big_hinv_cap = 0;
     double *big_bws = nullptr, *big_cat = nullptr;      // batched top-set workspaces (grown on demand)
     size_t big_bws_cap = 0, big_cat_cap = 0;
     // buffers of destroyed smcp_hess objects, reused by the next one (a new scaling point every IPM
@@ -227,7 +233,8 @@ int big_cholesky(smcp_sym *s, const BigNode &q, double *X, int64_t b);
 int big_llt(smcp_sym *s, const BigNode &q, double *X, int64_t b);
 int big_hess_up(smcp_sym *s, const BigNode &q, const double *Lt, const double *Yaa_all, double *X, int64_t b);
 int big_hess_down(smcp_sym *s, const BigNode &q, const double *Lt, double *X, int64_t b);
-int big_hess_inv(smcp_sym *s, const BigNode &q, const double *Lt, const double *Raa_all, double *X, int64_t b);
+int big_hess_inv_local(smcp_sym *s, const BigNode &q, const double *Lt, const double *Raa_all, const double *X, int64_t b, double *KS);
+int big_hess_inv_sweep(smcp_sym *s, const BigNode &q, const double *Lt, double *X, int64_t b, const double *KS);
 int big_projinv(smcp_sym *s, const BigNode &q, double *X, int64_t b);
 int big_completion(smcp_sym *s, const BigNode &q, double *X, const double *Xin, int64_t b);
 int big_hess_prep(smcp_sym *s, const BigNode &q, const double *L0, const double *Y0, double *Lt_out, double *Yaa_out);
@@ -246,8 +253,10 @@ int d_potrs(smcp_ctx *ctx, const double *H, int64_t m, double *y_dev);
 // potrs as one thread-block-cluster launch on the inverted 64 x 64 diagonal blocks (potrs_cluster.cu)
 bool potrs_cluster_enabled();
 bool potrs_cluster_for(int64_t m);
-int d_potrs_prepare(smcp_ctx *ctx, const double *H, int64_t m, double *Dinv);
+int d_potrs_prepare(smcp_ctx *ctx, const double *H, int64_t ld, int64_t m, double *Dinv);
 int d_potrs_cluster(smcp_ctx *ctx, const double *H, int64_t m, const double *Dinv, double *y_dev);
+int d_trs_cluster(smcp_ctx *ctx, const double *H, int64_t ld, int64_t m, const double *Dinv, double *y_dev, int64_t ldy, int64_t nrhs,
+                  int do_fwd, int do_bwd, const char *name);
 int launch_gemm_cyc(smcp_ctx *ctx, bool ta, bool tb, const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
                     int64_t ldc, int64_t M, int64_t N, int64_t K, double alpha, int accumulate, int tri, int64_t tri_off,
                     const char *name, int jb0, int jbstride, int tpb = 1);

@@ -62,6 +62,9 @@ struct PotrsArgs {
     int m;
     const double *Dinv;
     double *y;
+    long long ldy;      // right-hand sides are columns of y, solved one after the other
+    int nrhs;
+    int do_fwd, do_bwd; // L^-1 and / or L^-T
 };
 
 // 64 x 64 tile times a 64-vector: out[r] (-)= sum_c T(r, c) x[c]; the 256 threads split each row's sum in 4
@@ -172,29 +175,32 @@ __global__ void __launch_bounds__(PC_T, 1) potrs_cluster_kernel(PotrsArgs a) {
     double *ys = pcsm;                  // nloc x 64: the blocks of y this CTA owns
     double *xb = ys + nloc * 64;        // 2 x 64: x of the current step (written by its owner through DSMEM)
     double *part = xb + 128;            // 4 tiles x 4 x 64 partial sums
-    for (int idx = tid; idx < nloc * 64; idx += PC_T) {
-        const int b = (idx >> 6) * R + rk;
-        const long long i = 64LL * b + (idx & 63);
-        ys[idx] = (b < nb && i < a.m) ? a.y[i] : 0.0;
-    }
-    __syncthreads();
     cluster.sync();
-    cluster_sweep<false>(a, cluster, ys, xb, part, nullptr, tid);
-    cluster.sync();
-    cluster_sweep<true>(a, cluster, ys, xb, part, nullptr, tid);
-    __syncthreads();
-    for (int idx = tid; idx < nloc * 64; idx += PC_T) {
-        const int b = (idx >> 6) * R + rk;
-        const long long i = 64LL * b + (idx & 63);
-        if (b < nb && i < a.m) a.y[i] = ys[idx];
+    for (int rhs = 0; rhs < a.nrhs; ++rhs) {
+        double *y = a.y + (long long)rhs * a.ldy;
+        for (int idx = tid; idx < nloc * 64; idx += PC_T) {
+            const int b = (idx >> 6) * R + rk;
+            const long long i = 64LL * b + (idx & 63);
+            ys[idx] = (b < nb && i < a.m) ? y[i] : 0.0;
+        }
+        __syncthreads();
+        if (a.do_fwd) cluster_sweep<false>(a, cluster, ys, xb, part, nullptr, tid);
+        cluster.sync();
+        if (a.do_bwd) cluster_sweep<true>(a, cluster, ys, xb, part, nullptr, tid);
+        __syncthreads();
+        for (int idx = tid; idx < nloc * 64; idx += PC_T) {
+            const int b = (idx >> 6) * R + rk;
+            const long long i = 64LL * b + (idx & 63);
+            if (b < nb && i < a.m) y[i] = ys[idx];
+        }
+        cluster.sync();                 // no CTA may run ahead (or exit) while others still write into its shared memory
     }
-    cluster.sync();                     // no CTA may exit while others still write into its shared memory
 }
 
-int d_potrs_prepare(smcp_ctx *ctx, const double *H, int64_t m, double *Dinv) {
+int d_potrs_prepare(smcp_ctx *ctx, const double *H, int64_t ld, int64_t m, double *Dinv) {
     if (m <= 0) return 0;
     LaunchScope ls(ctx, "potrs_trtri");
-    trtri64_kernel<<<(unsigned)((m + 63) / 64), 64, 0, ctx->stream>>>(H, m, m, Dinv);
+    trtri64_kernel<<<(unsigned)((m + 63) / 64), 64, 0, ctx->stream>>>(H, ld, m, Dinv);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -209,7 +215,14 @@ bool potrs_cluster_enabled() {
 bool potrs_cluster_for(int64_t m) { return potrs_cluster_enabled() && m <= 4096; }
 
 int d_potrs_cluster(smcp_ctx *ctx, const double *H, int64_t m, const double *Dinv, double *y_dev) {
-    if (m <= 0) return 0;
+    return d_trs_cluster(ctx, H, m, m, Dinv, y_dev, m, 1, 1, 1, "potrs");
+}
+
+// L^-1 and / or L^-T applied to a few right-hand sides (columns of y); L lower triangular n x n (leading
+// dimension ld) whose inverted 64 x 64 diagonal blocks are in Dinv (d_potrs_prepare)
+int d_trs_cluster(smcp_ctx *ctx, const double *H, int64_t ld, int64_t m, const double *Dinv, double *y_dev, int64_t ldy, int64_t nrhs,
+                  int do_fwd, int do_bwd, const char *name) {
+    if (m <= 0 || nrhs <= 0) return 0;
     const int nb = (int)((m + 63) / 64);
     int R = nb >= 64 ? 16 : 8;
     if (R > nb) R = std::max(1, nb);
@@ -227,7 +240,8 @@ int d_potrs_cluster(smcp_ctx *ctx, const double *H, int64_t m, const double *Din
     }
     if (smem > 200 * 1024) { smcp_set_error("d_potrs_cluster: m too large"); return -2; }
     PotrsArgs a;
-    a.L = H; a.ld = m; a.m = (int)m; a.Dinv = Dinv; a.y = y_dev;
+    a.L = H; a.ld = ld; a.m = (int)m; a.Dinv = Dinv; a.y = y_dev;
+    a.ldy = ldy; a.nrhs = (int)nrhs; a.do_fwd = do_fwd; a.do_bwd = do_bwd;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)R);
     cfg.blockDim = dim3(PC_T);
@@ -240,7 +254,7 @@ int d_potrs_cluster(smcp_ctx *ctx, const double *H, int64_t m, const double *Din
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    LaunchScope ls(ctx, "potrs", 1, 8.0 * (double)m * (double)m);
+    LaunchScope ls(ctx, name, 1, 4.0 * (double)m * (double)m * (double)nrhs * (do_fwd + do_bwd));
     CUDA_TRY(cudaLaunchKernelEx(&cfg, potrs_cluster_kernel, a));
     return 0;
 }

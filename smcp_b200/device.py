@@ -299,6 +299,10 @@ class DeviceBackend:
         if self.batched_probes and symb.nblk * 255 * 8 <= (1 << 30):
             # workspaces of the batched line-search probes (255 candidates) sized at setup time
             _ck(lib, lib.smcp_sym_reserve(h, 255))
+        elif self.batched_probes:
+            # 255 candidate matrices would not fit the workspace budget: the 8 probes of a bisection run one
+            # after the other (no allocation inside the iterations, no out-of-memory surprise)
+            self.batched_probes = False
         self._pool = []
         # chordal-matrix buffers are recycled through this pool; fill it up front so that no
         # cudaMalloc (a synchronising driver call) happens inside the IPM iterations

@@ -13,6 +13,25 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _cuda_available():
+    try:
+        from smcp_b200.device import Context
+        Context.get()
+        return True
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    # without a CUDA device the gpu tests are skipped (the product path itself still fails loudly: see
+    # test_oracle_drivers.test_product_backend_fails_loudly_without_cuda); `-m gpu` on the box runs them all
+    gpu_items = [it for it in items if "gpu" in it.keywords]
+    if gpu_items and not _cuda_available():
+        skip = pytest.mark.skip(reason="no CUDA device")
+        for it in gpu_items:
+            it.add_marker(skip)
+
+
 @pytest.fixture(autouse=True)
 def _reset_solver_state():
     from smcp_b200 import solvers

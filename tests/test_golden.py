@@ -278,8 +278,9 @@ def test_cuda_driver_traces():
             for c in (2, 3, 4):
                 assert abs(st[k, c] - gt[k, c]) <= 1e-3 * gt[k, c] + 1e-10, (name, k, c, st[k, c], gt[k, c])
         if sol["status"] == "optimal":
+            # two exits inside the tolerance box (abstol = reltol = 1e-6) agree to the box, not better
             for key in ("primal objective", "dual objective"):
-                assert abs(sol[key] - g[key]) <= 1e-7 * max(1.0, abs(g[key])), (name, key, sol[key], g[key])
+                assert abs(sol[key] - g[key]) <= 2e-6 * max(1.0, abs(g[key])), (name, key, sol[key], g[key])
             y = np.asarray(sol["y"]).ravel()
             assert np.linalg.norm(y - np.array(g["y"])) <= 1e-5 * max(1.0, np.linalg.norm(g["y"])), name
         else:

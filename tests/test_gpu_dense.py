@@ -100,7 +100,9 @@ def test_potrf_ill_conditioned():
 
 @pytest.mark.parametrize("trans", [0, 1])
 @pytest.mark.parametrize("n,nrhs", [(1, 1), (5, 3), (63, 8), (64, 9), (65, 1), (130, 17), (200, 200), (1186, 1), (1186, 1186),
-                                    (1131, 9), (2816, 40), (3000, 50)])
+                                    (1131, 9), (2816, 40), (3000, 50),
+                                    # one or two right-hand sides on a large factor: cluster kernel on inverted diagonal blocks
+                                    (300, 1), (1131, 2), (2000, 2), (5000, 1)])
 def test_trsm(n, nrhs, trans):
     """n <= 2816: slab kernel (one launch); above: the blocked launch chain of front.cu."""
     from smcp_b200.device import _ck

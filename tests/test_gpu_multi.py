@@ -21,13 +21,19 @@ def _ngpu():
         return 0
 
 
-@pytest.mark.parametrize("args,block", [(["600", "300", "5"], 128), (["700", "600", "4"], 256), (["rand", "300", "700"], 128)])
-def test_sharded_assembly_and_block_cyclic_factor(args, block):
+@pytest.mark.parametrize("args,block,bignj", [(["600", "300", "5"], 128, None), (["700", "600", "4"], 256, None),
+                                              (["rand", "300", "700"], 128, None),
+                                              # dense top set forced on every supernode with >= 12 rows: completion, chol(Y_aa) and
+                                              # the local phase of the inverse Hessian are shared out over the ranks (NCCL broadcasts)
+                                              (["rand", "300", "700"], 128, "12")])
+def test_sharded_assembly_and_block_cyclic_factor(args, block, bignj):
     n = _ngpu()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
     nproc = 4 if n >= 4 else 2
     env = dict(os.environ, SMCP_BLOCK=str(block), MASTER_ADDR="127.0.0.1")
+    if bignj:
+        env["SMCP_B200_BIG_NJ"] = bignj
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
                           "--master-addr", "127.0.0.1", "--master-port", "29533",
                           os.path.join(ROOT, "scripts", "multi_gpu_check.py")] + args,

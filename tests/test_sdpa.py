@@ -78,11 +78,29 @@ def test_sdpa_roundtrip_and_constructor(tmp_path):
     A = misc.as_csc(sp.csc_matrix((vals, (rows, cols)), shape=(n * n, m + 1)))
     b = rng.standard_normal(m)
     P = S.SDP(A, b)
-    f = str(tmp_path / "rt.dat-s")
-    P.write_sdpa(f)
-    Q = S.SDP(f)
-    assert Q.n == n and Q.m == m
-    assert np.allclose(Q.b, b, rtol=1e-11) and abs(Q.A - A).max() <= 1e-11 * abs(A).max()
+    # the reference's signature (base.py:197-217): write_sdpa(fname=None, compress=False) appends '.dat-s'
+    # (and '.bz2'), defaults to the problem name and refuses to overwrite
+    f = P.write_sdpa(str(tmp_path / "rt"))
+    assert f == str(tmp_path / "rt.dat-s")
+    for Q in (S.SDP(f), S.SDP(filename=f)):
+        assert Q.n == n and Q.m == m
+        assert np.allclose(Q.b, b, rtol=1e-11) and abs(Q.A - A).max() <= 1e-11 * abs(A).max()
+    with pytest.raises(IOError):
+        P.write_sdpa(str(tmp_path / "rt"))
+    fz = P.write_sdpa(str(tmp_path / "rtz"), compress=True)
+    assert fz.endswith(".dat-s.bz2") and not os.path.exists(fz[:-4])
+    Qz = S.SDP(fz)
+    assert abs(Qz.A - A).max() <= 1e-11 * abs(A).max()
+    with pytest.raises(IOError):
+        P.write_sdpa(str(tmp_path / "rtz"), compress=True)
+    with pytest.raises(ValueError):
+        P.write_sdpa()                       # unnamed problem, no file name
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        assert S.SDP(A, b, name="named").write_sdpa() == "named.dat-s"
+    finally:
+        os.chdir(cwd)
 
 
 def test_sdp_from_bz2_and_counts(sdpa_file, tmp_path):
