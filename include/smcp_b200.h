@@ -208,6 +208,11 @@ int smcp_host_embed(int64_t n, const int64_t *colptr, const int64_t *rowind, int
  * supernode arrays of smcp_sym_desc; nn = columns and nj = rows of every supernode */
 int smcp_host_aaidx(int64_t nsn, const int64_t *snpar, const int64_t *nn, const int64_t *nj, const int64_t *relptr,
                     const int64_t *relidx, const int64_t *blkptr, const int64_t *updptr, int64_t *aaidx);
+/* supernode partition (maximal supernodes, first-qualifying-child rule), post-ordered relabelling, row lists and
+ * relative indices of a filled pattern in a perfect elimination ordering: chompack.symbolic (solvers.py:314, 1555).
+ * Caller-allocated outputs: perm[n], snptr[n+1], snpar[n], rowptr[n+1], rowidx[n + nnz], relptr[n+1], relidx[nnz]. */
+int smcp_host_supernodes(int64_t n, const int64_t *colptr, const int64_t *rowind, int64_t *nsn_out, int64_t *perm,
+                         int64_t *snptr, int64_t *snpar, int64_t *rowptr, int64_t *rowidx, int64_t *relptr, int64_t *relidx);
 
 /* ---- the dense LAPACK/BLAS calls of the path on host buffers (column-major) -----------------
  * Parity tests and micro-benchmarks of the kernels behind smcp_kkt_factor / smcp_kkt_solve and the

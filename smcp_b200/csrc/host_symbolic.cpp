@@ -226,4 +226,117 @@ int smcp_host_aaidx(int64_t nsn, const int64_t *snpar, const int64_t *nn, const 
     return 0;
 }
 
+// Post-order of a forest (parent = -1: root), children visited in increasing index order -- the rule of
+// smcp_b200/symbolic.py:_postorder.
+static void forest_postorder(int64_t n, const int64_t *parent, std::vector<int64_t> &post) {
+    std::vector<int64_t> head(n, -1), next(n, -1), tail(n, -1), roots;
+    for (int64_t v = 0; v < n; ++v) {
+        const int64_t p = parent[v];
+        if (p < 0) { roots.push_back(v); continue; }
+        if (head[p] < 0) head[p] = v; else next[tail[p]] = v;
+        tail[p] = v;
+    }
+    post.clear();
+    post.reserve(n);
+    std::vector<int64_t> stack, cur(head);
+    for (int64_t r : roots) {
+        stack.push_back(r);
+        while (!stack.empty()) {
+            const int64_t v = stack.back();
+            const int64_t c = cur[v];
+            if (c >= 0) {
+                cur[v] = next[c];
+                stack.push_back(c);
+            } else {
+                post.push_back(v);
+                stack.pop_back();
+            }
+        }
+    }
+}
+
+// Supernode partition, post-ordered relabelling, row lists and relative indices of a filled (chordal)
+// pattern given in a perfect elimination ordering: the native twin of the first half of
+// smcp_b200/symbolic.py:Symbolic.__init__ (maximal supernodes, Pothen-Sun first-qualifying-child rule;
+// stand-in for chompack.symbolic, solvers.py:314, 1555).  Outputs (caller-allocated): nsn; perm[n];
+// snptr[n+1]; snpar[n]; rowptr[n+1]; rowidx[n + nnz]; relptr[n+1]; relidx[nnz].  Bit-identical to the
+// NumPy specification (tests/test_host_symbolic.py).  Returns -2 when the pattern is not chordal in this order.
+int smcp_host_supernodes(int64_t n, const int64_t *colptr, const int64_t *rowind, int64_t *nsn_out, int64_t *perm,
+                         int64_t *snptr, int64_t *snpar, int64_t *rowptr, int64_t *rowidx, int64_t *relptr, int64_t *relidx) {
+    if (n < 0 || !colptr || !nsn_out) return -1;
+    std::vector<int64_t> parent(n, -1), colcount(n);
+    for (int64_t j = 0; j < n; ++j) {
+        colcount[j] = colptr[j + 1] - colptr[j];
+        if (colcount[j] < 1 || rowind[colptr[j]] != j) return -2;          // diagonal first
+        if (colcount[j] > 1) parent[j] = rowind[colptr[j] + 1];
+    }
+    std::vector<int64_t> post;
+    forest_postorder(n, parent.data(), post);
+    std::vector<int64_t> rep(n, -1);
+    for (int64_t j : post) {
+        if (rep[j] < 0) rep[j] = j;
+        const int64_t pj = parent[j];
+        if (pj >= 0 && rep[pj] < 0 && colcount[j] - 1 == colcount[pj]) rep[pj] = rep[j];
+    }
+    // supernodes numbered by increasing representative; members in path order (the post-order visits them so)
+    std::vector<int64_t> snid(n, -1);
+    int64_t nsn = 0;
+    for (int64_t v = 0; v < n; ++v)
+        if (rep[v] == v) snid[v] = nsn++;
+    std::vector<int64_t> cnt(nsn + 1, 0);
+    for (int64_t v = 0; v < n; ++v) ++cnt[snid[rep[v]] + 1];
+    for (int64_t k = 0; k < nsn; ++k) cnt[k + 1] += cnt[k];
+    std::vector<int64_t> mem(n), fill(cnt.begin(), cnt.end() - 1);
+    for (int64_t j : post) mem[fill[snid[rep[j]]]++] = j;
+    std::vector<int64_t> snpar0(nsn, -1);
+    for (int64_t k = 0; k < nsn; ++k) {
+        const int64_t top = mem[cnt[k + 1] - 1];
+        if (parent[top] >= 0) snpar0[k] = snid[rep[parent[top]]];
+    }
+    std::vector<int64_t> snpost;
+    forest_postorder(nsn, snpar0.data(), snpost);
+    std::vector<int64_t> renum(nsn);
+    for (int64_t knew = 0; knew < nsn; ++knew) renum[snpost[knew]] = knew;
+    std::vector<int64_t> iperm(n);
+    int64_t k0 = 0;
+    snptr[0] = 0;
+    for (int64_t knew = 0; knew < nsn; ++knew) {
+        const int64_t kold = snpost[knew];
+        for (int64_t q = cnt[kold]; q < cnt[kold + 1]; ++q) {
+            perm[k0] = mem[q];
+            iperm[mem[q]] = k0;
+            ++k0;
+        }
+        snptr[knew + 1] = k0;
+        snpar[knew] = snpar0[kold] >= 0 ? renum[snpar0[kold]] : -1;
+    }
+    rowptr[0] = 0;
+    relptr[0] = 0;
+    for (int64_t k = 0; k < nsn; ++k) {
+        const int64_t nn = snptr[k + 1] - snptr[k];
+        const int64_t top = perm[snptr[k + 1] - 1];
+        const int64_t na = colcount[top] - 1;
+        int64_t *r = rowidx + rowptr[k];
+        for (int64_t i = 0; i < nn; ++i) r[i] = snptr[k] + i;
+        for (int64_t i = 0; i < na; ++i) r[nn + i] = iperm[rowind[colptr[top] + 1 + i]];
+        std::sort(r + nn, r + nn + na);
+        rowptr[k + 1] = rowptr[k] + nn + na;
+        relptr[k + 1] = relptr[k] + na;
+    }
+    for (int64_t k = 0; k < nsn; ++k) {
+        const int64_t pk = snpar[k];
+        if (pk < 0) continue;
+        const int64_t nn = snptr[k + 1] - snptr[k], na = rowptr[k + 1] - rowptr[k] - nn;
+        const int64_t *a = rowidx + rowptr[k] + nn;
+        const int64_t *g = rowidx + rowptr[pk], *gend = rowidx + rowptr[pk + 1];
+        for (int64_t i = 0; i < na; ++i) {
+            const int64_t *it = std::lower_bound(g, gend, a[i]);
+            if (it == gend || *it != a[i]) return -2;
+            relidx[relptr[k] + i] = it - g;
+        }
+    }
+    *nsn_out = nsn;
+    return 0;
+}
+
 }  // extern "C"

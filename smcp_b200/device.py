@@ -101,6 +101,7 @@ API = {
     "smcp_host_maxcardsearch": (_int, [_i64, _i64p, _i64p, _i64p]),
     "smcp_host_embed": (_int, [_i64, _i64p, _i64p, _i64p, C.c_void_p, C.c_void_p]),
     "smcp_host_aaidx": (_int, [_i64, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p]),
+    "smcp_host_supernodes": (_int, [_i64, _i64p, _i64p, C.POINTER(_i64), _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p]),
 }
 
 

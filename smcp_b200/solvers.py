@@ -27,7 +27,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from . import misc
-from .symbolic import Symbolic, embed, maxcardsearch, min_degree, lower_pattern
+from .symbolic import Symbolic, amalgamate, embed, maxcardsearch, min_degree, lower_pattern
 from .chordal import (cspmatrix, cholesky, completion, projected_inverse, llt, hessian,
                       hessian_norm, dot, schur_token)
 
@@ -40,6 +40,8 @@ options = {
     "show_progress": True, "dimacs": True, "eta": None, "delta": 0.9, "alpha": 1e-1,
     "beta": 0.7, "minstep": 1e-8, "lifting": True, "t0": 1e-1, "equalsteps": True,
     "prediction": True, "step": 0.98,
+    # extension (not in the reference): relaxed supernodes, see smcp_b200.symbolic.amalgamate; 0 = the reference's pattern
+    "amalgamation": 0.0,
 }
 
 _backend_factory = None
@@ -105,6 +107,9 @@ def _read_options(n, feas):
     o.tnzcols = int(n * tz)
     o.dimacs = g["dimacs"]
     _check(type(o.dimacs) is bool, TypeError, "dimacs must be a bool")
+    o.amalgamation = g.get("amalgamation", 0.0)
+    _check(type(o.amalgamation) in (float, int) and 0.0 <= o.amalgamation < 1.0, ValueError,
+           "options['amalgamation'] must be a number in [0, 1)")
     if feas:
         o.alpha = g["alpha"]
         _check(type(o.alpha) is float and 0.0 < o.alpha < 0.5, TypeError,
@@ -190,6 +195,10 @@ class _Problem:
             _check(len(p) == n and np.array_equal(np.sort(p), np.arange(n)), ValueError,
                    "p must be a permutation of 0..n-1")
             fc, fr, _ = embed(n, va_colptr, va_rowind, p)
+        if opt.amalgamation > 0.0:
+            # opt-in: merge supernodes into their parents (explicit zeros in exchange for larger dense blocks);
+            # the embedding stays a filled pattern in the same elimination ordering
+            fc, fr = amalgamate(n, fc, fr, float(opt.amalgamation))
         self.p = p
         self.ip = np.empty(n, dtype=np.int64)
         self.ip[p] = np.arange(n, dtype=np.int64)

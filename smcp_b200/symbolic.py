@@ -311,6 +311,122 @@ def _py_aaidx(nsn, snpar, nn, na, nj, relptr, relidx, blkptr, updptr, nupd):
     return aaidx
 
 
+def amalgamate(n, colptr, rowind, tol):
+    """Relaxed supernodes (an OPT-IN performance knob: ``solvers.options['amalgamation']``):
+    greedy post-order merging of a supernode into its parent whenever the explicit zeros this stores,
+    ``nn_child * (nj_parent - na_child)``, are at most ``tol`` times the entries of the merged block.  Input
+    and output are filled patterns in the SAME perfect elimination ordering; the output contains the input.
+    A merged clique is ``nu_child + nu_parent + alpha_parent``, so on the band pattern (4995 blocks of 6 x 1)
+    ``tol = 0.3`` gives ~1000 blocks of ~10 x 5.  The enlarged pattern changes the cone the barrier lives on,
+    hence the iterates: the default (0) keeps the reference's pattern bit for bit."""
+    if tol <= 0.0:
+        return colptr, rowind
+    symb = Symbolic(n, colptr, rowind)
+    nsn = symb.nsn
+    perm = symb.perm
+    members = [list(perm[symb.snptr[k]:symb.snptr[k + 1]]) for k in range(nsn)]       # Vp indices
+    alpha = [perm[symb.rowidx[symb.rowptr[k] + symb.nn[k]:symb.rowptr[k + 1]]] for k in range(nsn)]
+    nnc = symb.nn.astype(np.int64).copy()
+    njc = symb.nj.astype(np.int64).copy()
+    zacc = np.zeros(nsn, dtype=np.int64)         # explicit zeros already stored in a (merged) supernode
+    for k in range(nsn):                         # post-order: children first; a child may have absorbed its own children
+        pk = int(symb.snpar[k])
+        if pk < 0:
+            continue
+        na_k = njc[k] - nnc[k]
+        zeros = zacc[k] + zacc[pk] + nnc[k] * (njc[pk] - na_k)
+        if zeros <= tol * (nnc[k] + nnc[pk]) * (njc[pk] + nnc[k]):
+            members[pk] = members[k] + members[pk]
+            members[k] = None
+            nnc[pk] += nnc[k]
+            njc[pk] += nnc[k]
+            zacc[pk] = zeros
+    newcols = [None] * n
+    for k in range(nsn):
+        if members[k] is None:
+            continue
+        mem = np.sort(np.asarray(members[k], dtype=np.int64))
+        al = np.sort(np.asarray(alpha[k], dtype=np.int64))
+        for t, j in enumerate(mem):
+            newcols[int(j)] = np.concatenate([mem[t:], al])
+    ncolptr = np.zeros(n + 1, dtype=np.int64)
+    ncolptr[1:] = np.cumsum([len(c) for c in newcols])
+    return ncolptr, np.concatenate(newcols).astype(np.int64)
+
+
+def _py_supernodes(n, colptr, rowind, parent):
+    """NumPy specification of ``smcp_host_supernodes`` (csrc/host_symbolic.cpp): maximal supernodes with the
+    Pothen-Sun first-qualifying-child rule, supernodes in post-order with contiguous columns, row lists
+    (own columns, then the separator ascending) and the positions of every separator in its parent's row list."""
+    colcount = np.diff(colptr)
+    post = _postorder(parent)
+    rep = np.full(n, -1, dtype=np.int64)      # representative (first vertex) of v's supernode
+    for j in post:
+        if rep[j] < 0:
+            rep[j] = j
+        pj = parent[j]
+        if pj >= 0 and rep[pj] < 0 and colcount[j] - 1 == colcount[pj]:
+            rep[pj] = rep[j]
+    # chains: vertices of a supernode in path order (child -> parent); post-order visits
+    # a path's vertices in that order
+    members = {}
+    for j in post:
+        members.setdefault(int(rep[j]), []).append(int(j))
+    reps = sorted(members.keys())
+    sn_of_rep = {r: k for k, r in enumerate(reps)}
+    nsn = len(reps)
+    snpar0 = np.full(nsn, -1, dtype=np.int64)
+    for k, r in enumerate(reps):
+        top = members[r][-1]
+        if parent[top] >= 0:
+            snpar0[k] = sn_of_rep[int(rep[parent[top]])]
+    snpost = _postorder(snpar0)
+    renum = np.empty(nsn, dtype=np.int64)
+    renum[snpost] = np.arange(nsn, dtype=np.int64)
+    snptr = np.zeros(nsn + 1, dtype=np.int64)
+    perm = np.empty(n, dtype=np.int64)        # internal index -> Vp index
+    k0 = 0
+    for knew, kold in enumerate(snpost):
+        mem = members[reps[kold]]
+        perm[k0:k0 + len(mem)] = mem
+        k0 += len(mem)
+        snptr[knew + 1] = k0
+    iperm = np.empty(n, dtype=np.int64)
+    iperm[perm] = np.arange(n, dtype=np.int64)
+    snpar = np.full(nsn, -1, dtype=np.int64)
+    snpar[renum] = np.where(snpar0 >= 0, renum[np.maximum(snpar0, 0)], -1)
+    nn = np.diff(snptr)
+    # separator = structure of the last (top) vertex of the chain
+    top = perm[snptr[1:] - 1] if nsn else np.zeros(0, dtype=np.int64)
+    na = colcount[top] - 1
+    nj = nn + na
+    rowptr = np.zeros(nsn + 1, dtype=np.int64)
+    rowptr[1:] = np.cumsum(nj)
+    rowidx = np.empty(rowptr[-1], dtype=np.int64)
+    for k in range(nsn):
+        r0 = rowptr[k]
+        rowidx[r0:r0 + nn[k]] = np.arange(snptr[k], snptr[k + 1])
+        t = top[k]
+        a = iperm[rowind[colptr[t] + 1:colptr[t + 1]]]
+        a.sort()
+        rowidx[r0 + nn[k]:rowptr[k + 1]] = a
+    # relative indices: alpha_k inside gamma_parent
+    relptr = np.zeros(nsn + 1, dtype=np.int64)
+    relptr[1:] = np.cumsum(na)
+    relidx = np.empty(relptr[-1], dtype=np.int64)
+    for k in range(nsn):
+        pk = snpar[k]
+        if pk < 0:
+            continue
+        a = rowidx[rowptr[k] + nn[k]:rowptr[k + 1]]
+        g = rowidx[rowptr[pk]:rowptr[pk + 1]]
+        pos = np.searchsorted(g, a)
+        if np.any(pos >= len(g)) or np.any(g[np.minimum(pos, len(g) - 1)] != a):  # pragma: no cover
+            raise ValueError("pattern is not chordal in the given ordering")
+        relidx[relptr[k]:relptr[k + 1]] = pos
+    return nsn, perm, snptr, snpar, rowptr, rowidx, relptr, relidx
+
+
 class Symbolic:
     """Supernodal clique tree of a *chordal* lower-triangular pattern given in a perfect
     elimination ordering (the ``symb = symbolic(Vp)`` object of ``solvers.py:314, 1555``).
@@ -348,73 +464,40 @@ class Symbolic:
         has = colcount > 1
         parent[has] = rowind[colptr[:-1][has] + 1]
         self.parent = parent
-        post = _postorder(parent)
-        self.post = post
 
-        # --- maximal supernodes (Pothen–Sun): parent joins first qualifying child -------
-        rep = np.full(n, -1, dtype=np.int64)      # representative (first vertex) of v's supernode
-        for j in post:
-            if rep[j] < 0:
-                rep[j] = j
-            pj = parent[j]
-            if pj >= 0 and rep[pj] < 0 and colcount[j] - 1 == colcount[pj]:
-                rep[pj] = rep[j]
-        # chains: vertices of a supernode in path order (child -> parent); post-order visits
-        # a path's vertices in that order
-        members = {}
-        for j in post:
-            members.setdefault(int(rep[j]), []).append(int(j))
-        reps = sorted(members.keys())
-        sn_of_rep = {r: k for k, r in enumerate(reps)}
-        nsn0 = len(reps)
-        snpar0 = np.full(nsn0, -1, dtype=np.int64)
-        for k, r in enumerate(reps):
-            top = members[r][-1]
-            if parent[top] >= 0:
-                snpar0[k] = sn_of_rep[int(rep[parent[top]])]
-        snpost = _postorder(snpar0)
-        renum = np.empty(nsn0, dtype=np.int64)
-        renum[snpost] = np.arange(nsn0, dtype=np.int64)
-
-        nsn = nsn0
+        # supernode partition, post-ordered relabelling, row lists, relative indices: native when the
+        # library is built (csrc/host_symbolic.cpp: smcp_host_supernodes), else the NumPy specification
+        lib = _native()
+        if lib is not None:
+            import ctypes
+            nsn_c = ctypes.c_int64(0)
+            perm = np.empty(n, dtype=np.int64)
+            snptr = np.empty(n + 1, dtype=np.int64)
+            snpar = np.empty(max(n, 1), dtype=np.int64)
+            rowptr = np.empty(n + 1, dtype=np.int64)
+            rowidx = np.empty(n + self.nvp, dtype=np.int64)
+            relptr = np.empty(n + 1, dtype=np.int64)
+            relidx = np.empty(max(self.nvp, 1), dtype=np.int64)
+            rc = lib.smcp_host_supernodes(n, _i64(colptr), _i64(rowind), ctypes.byref(nsn_c), perm, snptr, snpar, rowptr,
+                                          rowidx, relptr, relidx)
+            if rc == -2:
+                raise ValueError("pattern is not chordal in the given ordering")
+            if rc != 0:
+                raise RuntimeError("smcp_host_supernodes failed")
+            nsn = int(nsn_c.value)
+            snptr, snpar, rowptr, relptr = snptr[:nsn + 1].copy(), snpar[:nsn].copy(), rowptr[:nsn + 1].copy(), relptr[:nsn + 1].copy()
+            rowidx, relidx = rowidx[:rowptr[-1]].copy(), relidx[:relptr[-1]].copy()
+        else:
+            nsn, perm, snptr, snpar, rowptr, rowidx, relptr, relidx = _py_supernodes(n, colptr, rowind, parent)
         self.nsn = nsn
-        snptr = np.zeros(nsn + 1, dtype=np.int64)
-        perm = np.empty(n, dtype=np.int64)        # internal index -> Vp index
-        k0 = 0
-        for knew, kold in enumerate(snpost):
-            mem = members[reps[kold]]
-            perm[k0:k0 + len(mem)] = mem
-            k0 += len(mem)
-            snptr[knew + 1] = k0
         iperm = np.empty(n, dtype=np.int64)
         iperm[perm] = np.arange(n, dtype=np.int64)
-        self.perm = perm
-        self.iperm = iperm
-        self.snptr = snptr
-        snpar = np.full(nsn, -1, dtype=np.int64)
-        snpar[renum] = np.where(snpar0 >= 0, renum[np.maximum(snpar0, 0)], -1)
-        self.snpar = snpar
-
+        self.perm, self.iperm, self.snptr, self.snpar = perm, iperm, snptr, snpar
         nn = np.diff(snptr)
-        # separator = structure of the last (top) vertex of the chain
-        top = perm[snptr[1:] - 1]
-        na = colcount[top] - 1
-        nj = nn + na
-        self.nn = nn
-        self.na = na
-        self.nj = nj
-        rowptr = np.zeros(nsn + 1, dtype=np.int64)
-        rowptr[1:] = np.cumsum(nj)
-        rowidx = np.empty(rowptr[-1], dtype=np.int64)
-        for k in range(nsn):
-            r0 = rowptr[k]
-            rowidx[r0:r0 + nn[k]] = np.arange(snptr[k], snptr[k + 1])
-            t = top[k]
-            a = iperm[rowind[colptr[t] + 1:colptr[t + 1]]]
-            a.sort()
-            rowidx[r0 + nn[k]:rowptr[k + 1]] = a
-        self.rowptr = rowptr
-        self.rowidx = rowidx
+        nj = np.diff(rowptr)
+        na = nj - nn
+        self.nn, self.na, self.nj = nn, na, nj
+        self.rowptr, self.rowidx, self.relptr, self.relidx = rowptr, rowidx, relptr, relidx
         blkptr = np.zeros(nsn + 1, dtype=np.int64)
         blkptr[1:] = np.cumsum(nj * nn)
         self.blkptr = blkptr
@@ -429,32 +512,10 @@ class Symbolic:
         haspar = snpar >= 0
         np.add.at(chptr, snpar[haspar] + 1, 1)
         chptr = np.cumsum(chptr)
-        chidx = np.empty(chptr[-1], dtype=np.int64)
-        fill = chptr[:-1].copy()
-        for k in range(nsn):
-            pk = snpar[k]
-            if pk >= 0:
-                chidx[fill[pk]] = k
-                fill[pk] += 1
+        kids = np.nonzero(haspar)[0]
+        chidx = kids[np.argsort(snpar[kids], kind="stable")].astype(np.int64)
         self.chptr = chptr
         self.chidx = chidx
-
-        # relative indices: alpha_k inside gamma_parent
-        relptr = np.zeros(nsn + 1, dtype=np.int64)
-        relptr[1:] = np.cumsum(na)
-        relidx = np.empty(relptr[-1], dtype=np.int64)
-        for k in range(nsn):
-            pk = snpar[k]
-            if pk < 0:
-                continue
-            a = rowidx[rowptr[k] + nn[k]:rowptr[k + 1]]
-            g = rowidx[rowptr[pk]:rowptr[pk + 1]]
-            pos = np.searchsorted(g, a)
-            if np.any(g[pos] != a):  # pragma: no cover
-                raise ValueError("pattern is not chordal in the given ordering")
-            relidx[relptr[k]:relptr[k + 1]] = pos
-        self.relptr = relptr
-        self.relidx = relidx
 
         # height (leaves 0) and depth (roots 0) levels
         height = np.zeros(nsn, dtype=np.int64)

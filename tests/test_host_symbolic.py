@@ -67,3 +67,39 @@ def test_native_aaidx_matches_python(n, ne, band, seed):
     ref = sy._py_aaidx(symb.nsn, symb.snpar, symb.nn, symb.na, symb.nj, symb.relptr, symb.relidx, symb.blkptr,
                        symb.updptr, symb.nupd)
     assert symb.aaidx.dtype == np.int64 and np.array_equal(symb.aaidx, ref)
+
+
+@pytest.mark.parametrize("n,ne,band,seed", [(1, 0, 0, 0), (30, 40, 0, 2), (200, 300, 1, 3), (300, 2000, 0, 5), (150, 0, 3, 6), (64, 0, 0, 7)])
+def test_native_supernodes_match_python(n, ne, band, seed, monkeypatch):
+    """smcp_host_supernodes (partition, post-ordered relabelling, row lists, relative indices) against the NumPy
+    specification: every array of the Symbolic object bit-identical."""
+    cp, ri = _random_pattern(n, ne, seed, band)
+    p = sy.min_degree(n, cp, ri)
+    fc, fr, _ = sy.embed(n, cp, ri, p)
+    a = sy.Symbolic(n, fc, fr)
+    monkeypatch.setenv("SMCP_B200_NO_NATIVE_HOST", "1")
+    b = sy.Symbolic(n, fc, fr)
+    for k in ("nsn", "perm", "iperm", "snptr", "snpar", "rowptr", "rowidx", "relptr", "relidx", "chptr", "chidx", "blkptr",
+              "updptr", "aaidx", "vec2blk", "height", "depth", "diag_blk"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+
+
+def test_amalgamation_is_a_chordal_superset():
+    """Opt-in relaxed supernodes: the merged pattern contains the original, is still a filled pattern in the same
+    ordering (Symbolic accepts it), and has fewer, larger supernodes; tol = 0 is the identity."""
+    n = 400
+    cp, ri = _random_pattern(n, 0, 0, band=5)
+    assert sy.amalgamate(n, cp, ri, 0.0)[0] is cp
+    s0 = sy.Symbolic(n, cp, ri)
+    cp2, ri2 = sy.amalgamate(n, cp, ri, 0.3)
+    s1 = sy.Symbolic(n, cp2, ri2)
+    assert s1.nsn < s0.nsn // 3 and s1.nn.max() >= 3
+    old = set(zip(np.repeat(np.arange(n), np.diff(cp)).tolist(), ri.tolist()))
+    new = set(zip(np.repeat(np.arange(n), np.diff(cp2)).tolist(), ri2.tolist()))
+    assert old <= new and len(new) < 2 * len(old)
+    cp3, ri3 = _random_pattern(120, 150, 3, band=1)
+    p = sy.min_degree(120, cp3, ri3)
+    fc, fr, _ = sy.embed(120, cp3, ri3, p)
+    fc2, fr2 = sy.amalgamate(120, fc, fr, 0.2)
+    s2 = sy.Symbolic(120, fc2, fr2)                 # raises if the merged pattern were not chordal in this order
+    assert s2.nsn <= sy.Symbolic(120, fc, fr).nsn
