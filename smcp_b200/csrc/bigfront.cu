@@ -294,7 +294,40 @@ int big_setup(smcp_sym *s, const smcp_sym_desc *D) {
     CUDA_TRY(cudaMemcpy(d, flag.data(), (size_t)nsn * sizeof(int), cudaMemcpyHostToDevice));
     s->allocs.push_back(d);
     s->big_flag = (const int *)d;
-    CUDA_TRY(cudaMalloc(&d, (size_t)BIG_NWS * max_nj_big * max_nj_big * sizeof(double) + 64));
+    // levels of the top set's own tree: supernodes of equal height (depth) are independent in the
+    // leaves-to-root (root-to-leaves) sweeps -- each reads its children's update matrices (its ancestors'
+    // blocks) and writes its own block only
+    {
+        const int nb = (int)s->big.size();
+        std::vector<int> pos(nsn, -1), ht(nb, 0), dp(nb, 0);
+        for (int i = 0; i < nb; ++i) pos[s->big[i].k] = i;
+        int maxh = 0, maxd = 0;
+        for (int i = 0; i < nb; ++i) {
+            const int p = (int)D->snpar[s->big[i].k];
+            if (p >= 0) { ht[pos[p]] = std::max(ht[pos[p]], ht[i] + 1); maxh = std::max(maxh, ht[pos[p]]); }
+        }
+        for (int i = nb - 1; i >= 0; --i) {
+            const int p = (int)D->snpar[s->big[i].k];
+            if (p >= 0) { dp[i] = dp[pos[p]] + 1; maxd = std::max(maxd, dp[i]); }
+        }
+        s->big_up.assign(maxh + 1, std::vector<int>());
+        s->big_down.assign(maxd + 1, std::vector<int>());
+        for (int i = 0; i < nb; ++i) s->big_up[ht[i]].push_back(i);
+        for (int i = nb - 1; i >= 0; --i) s->big_down[dp[i]].push_back(i);
+    }
+    // lanes: the independent per-supernode operations of a top set of moderate fronts run on a few streams at once
+    // (one of the ~1100-row factorisations of the rand_SDP separators keeps at most 18 of the 148 SMs busy in
+    // its panel phase); SMCP_B200_LANES = 1 turns this off
+    {
+        const char *envl = getenv("SMCP_B200_LANES");
+        int nl = envl ? atoi(envl) : 8;
+        const size_t per_lane = (size_t)BIG_NWS * max_nj_big * max_nj_big * sizeof(double);
+        if (nl < 1 || s->big.size() < 2) nl = 1;
+        if (!envl && (s->big.size() < 4 || max_nj_big > 2560 || max_nj_big < 128)) nl = 1;    // an explicit setting is obeyed (tests)
+        while (nl > 1 && per_lane * nl > ((size_t)4 << 30)) --nl;
+        s->big_nlanes = std::min(nl, 16);
+    }
+    CUDA_TRY(cudaMalloc(&d, (size_t)s->big_nlanes * BIG_NWS * max_nj_big * max_nj_big * sizeof(double) + 64));
     s->allocs.push_back(d);
     s->big_ws = (double *)d;
     s->big_ws_stride = (size_t)max_nj_big * max_nj_big;
@@ -316,7 +349,8 @@ static BigArgs big_args(smcp_sym *s, const BigNode &q, int64_t b) {
     return r;
 }
 
-#define WS(i) (s->big_ws + (size_t)(i) * s->big_ws_stride)
+#define WS(i) (s->big_ws + ((size_t)s->big_lane * BIG_NWS + (i)) * s->big_ws_stride)
+#define BIG_INFO (s->big_info + s->big_lane)
 #define ELEM(name, total, ...)                                                      \
     do {                                                                            \
         LaunchScope ls_(ctx, "front_elem");                                         \
@@ -345,6 +379,21 @@ static int G(smcp_sym *s, bool ta, bool tb, const double *A, int64_t lda, const 
     return launch_gemm(s->ctx, ta, tb, A, lda, B, ldb, C, ldc, M, N, K, alpha, acc, tri, 0, "front_gemm_dmma");
 }
 
+// ---- lanes over the top set ---------------------------------------------------------------------
+int big_lanes_begin(smcp_sym *s) {
+    const int nl = (s->ctx->prof || s->ctx->lanes_active) ? 1 : s->big_nlanes;
+    if (nl > 1 && lanes_fork(s->ctx, nl)) return -1;
+    return nl;
+}
+void big_lane_pick(smcp_sym *s, int lane) {
+    s->big_lane = lane;
+    lane_select(s->ctx, lane);
+}
+int big_lanes_end(smcp_sym *s) {
+    s->big_lane = 0;
+    return lanes_join(s->ctx);
+}
+
 // ---- cholesky --------------------------------------------------------------------------
 int big_cholesky(smcp_sym *s, const BigNode &q, double *X, int64_t b) {
     smcp_ctx *ctx = s->ctx;
@@ -353,8 +402,8 @@ int big_cholesky(smcp_sym *s, const BigNode &q, double *X, int64_t b) {
     double *Uk = s->upd + (size_t)b * s->d.nupd + q.uoff;
     double *F = WS(0);
     ELEM(big_front_lower_kernel, (long long)nj * nj, big_args(s, q, b), blk, F);
-    if (d_potrf(ctx, F, nj, nj, nn, s->big_info, 0, 1)) return -1;
-    big_flag_kernel<<<1, 1, 0, ctx->stream>>>(s->big_info, s->fail + b);
+    if (d_potrf(ctx, F, nj, nj, nn, BIG_INFO, 0, 1)) return -1;
+    big_flag_kernel<<<1, 1, 0, ctx->stream>>>(BIG_INFO, s->fail + b);
     ELEM(big_store_cols_kernel, (long long)nj * nn, F, blk, nn, nj);
     if (na) ELEM(big_copy_mat_kernel, (long long)na * na, F + nn + (size_t)nn * nj, nj, Uk, na, na, na, 1);
     CUDA_TRY(cudaGetLastError());
@@ -526,14 +575,14 @@ int big_completion(smcp_sym *s, const BigNode &q, double *X, const double *Xin, 
     // the trailing block (instead of potrf + a forward solve + a rank-na product per supernode)
     ELEM(big_compl_front_kernel, (long long)nj * nj, s->d.aaidx + q.uoff, Xi, bin, T, nn, na, nj);
     if (na) {
-        if (d_potrf(ctx, T, nj, nj, na, s->big_info, 0, 1)) return -1;
-        big_flag_kernel<<<1, 1, 0, ctx->stream>>>(s->big_info, s->fail + b);
+        if (d_potrf(ctx, T, nj, nj, na, BIG_INFO, 0, 1)) return -1;
+        big_flag_kernel<<<1, 1, 0, ctx->stream>>>(BIG_INFO, s->fail + b);
         big_transpose(s, T + na, nj, nn, na, Z, na);                                                // Z = R^-1 X_an
         if (d_trsm_left_lower(ctx, true, T, nj, na, Z, na, nn)) return -1;                          // W = X_aa^-1 X_an
     }
     ELEM(big_reverse_kernel, (long long)nn * nn, T + na + (size_t)na * nj, nj, T0, nn, 0);
-    if (d_potrf(ctx, T0, nn, nn, nn, s->big_info, 0, 1)) return -1;
-    big_flag_kernel<<<1, 1, 0, ctx->stream>>>(s->big_info, s->fail + b);
+    if (d_potrf(ctx, T0, nn, nn, nn, BIG_INFO, 0, 1)) return -1;
+    big_flag_kernel<<<1, 1, 0, ctx->stream>>>(BIG_INFO, s->fail + b);
     ELEM(big_reverse_kernel, (long long)nn * nn, T0, nn, M, nn, 1);                                 // Delta = M^T M
     ELEM(big_identity_kernel, (long long)nn * nn, Li, nn, nn);
     if (d_trsm_left_lower(ctx, false, M, nn, nn, Li, nn, nn)) return -1;                            // L_nn = M^-1
@@ -613,8 +662,8 @@ int big_hess_prep_inv(smcp_sym *s, const BigNode &q, const double *Yaa_all, doub
     const int na = q.na;
     if (!na) return 0;
     ELEM(big_copy_mat_kernel, (long long)na * na, Yaa_all + q.uoff, na, Raa_all + q.uoff, na, na, na, 0);
-    if (d_potrf(ctx, Raa_all + q.uoff, na, na, na, s->big_info, 0, 1)) return -1;
-    big_flag_kernel<<<1, 1, 0, ctx->stream>>>(s->big_info, s->fail);
+    if (d_potrf(ctx, Raa_all + q.uoff, na, na, na, BIG_INFO, 0, 1)) return -1;
+    big_flag_kernel<<<1, 1, 0, ctx->stream>>>(BIG_INFO, s->fail);
     // strictly upper part <- 0 (the factorisation leaves Y's entries there; the half factors use R as a dense block)
     ELEM(big_copy_mat_kernel, (long long)na * na, Raa_all + q.uoff, na, Raa_all + q.uoff, na, na, na, 1);
     CUDA_TRY(cudaGetLastError());

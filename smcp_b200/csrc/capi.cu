@@ -143,10 +143,67 @@ extern "C" int smcp_ctx_create(int device, smcp_ctx **out) {
     return 0;
 }
 
+// ---- concurrent lanes ---------------------------------------------------------------------------
+// lanes_fork(n): lanes 1 .. n-1 wait for everything issued on the main stream so far; lane_select(i): the
+// helpers (launch_gemm, d_potrf, d_trsm_left_lower, the elementwise kernels) now launch on lane i's stream
+// with lane i's scratch; lanes_join(): the main stream waits for every lane.  Host code between fork and
+// join must not synchronise on ctx->stream expecting the lanes to be covered.
+static void lane_swap(smcp_ctx *ctx, CtxLane &L) {
+    std::swap(ctx->stream, L.stream);
+    std::swap(ctx->gemm_ws, L.gemm_ws);
+    std::swap(ctx->gemm_ws_cap, L.gemm_ws_cap);
+    std::swap(ctx->trs_dinv, L.trs_dinv);
+    std::swap(ctx->trs_dinv_cap, L.trs_dinv_cap);
+    std::swap(ctx->gridbar, L.gridbar);
+    std::swap(ctx->gridbar_next, L.gridbar_next);
+}
+void lane_select(smcp_ctx *ctx, int i) {
+    if (i == ctx->lane_cur) return;
+    if (ctx->lane_cur > 0) lane_swap(ctx, ctx->lanes[ctx->lane_cur - 1]);
+    ctx->lane_cur = 0;
+    if (i > 0) {
+        lane_swap(ctx, ctx->lanes[i - 1]);
+        ctx->lane_cur = i;
+    }
+}
+int lanes_fork(smcp_ctx *ctx, int n) {
+    if (n <= 1 || ctx->lanes_active) return 0;
+    while ((int)ctx->lanes.size() < n - 1) {
+        CtxLane L;
+        CUDA_TRY(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+        ctx->lanes.push_back(L);
+    }
+    if (!ctx->lane_fork_ev) CUDA_TRY(cudaEventCreateWithFlags(&ctx->lane_fork_ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(ctx->lane_fork_ev, ctx->stream));
+    for (int i = 0; i < n - 1; ++i) CUDA_TRY(cudaStreamWaitEvent(ctx->lanes[i].stream, ctx->lane_fork_ev, 0));
+    ctx->lanes_active = n;
+    return 0;
+}
+int lanes_join(smcp_ctx *ctx) {
+    if (!ctx->lanes_active) return 0;
+    lane_select(ctx, 0);
+    for (int i = 0; i < ctx->lanes_active - 1; ++i) {
+        CUDA_TRY(cudaEventRecord(ctx->lanes[i].done, ctx->lanes[i].stream));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->lanes[i].done, 0));
+    }
+    ctx->lanes_active = 0;
+    return 0;
+}
+
 extern "C" int smcp_ctx_destroy(smcp_ctx *ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
+    lanes_join(ctx);
     cudaStreamSynchronize(ctx->stream);
+    for (CtxLane &L : ctx->lanes) {
+        if (L.gemm_ws) cudaFree(L.gemm_ws);
+        if (L.trs_dinv) cudaFree(L.trs_dinv);
+        if (L.gridbar) cudaFree(L.gridbar);
+        cudaEventDestroy(L.done);
+        cudaStreamDestroy(L.stream);
+    }
+    if (ctx->lane_fork_ev) cudaEventDestroy(ctx->lane_fork_ev);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);
     if (ctx->gridbar) cudaFree(ctx->gridbar);

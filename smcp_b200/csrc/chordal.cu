@@ -169,6 +169,22 @@ static int dist_ops(const smcp_sym *s, int64_t batch) {
     return ctx->comm_nranks;
 }
 
+// One sweep over the top set, level by level; the supernodes of a level go round-robin to the concurrent lanes.
+template <class F>
+static int big_sweep(smcp_sym *s, const std::vector<std::vector<int>> &levels, F f) {
+    for (const std::vector<int> &lev : levels) {
+        const int nl = lev.size() > 1 ? big_lanes_begin(s) : 1;
+        if (nl < 0) return -1;
+        int j = 0, rc = 0;
+        for (int i : lev) {
+            if (nl > 1) big_lane_pick(s, j++ % nl);
+            if (f(s->big[i])) { rc = -1; break; }
+        }
+        if ((nl > 1 && big_lanes_end(s)) || rc) return -1;
+    }
+    return 0;
+}
+
 int k_cholesky(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
     RegionScope rs(s->ctx, batch > 1 ? "op_cholesky_batch" : "op_cholesky");
     if (s->small) return ks_cholesky(s, x, batch, info_host);
@@ -182,8 +198,7 @@ int k_cholesky(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
     if (launch_tree<OP_CHOL>(s, a, s->up, batch, pick_threads(s, big), batch > 1 ? "cholesky_batch" : "cholesky")) return -1;
     if (big)
         for (int64_t b = 0; b < batch; ++b)
-            for (const BigNode &q : s->big)
-                if (big_cholesky(s, q, x, b)) return -1;
+            if (big_sweep(s, s->big_up, [&](const BigNode &q) { return big_cholesky(s, q, x, b); })) return -1;
     if (info_host) return fetch_fail(s, batch, info_host);
     return 0;
 }
@@ -200,8 +215,7 @@ int k_llt(smcp_sym *s, double *x, int64_t batch) {
     if (launch_tree<OP_LLT>(s, a, s->up, batch, pick_threads(s, big), "llt")) return -1;
     if (big)
         for (int64_t b = 0; b < batch; ++b)
-            for (const BigNode &q : s->big)
-                if (big_llt(s, q, x, b)) return -1;
+            if (big_sweep(s, s->big_up, [&](const BigNode &q) { return big_llt(s, q, x, b); })) return -1;
     return 0;
 }
 
@@ -215,8 +229,7 @@ int k_projinv(smcp_sym *s, double *x, int64_t batch) {
     if (big) {
         a.skipflag = s->big_flag;
         for (int64_t b = 0; b < batch; ++b)
-            for (auto it = s->big.rbegin(); it != s->big.rend(); ++it)
-                if (big_projinv(s, *it, x, b)) return -1;
+            if (big_sweep(s, s->big_down, [&](const BigNode &q) { return big_projinv(s, q, x, b); })) return -1;
     }
     return launch_tree<OP_PROJINV>(s, a, s->down, batch, pick_threads(s, big), "projected_inverse");
 }
@@ -242,14 +255,21 @@ int k_completion(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
         // every owner broadcasts its block of L: the 27 factorisations of ~1100-row separators of the
         // rand_SDP pattern run 27/N per rank.  All ranks end with bitwise identical data and verdicts.
         const int nr = dist_ops(s, batch), rk = ctx->comm_rank;
-        for (int64_t b = 0; b < batch; ++b) {
+        // ... and on one GPU the supernodes a rank owns are issued round-robin on a few concurrent lanes
+        const int nl = big_lanes_begin(s);
+        if (nl < 0) return -1;
+        int rc = 0, mine = 0;
+        for (int64_t b = 0; b < batch && !rc; ++b) {
             int idx = 0;
             for (const BigNode &q : s->big) {
-                if (nr == 1 || idx % nr == rk)
-                    if (big_completion(s, q, x, s->tmp, b)) return -1;
+                if (nr == 1 || idx % nr == rk) {
+                    big_lane_pick(s, mine++ % nl);
+                    if (big_completion(s, q, x, s->tmp, b)) { rc = -1; break; }
+                }
                 ++idx;
             }
         }
+        if (big_lanes_end(s) || rc) return -1;
         if (nr > 1) {
             if (comm_group_start()) return -1;
             int idx = 0;
@@ -279,8 +299,12 @@ int k_hess_prep(smcp_hess *h, const double *L, const double *Y) {
     if (big) a.skipflag = s->big_flag;
     if (launch_tree<OP_HPREP>(s, a, flat_sched(s), 1, pick_threads(s, big), "hessian_prep")) return -1;
     if (big)
-        for (const BigNode &q : s->big)
-            if (big_hess_prep(s, q, L, Y, h->Lt, h->Yaa)) return -1;
+        {
+            // independent per supernode
+            std::vector<std::vector<int>> all(1);
+            for (int i = 0; i < (int)s->big.size(); ++i) all[0].push_back(i);
+            if (big_sweep(s, all, [&](const BigNode &q) { return big_hess_prep(s, q, L, Y, h->Lt, h->Yaa); })) return -1;
+        }
     return 0;
 }
 
@@ -300,12 +324,17 @@ int k_hess_prep_inv(smcp_hess *h) {
         // independent per supernode as well: chol(Y_aa) of the top set shared out over the ranks
         smcp_ctx *ctx = s->ctx;
         const int nr = dist_ops(s, 1), rk = ctx->comm_rank;
-        int idx = 0;
+        const int nl = big_lanes_begin(s);
+        if (nl < 0) return -1;
+        int idx = 0, rc = 0, mine = 0;
         for (const BigNode &q : s->big) {
-            if (nr == 1 || idx % nr == rk)
-                if (big_hess_prep_inv(s, q, h->Yaa, h->Raa)) return -1;
+            if (nr == 1 || idx % nr == rk) {
+                big_lane_pick(s, mine++ % nl);
+                if (big_hess_prep_inv(s, q, h->Yaa, h->Raa)) { rc = -1; break; }
+            }
             ++idx;
         }
+        if (big_lanes_end(s) || rc) return -1;
         if (nr > 1) {
             if (comm_group_start()) return -1;
             idx = 0;
@@ -343,10 +372,8 @@ int k_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
         if (bigb && big_hess_fwd_batched(s, h->Lt, h->Yaa, U, batch)) return -1;
         if (big)
             for (int64_t b = 0; b < batch; ++b) {
-                for (const BigNode &q : s->big)
-                    if (big_hess_up(s, q, h->Lt, h->Yaa, U, b)) return -1;
-                for (auto it = s->big.rbegin(); it != s->big.rend(); ++it)
-                    if (big_hess_down(s, *it, h->Lt, U, b)) return -1;
+                if (big_sweep(s, s->big_up, [&](const BigNode &q) { return big_hess_up(s, q, h->Lt, h->Yaa, U, b); })) return -1;
+                if (big_sweep(s, s->big_down, [&](const BigNode &q) { return big_hess_down(s, q, h->Lt, U, b); })) return -1;
             }
         return launch_tree<OP_HFWD_DOWN>(s, a, s->down, batch, threads, many ? "hessian_down_batch" : "hessian_down");
     }
@@ -362,12 +389,17 @@ int k_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
         if (grow((void **)&s->big_hinv, &s->big_hinv_cap, (size_t)s->d.nblk * sizeof(double))) return -1;
         const int nr = dist_ops(s, batch), rk = ctx->comm_rank;
         for (int64_t b = 0; b < batch; ++b) {
-            int idx = 0;
+            const int nl = big_lanes_begin(s);
+            if (nl < 0) return -1;
+            int idx = 0, rc = 0, mine = 0;
             for (const BigNode &q : s->big) {
-                if (nr == 1 || idx % nr == rk)
-                    if (big_hess_inv_local(s, q, h->Lt, h->Raa, U, b, s->big_hinv)) return -1;
+                if (nr == 1 || idx % nr == rk) {
+                    big_lane_pick(s, mine++ % nl);
+                    if (big_hess_inv_local(s, q, h->Lt, h->Raa, U, b, s->big_hinv)) { rc = -1; break; }
+                }
                 ++idx;
             }
+            if (big_lanes_end(s) || rc) return -1;
             if (nr > 1) {
                 if (comm_group_start()) return -1;
                 idx = 0;
@@ -377,8 +409,7 @@ int k_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
                 }
                 if (comm_group_end()) return -1;
             }
-            for (const BigNode &q : s->big)
-                if (big_hess_inv_sweep(s, q, h->Lt, U, b, s->big_hinv)) return -1;
+            if (big_sweep(s, s->big_up, [&](const BigNode &q) { return big_hess_inv_sweep(s, q, h->Lt, U, b, s->big_hinv); })) return -1;
         }
     }
     return 0;

@@ -349,7 +349,11 @@ int potrf_tile(smcp_ctx *ctx, double *H, int64_t ld, int64_t mm, int64_t npiv, b
         a.dbg = dbg_dev;
     }
     const int64_t ntiles = (int64_t)a.ntc * P - (int64_t)a.ntc * (a.ntc - 1) / 2;
-    const unsigned grid = (unsigned)std::min<int64_t>(ctx->num_sms, ntiles);
+    // between lanes_fork and lanes_join several factorisations run side by side: each takes its share of the SMs
+    // (a CTA then owns more tiles; the arithmetic of a tile does not depend on who owns it)
+    int64_t gcap = ctx->num_sms;
+    if (ctx->lanes_active > 1) gcap = std::max<int64_t>(ctx->num_sms / ctx->lanes_active, (ntiles + PT_MAXOWN - 1) / PT_MAXOWN);
+    const unsigned grid = (unsigned)std::min<int64_t>(std::min<int64_t>(gcap, ctx->num_sms), ntiles);
     void *args[] = {&a};
     LaunchScope ls(ctx, "potrf_tile", 1, (double)npiv * npiv * npiv / 3.0);
     CUDA_TRY(cudaLaunchCooperativeKernel((void *)potrf_tile_kernel, dim3(grid), dim3(PT_THREADS), args, smem, ctx->stream));

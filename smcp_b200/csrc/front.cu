@@ -104,8 +104,59 @@ __global__ void __launch_bounds__(128) trsm_diag_kernel(const double *__restrict
     }
 }
 
+// n <= 32 (the nn x nn pivot blocks of thin supernodes, nn = 1 .. 9): one right-hand side per thread, the factor
+// in shared memory, the column in registers -- a few microseconds instead of a slab launch with 200 KB of
+// shared memory for a 1 x 1 solve.
+template <bool TRANS>
+__global__ void __launch_bounds__(128) trsm_tiny_kernel(const double *__restrict__ L, long long ldl, int n, double *__restrict__ B, long long ldb,
+                                                        long long nrhs) {
+    __shared__ double Ls[32 * 33];
+    for (int idx = threadIdx.x; idx < n * n; idx += 128) {
+        const int r = idx % n, c = idx / n;
+        Ls[c * 33 + r] = (r >= c) ? L[r + (long long)c * ldl] : 0.0;
+    }
+    __syncthreads();
+    const long long col = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (col >= nrhs) return;
+    double *b = B + col * ldb;
+    double x[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) x[r] = (r < n) ? b[r] : 0.0;
+    if (!TRANS) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+            if (c < n) {
+                const double xc = x[c] / Ls[c * 33 + c];
+                x[c] = xc;
+#pragma unroll
+                for (int r = c + 1; r < 32; ++r)
+                    if (r < n) x[r] = fma(-Ls[c * 33 + r], xc, x[r]);
+            }
+    } else {
+#pragma unroll
+        for (int c = 31; c >= 0; --c)
+            if (c < n) {
+                const double xc = x[c] / Ls[c * 33 + c];
+                x[c] = xc;
+#pragma unroll
+                for (int r = 0; r < c; ++r) x[r] = fma(-Ls[r * 33 + c], xc, x[r]);
+            }
+    }
+#pragma unroll
+    for (int r = 0; r < 32; ++r)
+        if (r < n) b[r] = x[r];
+}
+
 int d_trsm_left_lower(smcp_ctx *ctx, bool trans, const double *L, int64_t ldl, int64_t n, double *B, int64_t ldb, int64_t nrhs) {
     if (n <= 0 || nrhs <= 0) return 0;
+    if (n <= 32) {
+        LaunchScope ls(ctx, "trsm_tiny");
+        const unsigned grid = (unsigned)((nrhs + 127) / 128);
+        if (trans) trsm_tiny_kernel<true><<<grid, 128, 0, ctx->stream>>>(L, ldl, (int)n, B, ldb, nrhs);
+        else trsm_tiny_kernel<false><<<grid, 128, 0, ctx->stream>>>(L, ldl, (int)n, B, ldb, nrhs);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     // L2-resident factors: one launch, every CTA keeps 8 right-hand sides in shared memory for the whole
     // solve (dense_tile.cu); SMCP_B200_TRSM_BLOCKED=1 keeps the launch chain below (A/B measurements)
     static const bool blocked_only = getenv("SMCP_B200_TRSM_BLOCKED") && atoi(getenv("SMCP_B200_TRSM_BLOCKED")) != 0;

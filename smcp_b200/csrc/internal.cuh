@@ -33,6 +33,21 @@ struct RegionAcc {
     int64_t calls = 0;
 };
 
+// Scratch of one concurrent LANE (lanes_fork / lane_select / lanes_join, capi.cu): supernodes of the top set whose
+// work is independent (completion, chol(Y_aa), the local phase of the inverse Hessian) are issued round-robin
+// on a few streams; every helper launches on ctx->stream with ctx's scratch buffers, so selecting a lane swaps
+// these members with the lane's own copies.
+struct CtxLane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    double *gemm_ws = nullptr;
+    size_t gemm_ws_cap = 0;
+    double *trs_dinv = nullptr;
+    size_t trs_dinv_cap = 0;
+    unsigned *gridbar = nullptr;
+    unsigned gridbar_next = 0;
+};
+
 struct smcp_ctx {
     std::map<std::string, RegionAcc> regions;
     std::vector<cudaEvent_t> region_pool;
@@ -57,6 +72,10 @@ struct smcp_ctx {
     size_t trs_dinv_cap = 0;
     unsigned *gridbar = nullptr;        // counters of the hand-rolled grid barrier (potrf_tile_kernel)
     unsigned gridbar_next = 0;
+    std::vector<CtxLane> lanes;         // lanes[i - 1] = lane i >= 1 (lane 0 is `stream` itself)
+    int lane_cur = 0;                   // lane whose members are currently swapped in
+    int lanes_active = 0;               // > 1 between lanes_fork and lanes_join
+    cudaEvent_t lane_fork_ev = nullptr;
     // pinned staging for small host<->device transfers
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
@@ -164,9 +183,12 @@ struct smcp_sym {
     // top set of large supernodes (and their ancestors) processed by dense kernels for single matrices (bigfront.cu)
     std::vector<BigNode> big;    // ascending supernode index = post-order
     const int *big_flag = nullptr, *big_inv = nullptr, *big_ch = nullptr;
-    double *big_ws = nullptr;
+    double *big_ws = nullptr;      // BIG_NWS workspaces per lane
     size_t big_ws_stride = 0;
-    int *big_info = nullptr;
+    int *big_info = nullptr;       // one flag per lane
+    std::vector<std::vector<int>> big_up, big_down;   // indices into `big` by height (leaves first) / by depth (root first)
+    int big_nlanes = 1;            // lanes the top set may use (1 = everything on the main stream)
+    int big_lane = 0;              // lane the next big_* call works in
     int max_nj_small = 0;        // largest frontal matrix left to the tree kernels when the top set is skipped
     double *big_hinv = nullptr;                         // inverse Hessian: K_nn | K_an of every top-set supernode (blkval layout)
     size_t big_hinv_cap = 0;
@@ -196,6 +218,10 @@ struct smcp_hess {
 
 int sym_ensure(smcp_sym *s, int64_t batch, bool need_tmp);
 int grow(void **p, size_t *cap, size_t bytes);
+// concurrent lanes (capi.cu): fork n lanes off ctx->stream, make lane i current, join them all back
+int lanes_fork(smcp_ctx *ctx, int n);
+void lane_select(smcp_ctx *ctx, int i);
+int lanes_join(smcp_ctx *ctx);
 
 // tiny-clique kernels (chordal_small.cu); same contracts as the k_* functions below
 int small_setup(smcp_sym *s, const smcp_sym_desc *D, const std::vector<int> &tp, const std::vector<int> &ts,
@@ -239,6 +265,9 @@ int big_projinv(smcp_sym *s, const BigNode &q, double *X, int64_t b);
 int big_completion(smcp_sym *s, const BigNode &q, double *X, const double *Xin, int64_t b);
 int big_hess_prep(smcp_sym *s, const BigNode &q, const double *L0, const double *Y0, double *Lt_out, double *Yaa_out);
 int big_hess_prep_inv(smcp_sym *s, const BigNode &q, const double *Yaa_all, double *Raa_all);
+int big_lanes_begin(smcp_sym *s);          // returns the number of lanes (>= 1), -1 on error
+void big_lane_pick(smcp_sym *s, int lane);
+int big_lanes_end(smcp_sym *s);
 int big_trsm_node(smcp_sym *s, const BigNode &q, const double *L, double *B, int64_t ldb, int64_t nrhs, int trans);
 int big_hess_fwd_batched(smcp_sym *s, const double *Lt, const double *Yaa_all, double *U, int64_t batch);
 

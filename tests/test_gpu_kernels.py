@@ -28,6 +28,9 @@ def _cases():
             # general trees: also with the dense multi-CTA path (bigfront.cu) forced on every
             # supernode with >= 3 rows (and all their ancestors), separators included ...
             out.append(p + ("bigtop3",))
+        if p[3] in (1, 5):
+            # the independent top-set operations issued on three concurrent lanes (streams)
+            out.append(p + ("bigtop3lanes",))
         if p[3] in (0, 1, 6, 14):
             # ... and with a threshold that splits the tree between the two code paths
             out.append(p + ("bigtop6",))
@@ -50,13 +53,16 @@ def setup(request):
     if mode == "nochain":
         os.environ["SMCP_B200_NO_CHAIN"] = "1"
     if mode.startswith("bigtop"):
-        os.environ["SMCP_B200_BIG_NJ"] = mode[6:]
+        os.environ["SMCP_B200_BIG_NJ"] = mode[6:].replace("lanes", "")
+        os.environ["SMCP_B200_LANES"] = "3" if mode.endswith("lanes") else "1"
+
     try:
         dev = DeviceBackend(symb, small_work=0 if mode == "split" else 2000)
     finally:
         os.environ.pop("SMCP_B200_NO_SMALL", None)
         os.environ.pop("SMCP_B200_NO_CHAIN", None)
         os.environ.pop("SMCP_B200_BIG_NJ", None)
+        os.environ.pop("SMCP_B200_LANES", None)
     s = random_pd(symb, seed)
     l = s.copy()
     sn.cholesky(symb, l)
