@@ -38,6 +38,10 @@ def run(name):
         T = dev.clone(S); return lambda: dev.hessian_apply(tok, [T], False), T
     if name == "hessian_inv":
         T = dev.clone(S); return lambda: dev.hessian_apply(tok, [T], True), T
+    if name == "kkt_assemble":
+        return (lambda: dev.schur_assemble(tok)), None
+    if name == "kkt_factor":
+        return (lambda: dev.schur_factor(tok)), None
     if name == "hessian_prep_inv":
         return (lambda: (dev.hessian_factor(L, X), dev.hessian_apply(dev._tok, [dev.clone(S)], True))), None
     raise SystemExit("unknown op " + name)

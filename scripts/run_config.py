@@ -64,9 +64,19 @@ solvers.options["show_progress"] = False
 stamps = {}
 
 
+per_iter = {}
+_prev = {}
+
+
 def hook(name, it):
     ctx.sync()
     stamps[it] = time.perf_counter()
+    if os.environ.get("RUNCFG_PER_ITER"):
+        # API regions of the iteration that just ended (device ms, calls)
+        cur = {nm: ctx.region_get(nm) for nm in ctx.region_names()}
+        per_iter[it - 1] = {nm: (v[0] - _prev.get(nm, (0.0, 0))[0], v[1] - _prev.get(nm, (0.0, 0))[1]) for nm, v in cur.items()}
+        _prev.clear()
+        _prev.update(cur)
 
 
 solvers._iteration_hook = hook
@@ -83,6 +93,9 @@ if full:
     raise SystemExit(0)
 for a, b in zip(its[:-1], its[1:]):
     print("  iteration %d: %.2f ms" % (a, 1e3 * (stamps[b] - stamps[a])))
+for itn in sorted(per_iter)[1:]:
+    row = sorted(per_iter[itn].items(), key=lambda kv: -kv[1][0])
+    print("  regions of iteration %d: " % itn + ", ".join("%s %.1f/%d" % (nm.replace("op_", "").replace("kkt_", "k_"), ms, c) for nm, (ms, c) in row if c))
 print("  API regions over the whole solve (device ms between event pairs, no synchronisation; calls):")
 for nm in sorted(ctx.region_names(), key=lambda k: -ctx.region_get(k)[0]):
     ms, calls = ctx.region_get(nm)

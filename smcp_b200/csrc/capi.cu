@@ -560,6 +560,12 @@ struct smcp_op {
     int npos = 0;
     long long sp_base = 0;        // first entry of the first sparse column
     double sp_avg_nnz = 0.0;
+    double *ell_val = nullptr;       // sparse constraints in column-major ELL form (entry q of constraint md + i at [q * ms + i]):
+    int *ell_pid = nullptr;          //   coalesced row walk of the position kernels; null when the row lengths are too uneven
+    int ell_w = 0;                   // entries per row (max nnz)
+    double *Kpos = nullptr;          // materialised position kernel matrix (scm_kmat_kernel), ldk x npos
+    size_t Kpos_cap = 0;
+    bool Kpos_valid = false;         // built from the current Zinv
     // CSR over blkval rows
     long long *r_ptr = nullptr;
     int *r_col = nullptr;
@@ -709,6 +715,9 @@ extern "C" int smcp_op_create(smcp_sym *s, int64_t m, int64_t Ns, const int64_t 
     return 0;
 }
 
+__global__ void scm_ell_build_kernel(const long long *__restrict__ colptr, const double *__restrict__ vals, const int *__restrict__ sp_pid,
+                                     long long sp_base, long long md, long long ms, int ell_w, double *__restrict__ ell_val,
+                                     int *__restrict__ ell_pid);
 // (row, col) in the internal order of every entry of Av, needed by the sparse technique
 extern "C" int smcp_op_set_entry_coords(smcp_op *op, const int64_t *rows_int, const int64_t *cols_int) {
     std::vector<int> r(op->nnz), c(op->nnz);
@@ -736,6 +745,21 @@ extern "C" int smcp_op_set_entry_coords(smcp_op *op, const int64_t *rows_int, co
         op->npos = (int)pr.size();
         op->sp_avg_nnz = (double)(p1 - p0) / (double)std::max<int64_t>(1, op->m - op->md);
         if (dev_upload(pid, &op->sp_pid) || dev_upload(pr, &op->pos_r) || dev_upload(pc, &op->pos_c)) return -1;
+        // ELL copy of the sparse constraints for the coalesced row walk, unless the row lengths are too uneven
+        const int64_t ms = op->m - op->md;
+        int64_t w = 0;
+        for (int64_t i = op->md; i < op->m; ++i) w = std::max<int64_t>(w, op->h_colptr[i + 1] - op->h_colptr[i]);
+        if (w > 0 && (double)w <= 2.0 * op->sp_avg_nnz + 8.0 && (size_t)w * ms * 12 <= ((size_t)2 << 30)) {
+            smcp_ctx *ctx = op->sym->ctx;
+            CUDA_TRY(cudaMalloc(&op->ell_val, (size_t)w * ms * sizeof(double)));
+            CUDA_TRY(cudaMalloc(&op->ell_pid, (size_t)w * ms * sizeof(int)));
+            op->ell_w = (int)w;
+            LaunchScope ls(ctx, "setup");
+            scm_ell_build_kernel<<<(unsigned)std::min<int64_t>((w * ms + 255) / 256, 4096), 256, 0, ctx->stream>>>(
+                op->colptr, op->vals, op->sp_pid, op->sp_base, op->md, ms, (int)w, op->ell_val, op->ell_pid);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        }
     }
     return 0;
 }
@@ -751,6 +775,8 @@ extern "C" int smcp_op_destroy(smcp_op *op) {
     if (op->AvW) cudaFree(op->AvW);
     if (op->Ub) cudaFree(op->Ub);
     if (op->Zinv) cudaFree(op->Zinv);
+    if (op->Kpos) cudaFree(op->Kpos);
+    if (op->ell_val) { cudaFree(op->ell_val); cudaFree(op->ell_pid); }
     if (op->Zq) cudaFree(op->Zq);
     if (op->sqrtw) cudaFree(op->sqrtw);
     if (op->Dinv) cudaFree(op->Dinv);
@@ -832,12 +858,46 @@ __global__ void scm_sparse_kernel(const long long *__restrict__ colptr, const do
 // every thread keeps KPOS positions in registers; afterwards G_j replaces the staged columns in
 // shared memory and the threads walk the rows i >= j.
 #define SCM_T 512
+// H[i, j] = sum_{(pid, beta) in A_i} beta G_j(pid) for the rows i >= j, G_j in shared memory; one thread per row,
+// entries in storage order (the same sums in CSR and ELL form: the ELL padding adds beta = 0 terms)
+__device__ __noinline__ void scm_rows(const double *G, const long long *__restrict__ colptr, const double *__restrict__ vals,
+                                         const int *__restrict__ sp_pid, long long sp_base, const double *__restrict__ ell_val,
+                                         const int *__restrict__ ell_pid, int ell_w, long long md, double *H, long long m, long long j) {
+    const long long ms = m - md;
+    for (long long i = j + threadIdx.x; i < m; i += SCM_T) {
+        double t = 0.0;
+        if (ell_val) {
+            const double *ev = ell_val + (i - md);
+            const int *ep = ell_pid + (i - md);
+#pragma unroll 4
+            for (int q = 0; q < ell_w; ++q) t = fma(ev[q * ms], G[ep[q * ms]], t);
+        } else {
+            for (long long q = colptr[i]; q < colptr[i + 1]; ++q) t = fma(vals[q], G[sp_pid[q - sp_base]], t);
+        }
+        H[i + j * m] = t;
+    }
+}
+__global__ void scm_ell_build_kernel(const long long *__restrict__ colptr, const double *__restrict__ vals, const int *__restrict__ sp_pid,
+                                     long long sp_base, long long md, long long ms, int ell_w, double *__restrict__ ell_val,
+                                     int *__restrict__ ell_pid) {
+    const long long total = ms * ell_w;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long i = idx % ms;
+        const int q = (int)(idx / ms);
+        const long long p = colptr[md + i] + q;
+        const bool live = p < colptr[md + i + 1];
+        ell_val[idx] = live ? vals[p] : 0.0;
+        ell_pid[idx] = live ? sp_pid[p - sp_base] : 0;
+    }
+}
+
 template <int KPOS>
 __global__ void __launch_bounds__(SCM_T, 1)
 scm_position_kernel(const long long *__restrict__ colptr, const double *__restrict__ vals, const int *__restrict__ er,
                     const int *__restrict__ ec, const int *__restrict__ sp_pid, long long sp_base,
                     const int *__restrict__ pos_r, const int *__restrict__ pos_c, int npos, const double *__restrict__ Z,
-                    int n, double *H, long long m, long long j0, int E) {
+                    int n, double *H, long long m, long long j0, int E, const double *__restrict__ ell_val,
+                    const int *__restrict__ ell_pid, int ell_w, long long md) {
     extern __shared__ double scm_sm[];      // max(2 E n, npos) doubles
     __shared__ double alpha_s[64];
     __shared__ int col_s[128];
@@ -886,13 +946,77 @@ scm_position_kernel(const long long *__restrict__ colptr, const double *__restri
         if (pid < npos) scm_sm[pid] = acc[k];
     }
     __syncthreads();
-    for (long long i = j + tid; i < m; i += SCM_T) {
-        double t = 0.0;
-        for (long long q = colptr[i]; q < colptr[i + 1]; ++q) t = fma(vals[q], scm_sm[sp_pid[q - sp_base]], t);
-        H[i + j * m] = t;
+    scm_rows(scm_sm, colptr, vals, sp_pid, sp_base, ell_val, ell_pid, ell_w, md, H, m, j);
+}
+
+
+// POSITION form with a materialised kernel matrix.  G_j(p, q) = sum_e alpha'_e K[(p, q), (r_e, c_e)] with
+//     K[(p, q), (r, c)] = Z(p, r) Z(q, c) + (p != q) Z(q, r) Z(p, c)
+// over the npos positions the sparse constraints touch.  scm_position_kernel recomputes K's entries for
+// every constraint entry (4 shared-memory gathers with bank conflicts each: npos * nnz(A) of them, the
+// bound of that kernel); here K is built ONCE per scaling point (npos^2 entries, same expressions, so the
+// same bits) and column j streams the nnz(A_j) columns of K it needs: coalesced 8-byte loads, HBM bound at
+// 8 * npos * nnz(A) bytes in total (rand_SDP n = 2000, m = 10^4: 2 GB for K, 100 GB streamed).
+__global__ void __launch_bounds__(SCM_T)
+scm_kmat_kernel(const int *__restrict__ pos_r, const int *__restrict__ pos_c, int npos, const double *__restrict__ Z, int n,
+                double *__restrict__ K, long long ldk) {
+    extern __shared__ double km_sm[];       // Z(:, r) | Z(:, c)
+    const int tid = threadIdx.x;
+    const int e = blockIdx.x;
+    const int r = pos_r[e], c = pos_c[e];
+    const double *Zr = Z + (long long)r * n, *Zc = Z + (long long)c * n;
+    for (int i = tid; i < n; i += SCM_T) {
+        km_sm[i] = Zr[i];
+        km_sm[n + i] = Zc[i];
+    }
+    __syncthreads();
+    const double *zr = km_sm, *zc = km_sm + n;
+    double *Ke = K + (long long)e * ldk;
+    for (int pid = tid; pid < ldk; pid += SCM_T) {
+        double v = 0.0;
+        if (pid < npos) {
+            const int p_ = pos_r[pid], q_ = pos_c[pid];
+            v = zr[p_] * zc[q_];
+            if (p_ != q_) v = fma(zr[q_], zc[p_], v);
+        }
+        Ke[pid] = v;
     }
 }
 
+template <int KPOS>
+__global__ void __launch_bounds__(SCM_T, 1)
+scm_kstream_kernel(const long long *__restrict__ colptr, const double *__restrict__ vals, const int *__restrict__ er,
+                   const int *__restrict__ ec, const int *__restrict__ sp_pid, long long sp_base, int npos, long long ldk,
+                   const double *__restrict__ K, double *H, long long m, long long j0, const double *__restrict__ ell_val,
+                   const int *__restrict__ ell_pid, int ell_w, long long md) {
+    extern __shared__ double scm_sm[];      // ldk doubles: G_j
+    const int tid = threadIdx.x;
+    const long long j = j0 + blockIdx.x;
+    const long long pj0 = colptr[j], pj1 = colptr[j + 1];
+    // thread tid accumulates the positions 2 (k SCM_T + tid) and + 1, k < KPOS / 2 (16-byte loads; ldk is even)
+    double2 acc[KPOS / 2];
+#pragma unroll
+    for (int k = 0; k < KPOS / 2; ++k) acc[k] = make_double2(0.0, 0.0);
+    for (long long e = pj0; e < pj1; ++e) {
+        const double al = vals[e] * (er[e] != ec[e] ? 2.0 : 1.0);
+        const double2 *Ke = reinterpret_cast<const double2 *>(K + (long long)sp_pid[e - sp_base] * ldk) + tid;
+        double2 v[KPOS / 2];
+#pragma unroll
+        for (int k = 0; k < KPOS / 2; ++k) v[k] = (2 * (k * SCM_T + tid) < npos) ? __ldcs(Ke + k * SCM_T) : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < KPOS / 2; ++k) {
+            acc[k].x = fma(al, v[k].x, acc[k].x);
+            acc[k].y = fma(al, v[k].y, acc[k].y);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KPOS / 2; ++k) {
+        const int pid = 2 * (k * SCM_T + tid);
+        if (pid < npos) reinterpret_cast<double2 *>(scm_sm)[k * SCM_T + tid] = acc[k];
+    }
+    __syncthreads();
+    scm_rows(scm_sm, colptr, vals, sp_pid, sp_base, ell_val, ell_pid, ell_w, md, H, m, j);
+}
 
 // technique 1 on a set of column ranges: ONE batched Hessian over all of them (the chordal kernels
 // are latency/issue bound, small batches waste the machine), then one DMMA contraction per range
@@ -970,6 +1094,7 @@ static int build_zinv(smcp_op *op, smcp_hess *h, bool sharded) {
         if (k_trsm(s, h->L, op->Zinv + (size_t)c0 * n, n, c1 - c0, 1)) return -1;
     }
     if (nr > 1 && comm_allgather(ctx, op->Zinv, (size_t)chunk * n, ctx->stream)) return -1;
+    op->Kpos_valid = false;
     return 0;
 }
 
@@ -986,15 +1111,45 @@ static int assemble_sparse_range(smcp_op *op, smcp_hess *h, int64_t s0, int64_t 
     const long long cap = 25600;                 // doubles of dynamic shared memory (200 KB)
     const int E = (int)std::min<long long>(64, cap / (2 * n));
     static const bool allow_pos = !(getenv("SMCP_B200_SCM_PAIRWISE") && atoi(getenv("SMCP_B200_SCM_PAIRWISE")) != 0);
-    if (allow_pos && op->sp_pid && E >= 2 && n < 65536 && op->npos <= 32 * SCM_T && op->npos <= cap && op->sp_avg_nnz >= 3.0) {
-        const size_t smem = (size_t)std::max<long long>(2LL * E * n, op->npos) * sizeof(double);
+    if (allow_pos && op->sp_pid && E >= 2 && n < 65536 && op->npos <= 32 * SCM_T && op->npos + 1 <= cap && op->sp_avg_nnz >= 3.0) {
         const int kpos = (op->npos + SCM_T - 1) / SCM_T;
+        // materialised kernel matrix when it fits (SMCP_B200_SCM_KMAT_GB, default 4 GB) and pays: building it
+        // costs npos^2 entries, the direct form npos * nnz per column
+        const double kmat_gb = getenv("SMCP_B200_SCM_KMAT_GB") ? atof(getenv("SMCP_B200_SCM_KMAT_GB")) : 4.0;
+        const long long ldk = (op->npos + 1) & ~1LL;
+        const double kbytes = (double)ldk * (double)op->npos * 8.0;
+        const double nnz_sp = op->sp_avg_nnz * (double)(m - op->md);
+        if (kbytes <= kmat_gb * 1073741824.0 && 2 * n <= cap && nnz_sp >= 2.0 * (double)op->npos) {
+            if (!op->Kpos_valid) {
+                if (grow((void **)&op->Kpos, &op->Kpos_cap, (size_t)kbytes)) return -1;
+                LaunchScope ls(ctx, "scm_kmat");
+                CUDA_TRY(cudaFuncSetAttribute(scm_kmat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap * 8)));
+                scm_kmat_kernel<<<(unsigned)op->npos, SCM_T, (size_t)2 * n * sizeof(double), ctx->stream>>>(op->pos_r, op->pos_c, op->npos, op->Zinv, (int)n, op->Kpos, ldk);
+                op->Kpos_valid = true;
+            }
+            LaunchScope ls(ctx, "scm_kstream");
+#define SCM_KLAUNCH(K_)                                                                                                      \
+    do {                                                                                                                    \
+        CUDA_TRY(cudaFuncSetAttribute(scm_kstream_kernel<K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap * 8))); \
+        scm_kstream_kernel<K_><<<(unsigned)(s1 - s0), SCM_T, (size_t)ldk * sizeof(double), ctx->stream>>>(op->colptr, op->vals,     \
+            op->ent_r, op->ent_c, op->sp_pid, op->sp_base, op->npos, ldk, op->Kpos, op->H, m, s0, op->ell_val, op->ell_pid,  \
+            op->ell_w, op->md);                                                                                              \
+    } while (0)
+            if (kpos <= 8) SCM_KLAUNCH(8);
+            else if (kpos <= 16) SCM_KLAUNCH(16);
+            else SCM_KLAUNCH(32);
+#undef SCM_KLAUNCH
+            CUDA_TRY(cudaGetLastError());
+            return 0;
+        }
+        const size_t smem = (size_t)std::max<long long>(2LL * E * n, op->npos) * sizeof(double);
         LaunchScope ls(ctx, "scm_position");
 #define SCM_LAUNCH(K_)                                                                                                      \
     do {                                                                                                                    \
         CUDA_TRY(cudaFuncSetAttribute(scm_position_kernel<K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap * 8))); \
         scm_position_kernel<K_><<<(unsigned)(s1 - s0), SCM_T, smem, ctx->stream>>>(op->colptr, op->vals, op->ent_r, op->ent_c, \
-            op->sp_pid, op->sp_base, op->pos_r, op->pos_c, op->npos, op->Zinv, (int)n, op->H, m, s0, E);                     \
+            op->sp_pid, op->sp_base, op->pos_r, op->pos_c, op->npos, op->Zinv, (int)n, op->H, m, s0, E, op->ell_val,         \
+            op->ell_pid, op->ell_w, op->md);                                                                                 \
     } while (0)
         if (kpos <= 8) SCM_LAUNCH(8);
         else if (kpos <= 16) SCM_LAUNCH(16);

@@ -53,6 +53,55 @@ def _make(kind):
     raise ValueError(kind)
 
 
+def test_sparse_schur_kernel_matrix():
+    """Sparse-constraint technique (misc.SCMcolumn2, src/C/misc.c:620-663) with many more constraint entries than
+    positions: the materialised position kernel matrix (scm_kmat / scm_kstream) must give the SAME BITS as the
+    recomputing position kernel, and the oracle's H to rounding."""
+    import os
+    import smcp_b200 as S
+    from smcp_b200 import solvers
+    from smcp_b200.chordal import cspmatrix, cholesky, projected_inverse, schur_token
+    from oracle.backend import OracleBackend
+    fo, fd = _factories()
+    solvers.set_backend_factory(lambda symb: OracleBackend(symb))
+    rng = np.random.default_rng(21)
+    n = 200
+    e = rng.integers(0, n, size=(500, 2))
+    V = sp.coo_matrix((np.ones(500 + n), (np.concatenate([e[:, 0], np.arange(n)]),
+                                          np.concatenate([e[:, 1], np.arange(n)]))), shape=(n, n))
+    P = S.rand_SDP(V, 350, density=0.02, seed=6)
+    po, pd = _problem(P, fo), _problem(P, fd)
+    assert pd.Ns == po.Ns and pd.Ns > 300
+    symb = po.symb
+    s = np.zeros(symb.nvp)
+    s[symb.diag_vec] = 2.0
+    s += 0.05 * rng.standard_normal(symb.nvp)
+    Hs = {}
+    for tag, pr, env in (("oracle", po, None), ("kmat", pd, None), ("position", pd, "0")):
+        if env is not None:
+            os.environ["SMCP_B200_SCM_KMAT_GB"] = env
+        try:
+            L = cspmatrix.from_vec(pr.ops, s)
+            cholesky(L)
+            Y = L.copy()
+            projected_inverse(Y)
+            if pr is pd:
+                pr.ops.ctx.prof_enable(True)
+                pr.ops.ctx.prof_reset()
+            pr.ops.schur_assemble(schur_token(L, Y))
+            if pr is pd:
+                fam = {nm for nm in pr.ops.ctx.prof_names() if pr.ops.ctx.prof_get(nm)[1] > 0}
+                pr.ops.ctx.prof_enable(False)
+                assert ("scm_kstream" in fam) == (tag == "kmat"), (tag, sorted(fam))
+                assert ("scm_position" in fam) == (tag == "position"), (tag, sorted(fam))
+            H = pr.ops.get_H() if pr is pd else (pr.ops.H.copy() if getattr(pr.ops, "H", None) is not None else pr.ops.get_H())
+            Hs[tag] = np.tril(H)
+        finally:
+            os.environ.pop("SMCP_B200_SCM_KMAT_GB", None)
+    assert np.array_equal(Hs["kmat"], Hs["position"])
+    assert np.linalg.norm(Hs["kmat"] - Hs["oracle"]) <= 1e-11 * np.linalg.norm(Hs["oracle"])
+
+
 @pytest.mark.parametrize("kind", ["band", "mtxnorm", "rand_sparse", "rand_mixed", "maxcut"])
 def test_operator_and_schur(kind):
     from smcp_b200.chordal import cspmatrix, cholesky, projected_inverse, schur_token
