@@ -1127,7 +1127,10 @@ static int assemble_sparse_range(smcp_op *op, smcp_hess *h, int64_t s0, int64_t 
                 scm_kmat_kernel<<<(unsigned)op->npos, SCM_T, (size_t)2 * n * sizeof(double), ctx->stream>>>(op->pos_r, op->pos_c, op->npos, op->Zinv, (int)n, op->Kpos, ldk);
                 op->Kpos_valid = true;
             }
-            LaunchScope ls(ctx, "scm_kstream");
+            // algorithmic bytes: the nnz(A_j) columns of K each column j streams + the lower triangle of H written
+            const double kbytes_streamed = 8.0 * (double)ldk * (double)(op->h_colptr[s1] - op->h_colptr[s0])
+                                           + 8.0 * ((double)(m - s0) * (m - s0 + 1) - (double)(m - s1) * (m - s1 + 1)) / 2.0;
+            LaunchScope ls(ctx, "scm_kstream", 1, kbytes_streamed);
 #define SCM_KLAUNCH(K_)                                                                                                      \
     do {                                                                                                                    \
         CUDA_TRY(cudaFuncSetAttribute(scm_kstream_kernel<K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap * 8))); \
