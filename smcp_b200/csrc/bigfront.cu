@@ -423,6 +423,383 @@ int big_llt(smcp_sym *s, const BigNode &q, double *X, int64_t b) {
     return 0;
 }
 
+// ---- thin supernodes (nn <= THIN_NN columns under a large separator) ------------------------------
+// rand_SDP n = 2000: 41 of the 43 top-set supernodes have ONE or two columns under ~1100-row separators,
+// chained one per level.  Through the generic building blocks above one forward Hessian costs 22 launches
+// per supernode (16 up, 6 down) of which all but two touch nj x nn = a few thousand numbers: the sweep is a
+// chain of launch latencies (956 launches, 5.3 ms; the host cannot even issue them faster).  Here the nn-wide
+// algebra of a supernode is done by the threads that own the rows: 3 launches up, 1 down.
+#define THIN_NN 8
+static bool thin_on() {
+    static const bool off = getenv("SMCP_B200_NO_THIN") && atoi(getenv("SMCP_B200_NO_THIN")) != 0;
+    return !off;
+}
+
+// w <- (L L^T)^-1 w, L = Lnn (nn x nn lower, ld THIN_NN) in shared memory
+__device__ __forceinline__ void thin_dsolve(const double *Lnn, int nn, double (&w)[THIN_NN]) {
+#pragma unroll
+    for (int a = 0; a < THIN_NN; ++a) {
+        if (a < nn) {
+            double t = w[a];
+#pragma unroll
+            for (int b = 0; b < THIN_NN; ++b)
+                if (b < a) t = fma(-Lnn[a + b * THIN_NN], w[b], t);
+            w[a] = t / Lnn[a + a * THIN_NN];
+        }
+    }
+#pragma unroll
+    for (int a = THIN_NN - 1; a >= 0; --a) {
+        if (a < nn) {
+            double t = w[a];
+#pragma unroll
+            for (int b = THIN_NN - 1; b >= 0; --b)
+                if (b > a && b < nn) t = fma(-Lnn[b + a * THIN_NN], w[b], t);
+            w[a] = t / Lnn[a + a * THIN_NN];
+        }
+    }
+}
+
+// Forward Hessian, leaves-to-root pass, part 1: row i of alpha (one thread) forms F_an(i, :) (block + children),
+// K_an(i, :) = F_an(i, :) - Lt(i, :) F_nn and W(:, i) = D^-1 K_an(i, :)^T; CTA 0 also forms M_nn = D^-1 F_nn D^-1.
+__global__ void __launch_bounds__(128) thin_up_rows_kernel(BigArgs r, const double *__restrict__ blk, const double *__restrict__ Lb,
+                                                           double *__restrict__ FanOld, double *__restrict__ Kan, double *__restrict__ W,
+                                                           double *__restrict__ Mnn) {
+    __shared__ double Fnn[THIN_NN * THIN_NN], Lnn[THIN_NN * THIN_NN], T1[THIN_NN * THIN_NN];
+    const int nn = r.nn, na = r.na, nj = r.nj, tid = threadIdx.x;
+    if (tid < nn * nn) {
+        const int a = tid % nn, b = tid / nn;
+        const int hi = max(a, b), lo = min(a, b);
+        Fnn[a + b * THIN_NN] = blk[hi + (long long)lo * nj] + big_children(r, a, b, false);
+        Lnn[a + b * THIN_NN] = (a >= b) ? Lb[a + (long long)b * nj] : 0.0;
+    }
+    __syncthreads();
+    const int i = blockIdx.x * 128 + tid;
+    if (i < na) {
+        double fan[THIN_NN], kan[THIN_NN], lt[THIN_NN];
+#pragma unroll
+        for (int k = 0; k < THIN_NN; ++k) {
+            if (k < nn) {
+                fan[k] = blk[(nn + i) + (long long)k * nj] + big_children(r, nn + i, k, false);
+                lt[k] = Lb[(nn + i) + (long long)k * nj];
+            } else { fan[k] = 0.0; lt[k] = 0.0; }
+        }
+#pragma unroll
+        for (int k = 0; k < THIN_NN; ++k) {
+            double t = fan[k];
+            if (k < nn) {
+#pragma unroll
+                for (int l = 0; l < THIN_NN; ++l)
+                    if (l < nn) t = fma(-lt[l], Fnn[l + k * THIN_NN], t);
+            }
+            kan[k] = t;
+        }
+#pragma unroll
+        for (int k = 0; k < THIN_NN; ++k)
+            if (k < nn) {
+                FanOld[i + (long long)k * na] = fan[k];
+                Kan[i + (long long)k * na] = kan[k];
+            }
+        thin_dsolve(Lnn, nn, kan);
+#pragma unroll
+        for (int k = 0; k < THIN_NN; ++k)
+            if (k < nn) W[k + (long long)i * nn] = kan[k];
+    }
+    if (blockIdx.x == 0) {
+        // T1 = D^-1 F_nn (columns), M = T1 D^-1 (rows)
+        if (tid < nn) {
+            double c[THIN_NN];
+#pragma unroll
+            for (int a = 0; a < THIN_NN; ++a) c[a] = (a < nn) ? Fnn[a + tid * THIN_NN] : 0.0;
+            thin_dsolve(Lnn, nn, c);
+#pragma unroll
+            for (int a = 0; a < THIN_NN; ++a)
+                if (a < nn) T1[a + tid * THIN_NN] = c[a];
+        }
+        __syncthreads();
+        if (tid < nn) {
+            double c[THIN_NN];
+#pragma unroll
+            for (int b = 0; b < THIN_NN; ++b) c[b] = (b < nn) ? T1[tid + b * THIN_NN] : 0.0;
+            thin_dsolve(Lnn, nn, c);
+#pragma unroll
+            for (int b = 0; b < THIN_NN; ++b)
+                if (b < nn) Mnn[tid + b * nn] = c[b];
+        }
+    }
+}
+
+// part 2: U'(i, j) = children(i, j) - Lt(i, :) F_an(j, :)^T - K_an(i, :) Lt(j, :)^T over alpha x alpha (32 x 32 per CTA);
+// CTA (0, 0) stores M_nn (symmetrised, lower) into the block.
+__global__ void __launch_bounds__(256) thin_up_update_kernel(BigArgs r, const double *__restrict__ Lb, const double *__restrict__ FanOld,
+                                                             const double *__restrict__ Kan, const double *__restrict__ Mnn,
+                                                             double *__restrict__ blk, double *__restrict__ U) {
+    __shared__ double Li[THIN_NN][33], Lj[THIN_NN][33], Fj[THIN_NN][33], Ki[THIN_NN][33];
+    const int nn = r.nn, na = r.na, nj = r.nj, tid = threadIdx.x;
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    for (int idx = tid; idx < 32 * nn; idx += 256) {
+        const int rr = idx & 31, k = idx >> 5;
+        const bool vi = i0 + rr < na, vj = j0 + rr < na;
+        Li[k][rr] = vi ? Lb[(nn + i0 + rr) + (long long)k * nj] : 0.0;
+        Ki[k][rr] = vi ? Kan[(i0 + rr) + (long long)k * na] : 0.0;
+        Lj[k][rr] = vj ? Lb[(nn + j0 + rr) + (long long)k * nj] : 0.0;
+        Fj[k][rr] = vj ? FanOld[(j0 + rr) + (long long)k * na] : 0.0;
+    }
+    __syncthreads();
+    const int tx = tid & 31, ty = tid >> 5;
+    const int i = i0 + tx;
+    if (i < na) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int jj = ty + 8 * q, j = j0 + jj;
+            if (j < na) {
+                double v = big_children(r, nn + i, nn + j, false);
+                for (int k = 0; k < nn; ++k) v = fma(-Li[k][tx], Fj[k][jj], v);
+                for (int k = 0; k < nn; ++k) v = fma(-Ki[k][tx], Lj[k][jj], v);
+                U[i + (long long)j * na] = v;
+            }
+        }
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid < nn * nn) {
+        const int a = tid % nn, b = tid / nn;
+        blk[a + (long long)b * nj] = (a >= b) ? 0.5 * (Mnn[a + b * nn] + Mnn[b + a * nn]) : 0.0;
+    }
+}
+
+// Forward Hessian, root-to-leaves pass of a thin supernode in ONE launch: a CTA owns 32 rows of alpha,
+// Z_an(i, :) = M_an(i, :) - sum_k Z_aa(i, k) Lt(k, :) with Z_aa gathered from the ancestors' blocks (8 warps
+// split k, lane = row; partial sums combined in a fixed order), then its share of S = Lt^T M_an + Z_an^T Lt; the
+// CTA that finishes last adds the shares in CTA order and forms Z_nn = M_nn - sym(S)  (deterministic).
+__global__ void __launch_bounds__(256) thin_down_kernel(int nn, int na, int nj, const int *__restrict__ aaidx, const double *__restrict__ Xb,
+                                                        const double *__restrict__ Lb, double *__restrict__ blk, double *__restrict__ part,
+                                                        unsigned *__restrict__ counter) {
+    __shared__ double red[8][32][THIN_NN + 1];
+    __shared__ double Ssm[THIN_NN * THIN_NN];
+    __shared__ bool last_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    const int kc = (na + 7) / 8, k0 = warp * kc, k1 = min(na, k0 + kc);
+    double acc[THIN_NN];
+#pragma unroll
+    for (int l = 0; l < THIN_NN; ++l) acc[l] = 0.0;
+    if (i < na) {
+        const int *ai = aaidx + i;
+        const double *Lt = Lb + nn;
+        for (int k = k0; k < k1; ++k) {
+            const double z = Xb[ai[(long long)k * na]];
+#pragma unroll
+            for (int l = 0; l < THIN_NN; ++l)
+                if (l < nn) acc[l] = fma(z, __ldg(Lt + k + (long long)l * nj), acc[l]);
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < THIN_NN; ++l) red[warp][lane][l] = acc[l];
+    __syncthreads();
+    if (warp == 0) {
+        double mold[THIN_NN], zan[THIN_NN], lt[THIN_NN];
+#pragma unroll
+        for (int l = 0; l < THIN_NN; ++l) {
+            mold[l] = zan[l] = lt[l] = 0.0;
+            if (l < nn && i < na) {
+                double t = red[0][lane][l];
+#pragma unroll
+                for (int w = 1; w < 8; ++w) t += red[w][lane][l];
+                double *p = blk + (nn + i) + (long long)l * nj;
+                mold[l] = *p;
+                zan[l] = mold[l] - t;
+                *p = zan[l];
+                lt[l] = Lb[(nn + i) + (long long)l * nj];
+            }
+        }
+        // this CTA's share of S(a, b) = sum_i Lt(i, a) M_an(i, b) + Z_an(i, a) Lt(i, b)
+#pragma unroll
+        for (int a = 0; a < THIN_NN; ++a)
+#pragma unroll
+            for (int b = 0; b < THIN_NN; ++b)
+                if (a < nn && b < nn) {
+                    double v = fma(lt[a], mold[b], zan[a] * lt[b]);
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                    if (lane == 0) part[(long long)blockIdx.x * (THIN_NN * THIN_NN) + a + b * THIN_NN] = v;
+                }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned done = atomicAdd(counter, 1u);
+        last_s = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last_s) return;
+    __threadfence();
+    if (tid < nn * nn) {
+        const int a = tid % nn, b = tid / nn;
+        double sacc = 0.0;
+        for (unsigned c = 0; c < gridDim.x; ++c) sacc += __ldcg(part + (long long)c * (THIN_NN * THIN_NN) + a + b * THIN_NN);
+        Ssm[a + b * THIN_NN] = sacc;
+    }
+    __syncthreads();
+    if (tid < nn * nn) {
+        const int a = tid % nn, b = tid / nn;
+        double *d = blk + a + (long long)b * nj;
+        *d = (a >= b) ? *d - 0.5 * (Ssm[a + b * THIN_NN] + Ssm[b + a * THIN_NN]) : 0.0;
+    }
+    if (tid == 0) *counter = 0u;
+}
+
+// Inverse Hessian, per-supernode phase of a thin supernode in ONE launch (same layout as thin_down_kernel):
+// M_an(i, :) = Z_an(i, :) + sum_k Z_aa(i, k) Lt(k, :), the row of M_an D goes to Kan (the two triangular solves with
+// chol(Y_aa) follow), the CTA's share of Lt^T Z_an + M_an^T Lt to `part`; the last CTA forms K_nn = D (Z_nn + S) D.
+__global__ void __launch_bounds__(256) thin_hinv_local_kernel(int nn, int na, int nj, const int *__restrict__ aaidx, const double *__restrict__ Xb,
+                                                              const double *__restrict__ Lb, const double *__restrict__ blk,
+                                                              double *__restrict__ Knn, double *__restrict__ Kan, double *__restrict__ part,
+                                                              unsigned *__restrict__ counter) {
+    __shared__ double red[8][32][THIN_NN + 1];
+    __shared__ double Dsm[THIN_NN * THIN_NN], Msm[THIN_NN * THIN_NN], Tsm[THIN_NN * THIN_NN];
+    __shared__ bool last_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    const int kc = (na + 7) / 8, k0 = warp * kc, k1 = min(na, k0 + kc);
+    if (tid < nn * nn) {
+        // D = L L^T
+        const int a = tid % nn, b = tid / nn;
+        double t = 0.0;
+        for (int c = 0; c <= min(a, b); ++c) t = fma(Lb[a + (long long)c * nj], Lb[b + (long long)c * nj], t);
+        Dsm[a + b * THIN_NN] = t;
+    }
+    double acc[THIN_NN];
+#pragma unroll
+    for (int l = 0; l < THIN_NN; ++l) acc[l] = 0.0;
+    if (i < na) {
+        const int *ai = aaidx + i;
+        const double *Lt = Lb + nn;
+        for (int k = k0; k < k1; ++k) {
+            const double z = Xb[ai[(long long)k * na]];
+#pragma unroll
+            for (int l = 0; l < THIN_NN; ++l)
+                if (l < nn) acc[l] = fma(z, __ldg(Lt + k + (long long)l * nj), acc[l]);
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < THIN_NN; ++l) red[warp][lane][l] = acc[l];
+    __syncthreads();
+    if (warp == 0) {
+        double zan[THIN_NN], man[THIN_NN], lt[THIN_NN];
+#pragma unroll
+        for (int l = 0; l < THIN_NN; ++l) {
+            zan[l] = man[l] = lt[l] = 0.0;
+            if (l < nn && i < na) {
+                double t = red[0][lane][l];
+#pragma unroll
+                for (int w = 1; w < 8; ++w) t += red[w][lane][l];
+                zan[l] = blk[(nn + i) + (long long)l * nj];
+                man[l] = zan[l] + t;
+                lt[l] = Lb[(nn + i) + (long long)l * nj];
+            }
+        }
+        if (i < na) {
+#pragma unroll
+            for (int b = 0; b < THIN_NN; ++b)
+                if (b < nn) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int a = 0; a < THIN_NN; ++a)
+                        if (a < nn) t = fma(man[a], Dsm[a + b * THIN_NN], t);
+                    Kan[i + (long long)b * na] = t;
+                }
+        }
+#pragma unroll
+        for (int a = 0; a < THIN_NN; ++a)
+#pragma unroll
+            for (int b = 0; b < THIN_NN; ++b)
+                if (a < nn && b < nn) {
+                    double v = fma(lt[a], zan[b], man[a] * lt[b]);
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                    if (lane == 0) part[(long long)blockIdx.x * (THIN_NN * THIN_NN) + a + b * THIN_NN] = v;
+                }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned done = atomicAdd(counter, 1u);
+        last_s = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last_s) return;
+    __threadfence();
+    if (tid < nn * nn) {
+        const int a = tid % nn, b = tid / nn;
+        const int hi = max(a, b), lo = min(a, b);
+        double sacc = blk[hi + (long long)lo * nj];
+        for (unsigned c = 0; c < gridDim.x; ++c) sacc += __ldcg(part + (long long)c * (THIN_NN * THIN_NN) + a + b * THIN_NN);
+        Msm[a + b * THIN_NN] = sacc;
+    }
+    __syncthreads();
+    if (tid < nn * nn) {
+        const int a = tid % nn, b = tid / nn;
+        double t = 0.0;
+        for (int c = 0; c < nn; ++c) t = fma(Dsm[a + c * THIN_NN], Msm[c + b * THIN_NN], t);
+        Tsm[a + b * THIN_NN] = t;
+    }
+    __syncthreads();
+    if (tid < nn * nn) {
+        const int a = tid % nn, b = tid / nn;
+        double t = 0.0;
+        for (int c = 0; c < nn; ++c) t = fma(Tsm[a + c * THIN_NN], Dsm[c + b * THIN_NN], t);
+        Knn[a + b * nn] = t;
+    }
+    if (tid == 0) *counter = 0u;
+}
+
+// Inverse Hessian, leaves-to-root sweep of a thin supernode in ONE launch: F_an = K_an + Lt K_nn,
+// U = Lt K_an^T + F_an Lt^T + children over alpha x alpha (32 x 32 per CTA); the CTAs of the first tile column
+// also store F_an + children into the block, CTA (0, 0) the symmetrised K_nn + children.
+__global__ void __launch_bounds__(256) thin_hinv_sweep_kernel(BigArgs r, const double *__restrict__ Lb, const double *__restrict__ Knn,
+                                                              const double *__restrict__ Kan, double *__restrict__ blk, double *__restrict__ U) {
+    __shared__ double Li[THIN_NN][33], Lj[THIN_NN][33], Kj[THIN_NN][33], Fi[THIN_NN][33], Ks[THIN_NN * THIN_NN];
+    const int nn = r.nn, na = r.na, nj = r.nj, tid = threadIdx.x;
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    if (tid < nn * nn) Ks[(tid % nn) + (tid / nn) * THIN_NN] = Knn[tid];
+    for (int idx = tid; idx < 32 * nn; idx += 256) {
+        const int rr = idx & 31, k = idx >> 5;
+        const bool vi = i0 + rr < na, vj = j0 + rr < na;
+        Li[k][rr] = vi ? Lb[(nn + i0 + rr) + (long long)k * nj] : 0.0;
+        Lj[k][rr] = vj ? Lb[(nn + j0 + rr) + (long long)k * nj] : 0.0;
+        Kj[k][rr] = vj ? Kan[(j0 + rr) + (long long)k * na] : 0.0;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 32 * nn; idx += 256) {
+        const int rr = idx & 31, k = idx >> 5;
+        double t = (i0 + rr < na) ? Kan[(i0 + rr) + (long long)k * na] : 0.0;
+        for (int c = 0; c < nn; ++c) t = fma(Li[c][rr], Ks[c + k * THIN_NN], t);
+        Fi[k][rr] = t;
+    }
+    __syncthreads();
+    const int tx = tid & 31, ty = tid >> 5;
+    const int i = i0 + tx;
+    if (i < na) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int jj = ty + 8 * q, j = j0 + jj;
+            if (j < na) {
+                double v = 0.0;
+                for (int k = 0; k < nn; ++k) v = fma(Li[k][tx], Kj[k][jj], v);
+                for (int k = 0; k < nn; ++k) v = fma(Fi[k][tx], Lj[k][jj], v);
+                U[i + (long long)j * na] = v + big_children(r, nn + i, nn + j, false);
+            }
+        }
+        if (blockIdx.y == 0 && ty < nn) {
+            for (int k = ty; k < nn; k += 8) blk[(nn + i) + (long long)k * nj] = Fi[k][tx] + big_children(r, nn + i, k, false);
+        }
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid < nn * nn) {
+        const int a = tid % nn, b = tid / nn;
+        if (a >= b) {
+            const double x = Ks[a + b * THIN_NN] + big_children(r, a, b, false);
+            const double y = Ks[b + a * THIN_NN] + big_children(r, b, a, false);
+            blk[a + (long long)b * nj] = 0.5 * (x + y);
+        } else blk[a + (long long)b * nj] = 0.0;
+    }
+}
+
 // ---- forward Hessian, pass 1 + scaling ---------------------------------------------------
 int big_hess_up(smcp_sym *s, const BigNode &q, const double *Lt, const double *Yaa_all, double *X, int64_t b) {
     smcp_ctx *ctx = s->ctx;
@@ -431,6 +808,21 @@ int big_hess_up(smcp_sym *s, const BigNode &q, const double *Lt, const double *Y
     double *Uk = s->upd + (size_t)b * s->d.nupd + q.uoff;
     const double *Lb = Lt + q.boff, *Ltan = Lb + nn, *Yaa = Yaa_all + q.uoff;
     double *F = WS(0), *T1 = WS(1), *T2 = WS(2);
+    if (nn <= THIN_NN && na >= 1 && thin_on()) {
+        double *FanOld = WS(0), *Kan = FanOld + (size_t)na * nn, *W = Kan + (size_t)na * nn, *Mnn = W + (size_t)na * nn;
+        const BigArgs ra = big_args(s, q, b);
+        {
+            LaunchScope ls_(ctx, "front_thin");
+            thin_up_rows_kernel<<<(unsigned)((na + 127) / 128), 128, 0, ctx->stream>>>(ra, blk, Lb, FanOld, Kan, W, Mnn);
+        }
+        {
+            LaunchScope ls_(ctx, "front_thin");
+            thin_up_update_kernel<<<dim3((unsigned)((na + 31) / 32), (unsigned)((na + 31) / 32)), 256, 0, ctx->stream>>>(ra, Lb, FanOld, Kan, Mnn, blk, Uk);
+        }
+        if (G(s, false, false, Yaa, na, W, nn, blk + nn, nj, na, nn, na, 1.0, 0)) return -1;        // M_an = Y_aa W^T
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     double *Fan = F + nn, *Faa = F + nn + (size_t)nn * nj, *Fna = F + (size_t)nn * nj;
     ELEM(big_front_full_kernel, (long long)nj * nj, big_args(s, q, b), blk, F);
     if (na) {
@@ -470,6 +862,18 @@ int big_hess_down(smcp_sym *s, const BigNode &q, const double *Lt, double *X, in
     double *blk = Xb + q.boff;
     const double *Ltan = Lt + q.boff + nn;
     double *Zaa = WS(0), *Mold = WS(1), *S = WS(2);
+    if (nn <= THIN_NN && na >= 1 && thin_on()) {
+        if (!s->thin_counters) {
+            CUDA_TRY(cudaMalloc(&s->thin_counters, 64 * sizeof(unsigned)));
+            CUDA_TRY(cudaMemset(s->thin_counters, 0, 64 * sizeof(unsigned)));
+            s->allocs.push_back(s->thin_counters);
+        }
+        LaunchScope ls_(ctx, "front_thin");
+        thin_down_kernel<<<(unsigned)((na + 31) / 32), 256, 0, ctx->stream>>>(nn, na, nj, s->d.aaidx + q.uoff, Xb, Lt + q.boff, blk, WS(0),
+                                                                              s->thin_counters + s->big_lane);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     ELEM(big_gather_aa_kernel, (long long)na * na, s->d.aaidx + q.uoff, Xb, Zaa, (long long)na * na);
     ELEM(big_copy_mat_kernel, (long long)na * nn, blk + nn, nj, Mold, na, na, nn, 0);
     // Z_an = M_an - Z_aa Lt
@@ -496,6 +900,22 @@ int big_hess_inv_local(smcp_sym *s, const BigNode &q, const double *Lt, const do
     const double *Lb = Lt + q.boff, *Ltan = Lb + nn, *R = Raa_all + q.uoff;
     double *D = WS(0), *Zaa = WS(1), *Man = WS(2), *T = WS(4);
     double *Mnn = KS + q.boff, *Kan = Mnn + (size_t)nn * nn;
+    if (nn <= THIN_NN && na >= 1 && thin_on()) {
+        if (!s->thin_counters) {
+            CUDA_TRY(cudaMalloc(&s->thin_counters, 64 * sizeof(unsigned)));
+            CUDA_TRY(cudaMemset(s->thin_counters, 0, 64 * sizeof(unsigned)));
+            s->allocs.push_back(s->thin_counters);
+        }
+        {
+            LaunchScope ls_(ctx, "front_thin");
+            thin_hinv_local_kernel<<<(unsigned)((na + 31) / 32), 256, 0, ctx->stream>>>(nn, na, nj, s->d.aaidx + q.uoff, Xb, Lb, blk, Mnn, Kan, WS(0),
+                                                                                        s->thin_counters + s->big_lane);
+        }
+        if (d_trsm_left_lower(ctx, false, R, na, na, Kan, na, nn)) return -1;                      // K_an = Y_aa^-1 M_an D
+        if (d_trsm_left_lower(ctx, true, R, na, na, Kan, na, nn)) return -1;
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     if (G(s, false, false, Lb, nj, Lb, nj, D, nn, nn, nn, nn, 1.0, 0)) return -1;                 // D = L L^T (full)
     ELEM(big_sym_copy_kernel, (long long)nn * nn, blk, nj, Mnn, nn, nn);                          // Z_nn (full)
     if (na) {
@@ -524,6 +944,13 @@ int big_hess_inv_sweep(smcp_sym *s, const BigNode &q, const double *Lt, double *
     const double *Ltan = Lt + q.boff + nn;
     const double *Mnn = KS + q.boff, *Kan = Mnn + (size_t)nn * nn;
     double *Zaa = WS(1), *Man = WS(2);
+    if (nn <= THIN_NN && na >= 1 && thin_on()) {
+        LaunchScope ls_(ctx, "front_thin");
+        thin_hinv_sweep_kernel<<<dim3((unsigned)((na + 31) / 32), (unsigned)((na + 31) / 32)), 256, 0, ctx->stream>>>(big_args(s, q, b), Lt + q.boff, Mnn,
+                                                                                                                      Kan, blk, Uk);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     if (na) {
         ELEM(big_copy_mat_kernel, (long long)na * nn, Kan, na, Man, na, na, nn, 0);
         if (G(s, false, true, Ltan, nj, Mnn, nn, Man, na, na, nn, nn, 1.0, 1)) return -1;          // F_an = K_an + Lt K_nn

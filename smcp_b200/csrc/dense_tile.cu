@@ -79,12 +79,17 @@ __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned &target) {
 
 // Cholesky of the 64 x 64 tile in D (kb pivots; the trailing part of the tile receives the Schur
 // complement), all 256 threads: thread (i, jq) keeps the entries (i, 16 jq .. 16 jq + 15) of the lower
-// triangle in REGISTERS; per pivot the (unscaled) pivot column goes through a double-buffered 64-entry
-// column in shared memory and the thread that owns the next diagonal entry computes 1/sqrt(pivot) for the
-// NEXT step before the barrier: one barrier per pivot, a_ij -= a_ic a_jc / d_c on registers.
-// Returns the 1-based index of the first non-positive pivot (0 = none) in *bad_s.
-__device__ __forceinline__ void tile_chol64(double *D, double *rs, double *rinv_s, double *dsv, double *colbuf, int *bad_s, int kb, int tid) {
-    const int i = tid & 63, jq = tid >> 6;
+// triangle in REGISTERS.  The tile is processed in four 16-column sub-steps; per sub-step
+//   (a) the 16 x 16 diagonal block is factored by the 16 lanes that hold its rows: the pivot column
+//       travels by width-16 shuffles, every lane computes 1/sqrt(pivot) itself -- no block barrier
+//       per pivot (the previous version had one __syncthreads per pivot: 0.45 us x 64 = 29 us a tile),
+//   (b) the rows below it solve against the block from shared memory, thread-local in registers,
+//   (c) the later column blocks take the rank-16 update; L(:, 16 s ..) is exchanged through Ls
+//       (two 16 x 64 buffers alternating with s: two barriers per sub-step in all).
+// rs[c] = 1/sqrt(pivot c).  The 1-based index of the first non-positive pivot (0 = none) goes to *bad_s.
+#define PT_FULL 0xffffffffu
+__device__ __forceinline__ void tile_chol64(double *D, double *rs, double *Ls, int *bad_s, int kb, int tid) {
+    const int i = tid & 63, jq = tid >> 6, lane = tid & 31;
     double a[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
@@ -92,54 +97,132 @@ __device__ __forceinline__ void tile_chol64(double *D, double *rs, double *rinv_
         a[q] = (j <= i) ? D[j * DLD + i] : 0.0;
     }
     if (tid == 0) *bad_s = 0;
-    if (jq == 0) {
-        colbuf[i] = a[0];
-        if (i == 0) {
-            double d = a[0];
-            if (!(d > 0.0)) { *bad_s = 1; d = 1.0; }
-            const double r = rsqrt(d);
-            rs[0] = r; rinv_s[0] = r * r; dsv[0] = d;
-        }
-    }
-    __syncthreads();
 #pragma unroll 1
-    for (int cb = 0; cb < 4; ++cb) {
+    for (int s = 0; s < 4; ++s) {
+        const int nbs = min(16, kb - 16 * s);
+        if (nbs <= 0) break;
+        double *Lb = Ls + (s & 1) * (16 * TT);
+        if ((tid >> 5) == ((80 * s) >> 5)) {
+            // (a) this warp holds rows 16 s .. 16 s + 15 of column block s in one of its halves; the other
+            // half runs along on its own (unused) copy
+            const int t = lane & 15;
+            const bool mine = (i >> 4) == s;
+            double b[16];
 #pragma unroll
-        for (int cq = 0; cq < 16; ++cq) {
-            const int c = 16 * cb + cq;
-            if (c < kb) {
-                const double *col = colbuf + (c & 1) * 64;
-                if (i > c && 16 * jq + 15 > c) {
-                    const double t = col[i] * rinv_s[c];
-                    const double2 *c2 = reinterpret_cast<const double2 *>(col + 16 * jq);
+            for (int q = 0; q < 16; ++q) b[q] = a[q];
+            int bad = 0;
+            double d = __shfl_sync(PT_FULL, b[0], 0, 16);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                if (c < nbs) {
+                    if (!(d > 0.0)) { if (!bad) bad = c + 1; d = 1.0; }
+                    const double r = rsqrt(d);
+                    const double l = b[c] * r;
+                    b[c] = l;
+                    if (mine && t == c) rs[16 * s + c] = r;
+                    if (c + 1 < 16) {
+                        // next pivot straight from its owner (on lane c + 1 the shuffled l1 below is its own l:
+                        // same value, one shuffle less on the pivot-to-pivot dependency chain)
+                        d = __shfl_sync(PT_FULL, fma(-l, l, b[c + 1]), c + 1, 16);
+                        const double l1 = __shfl_sync(PT_FULL, l, c + 1, 16);
+                        b[c + 1] = fma(-l, l1, b[c + 1]);
+                    }
+#pragma unroll
+                    for (int j = c + 2; j < 16; ++j) {
+                        const double lj = __shfl_sync(PT_FULL, l, j, 16);
+                        b[j] = fma(-l, lj, b[j]);
+                    }
+                }
+            }
+            if (mine) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    a[q] = b[q];
+                    Lb[q * TT + i] = (q <= t) ? b[q] : 0.0;
+                }
+                if (t == 0 && bad && !*bad_s) *bad_s = 16 * s + bad;
+            }
+        }
+        __syncthreads();
+        if (jq == s && i >= 16 * s + 16) {
+            // (b) l_ic = (a_ic - sum_{c' < c} l_ic' l_cc') / l_cc, right-looking over the block's columns
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                if (c < nbs) {
+                    const double l = a[c] * rs[16 * s + c];
+                    a[c] = l;
+#pragma unroll
+                    for (int j = c + 1; j < 16; ++j) a[j] = fma(-l, Lb[c * TT + 16 * s + j], a[j]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) Lb[q * TT + i] = a[q];
+        }
+        __syncthreads();
+        if (jq > s && i >= 16 * jq) {
+            // (c) a_ij -= sum_c l_ic l_jc for the columns j of block jq
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                if (c < nbs) {
+                    const double li = Lb[c * TT + i];
+                    const double2 *lc = reinterpret_cast<const double2 *>(Lb + c * TT + 16 * jq);
 #pragma unroll
                     for (int q2 = 0; q2 < 8; ++q2) {
-                        const double2 lv = c2[q2];
-                        const int j = 16 * jq + 2 * q2;
-                        if (j > c && j <= i) a[2 * q2] = fma(-t, lv.x, a[2 * q2]);
-                        if (j + 1 > c && j + 1 <= i) a[2 * q2 + 1] = fma(-t, lv.y, a[2 * q2 + 1]);
+                        const double2 lv = lc[q2];
+                        a[2 * q2] = fma(-li, lv.x, a[2 * q2]);
+                        a[2 * q2 + 1] = fma(-li, lv.y, a[2 * q2 + 1]);
                     }
                 }
-                // publish column c + 1 (final after this update) and its pivot
-                if (c + 1 < kb && jq == ((c + 1) >> 4)) {
-                    const double v = a[(cq + 1) & 15];
-                    colbuf[((c + 1) & 1) * 64 + i] = v;
-                    if (i == c + 1) {
-                        double d = v;
-                        if (!(d > 0.0)) { if (!*bad_s) *bad_s = c + 2; d = 1.0; }
-                        const double r = rsqrt(d);
-                        rs[c + 1] = r; rinv_s[c + 1] = r * r; dsv[c + 1] = d;
-                    }
-                }
-                __syncthreads();
             }
         }
     }
-    // scaled factor (columns < kb) and the untouched-scale trailing part back to D
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
         const int j = 16 * jq + q;
-        if (j <= i) D[j * DLD + i] = (j < kb) ? ((i == j) ? dsv[j] * rs[j] : a[q] * rs[j]) : a[q];
+        if (j <= i) D[j * DLD + i] = a[q];
+    }
+    __syncthreads();
+}
+
+// Panel tile X L^T = B against the factored diagonal tile in D (kb pivots; the columns past kb take the
+// Schur complement): thread (r, jq) keeps the entries (r, 16 jq .. 16 jq + 15) of the tile in registers,
+// same sub-step scheme as tile_chol64 without its phase (a).
+__device__ __forceinline__ void tile_panel64(const double *D, const double *rs, double *Ls, double (&x)[16], int kb, int tid) {
+    const int r = tid & 63, jq = tid >> 6;
+#pragma unroll 1
+    for (int s = 0; s < 4; ++s) {
+        const int nbs = min(16, kb - 16 * s);
+        if (nbs <= 0) break;
+        double *Lb = Ls + (s & 1) * (16 * TT);
+        if (jq == s) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                if (c < nbs) {
+                    const double l = x[c] * rs[16 * s + c];
+                    x[c] = l;
+#pragma unroll
+                    for (int j = c + 1; j < 16; ++j) x[j] = fma(-l, D[(16 * s + c) * DLD + 16 * s + j], x[j]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) Lb[q * TT + r] = x[q];
+        }
+        __syncthreads();
+        if (jq > s) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                if (c < nbs) {
+                    const double li = Lb[c * TT + r];
+                    const double2 *lc = reinterpret_cast<const double2 *>(D + (16 * s + c) * DLD + 16 * jq);
+#pragma unroll
+                    for (int q2 = 0; q2 < 8; ++q2) {
+                        const double2 lv = lc[q2];
+                        x[2 * q2] = fma(-li, lv.x, x[2 * q2]);
+                        x[2 * q2 + 1] = fma(-li, lv.y, x[2 * q2 + 1]);
+                    }
+                }
+            }
+        }
     }
     __syncthreads();
 }
@@ -148,11 +231,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) potrf_tile_kernel(PotrfTileArgs
     extern __shared__ __align__(16) double ptsm[];
     double *D = ptsm;                    // TT x DLD, D[c*DLD + r] = tile(r, c)
     double *rs = D + TT * DLD;           // 1/sqrt(pivot)
-    double *dsv = rs + TT;               // pivots
-    double *rinv_s = dsv + TT;           // 1/pivot
-    double *colbuf = rinv_s + TT;        // 2 x 64
-    double *Dp = colbuf + 2 * TT;        // TT x 72: the factored tile with its four 16-row groups 18 apart (panel solve)
-    double *W = Dp + TT * 72;            // phase B: As | Bs
+    double *Ls = rs + TT;                // 2 x (16 x TT): L(:, 16 s ..) of the current sub-step (tile_chol64 / tile_panel64)
+    double *W = Ls + 2 * 16 * TT;        // phase B: As | Bs
     __shared__ short2 own[PT_MAXOWN];
     __shared__ int nown_s, bad_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -196,52 +276,24 @@ __global__ void __launch_bounds__(PT_THREADS, 1) potrf_tile_kernel(PotrfTileArgs
                 D[c * DLD + r] = v;
             }
             __syncthreads();
-            tile_chol64(D, rs, rinv_s, dsv, colbuf, &bad_s, kb, tid);
+            tile_chol64(D, rs, Ls, &bad_s, kb, tid);
             if (diag_owner && bad_s && tid == 0 && *a.info == 0) *a.info = a.col_off + (int)kc + bad_s;
-            // copy for the panel solve: four lanes read four different 16-row groups of a column at once;
-            // 18 doubles apart they fall into different banks (in D they are 128 bytes apart: 4-way conflicts)
-            for (int idx = tid; idx < TT * TT; idx += PT_THREADS) {
-                const int r = idx & 63, c = idx >> 6;
-                Dp[c * 72 + 18 * (r >> 4) + (r & 15)] = D[c * DLD + r];
-            }
-            __syncthreads();
             PT_STAMP(1);
-            // ---- panel tiles (i, k), i > k: X L^T = B.  Four consecutive lanes share a row (16 columns
-            // each in registers); the pivot column's x is broadcast by a shuffle inside the lane group.
+            // ---- panel tiles (i, k), i > k: X L^T = B
             for (int q = 0; q < nown; ++q) {
                 if (own[q].y != k || own[q].x == k) continue;
-                const int r = tid >> 2, p = tid & 3;
+                const int r = tid & 63, jq = tid >> 6;
                 const long long R = (long long)TT * own[q].x + r;
                 const bool live = R < mm;
-                double *Pg = H + R + (kc + 16 * p) * ld;
+                double *Pg = H + R + (kc + 16 * jq) * ld;
                 double x[16];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) x[e] = (live && kc + 16 * p + e < mm) ? Pg[(long long)e * ld] : 0.0;
-                const int gbase = lane & ~3;
-#pragma unroll 1
-                for (int pc = 0; pc < 4; ++pc) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const int c = 16 * pc + e;
-                        if (c < kb) {
-                            const double xc = __shfl_sync(0xffffffffu, x[e] * rs[c], gbase + pc);
-                            if (p == pc) x[e] = xc;
-                            if (p >= pc) {
-                                const double2 *lc = reinterpret_cast<const double2 *>(Dp + c * 72 + 18 * p);
-#pragma unroll
-                                for (int e2 = 0; e2 < 8; ++e2) {
-                                    const double2 lv = lc[e2];
-                                    if (16 * p + 2 * e2 > c) x[2 * e2] = fma(-xc, lv.x, x[2 * e2]);
-                                    if (16 * p + 2 * e2 + 1 > c) x[2 * e2 + 1] = fma(-xc, lv.y, x[2 * e2 + 1]);
-                                }
-                            }
-                        }
-                    }
-                }
+                for (int e = 0; e < 16; ++e) x[e] = (live && kc + 16 * jq + e < mm) ? Pg[(long long)e * ld] : 0.0;
+                tile_panel64(D, rs, Ls, x, kb, tid);
                 if (live) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e)
-                        if (kc + 16 * p + e < mm) Pg[(long long)e * ld] = x[e];
+                        if (kc + 16 * jq + e < mm) Pg[(long long)e * ld] = x[e];
                 }
             }
         }
@@ -309,7 +361,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) potrf_tile_kernel(PotrfTileArgs
     }
 }
 
-static size_t potrf_tile_smem() { return (size_t)(TT * DLD + 5 * TT + TT * 72 + 2 * TT * OLDT) * sizeof(double); }
+static size_t potrf_tile_smem() { return (size_t)(TT * DLD + TT + 2 * 16 * TT + 2 * TT * OLDT) * sizeof(double); }
 
 // Largest order handled by one launch (tiles per CTA bounded by PT_MAXOWN)
 bool potrf_tile_fits(const smcp_ctx *ctx, int64_t mm, int64_t npiv, bool panel_only) {

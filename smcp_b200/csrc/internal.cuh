@@ -186,6 +186,7 @@ struct smcp_sym {
     double *big_ws = nullptr;      // BIG_NWS workspaces per lane
     size_t big_ws_stride = 0;
     int *big_info = nullptr;       // one flag per lane
+    unsigned *thin_counters = nullptr;   // one arrival counter per lane (thin_down_kernel)
     std::vector<std::vector<int>> big_up, big_down;   // indices into `big` by height (leaves first) / by depth (root first)
     int big_nlanes = 1;            // lanes the top set may use (1 = everything on the main stream)
     int big_lane = 0;              // lane the next big_* call works in
