@@ -314,6 +314,7 @@ int k_hess_prep_inv(smcp_hess *h) {
     smcp_sym *s = h->sym;
     if (sym_ensure(s, 1, false)) return -1;
     CUDA_TRY(cudaMemsetAsync(s->fail, 0, sizeof(int), s->ctx->stream));
+    h->raa_gen = ++s->raa_gen_next;
     TreeArgs a = {};
     a.Yaa = h->Yaa;
     a.Raa = h->Raa;
@@ -388,6 +389,7 @@ int k_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
         smcp_ctx *ctx = s->ctx;
         if (grow((void **)&s->big_hinv, &s->big_hinv_cap, (size_t)s->d.nblk * sizeof(double))) return -1;
         const int nr = dist_ops(s, batch), rk = ctx->comm_rank;
+        s->raa_gen_cur = h->raa_gen;
         for (int64_t b = 0; b < batch; ++b) {
             const int nl = big_lanes_begin(s);
             if (nl < 0) return -1;

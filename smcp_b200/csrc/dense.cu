@@ -679,7 +679,7 @@ static int d_potrf_chain(smcp_ctx *ctx, double *H, int64_t ld, int64_t m, int64_
     const int64_t nblocks = (ncols + OB - 1) / OB;
     if (nranks > 1 && (ld != m || ncols != m)) { smcp_set_error("d_potrf: the distributed factorisation needs a full square matrix"); return -2; }
     // one profiling scope for the whole factorisation (the two streams overlap)
-    LaunchScope outer(ctx, "potrf_dmma", 0, (double)ncols * ncols * ncols / 3.0 + (double)(m - ncols) * ncols * (double)m);
+    LaunchScope outer(ctx, ctx->potrf_family ? ctx->potrf_family : "potrf_dmma", 0, (double)ncols * ncols * ncols / 3.0 + (double)(m - ncols) * ncols * (double)m);
     ctx->prof_mute++;
     struct Unmute { smcp_ctx *c; ~Unmute() { c->prof_mute--; } } unmute{ctx};
     cudaStream_t sB = ctx->stream, sA = ctx->stream2;
@@ -764,7 +764,7 @@ int d_potrf(smcp_ctx *ctx, double *H, int64_t ld, int64_t m, int64_t ncols, int3
     if (m <= 0 || ncols <= 0) return 0;
     static const int64_t tile_max = getenv("SMCP_B200_POTRF_TILE_MAX") ? atoll(getenv("SMCP_B200_POTRF_TILE_MAX")) : 2560;
     if (nranks > 1 && (ld != m || ncols != m)) { smcp_set_error("d_potrf: the distributed factorisation needs a full square matrix"); return -2; }
-    LaunchScope outer(ctx, "potrf_dmma", 0, (double)ncols * ncols * ncols / 3.0 + (double)(m - ncols) * ncols * (double)m);
+    LaunchScope outer(ctx, ctx->potrf_family ? ctx->potrf_family : "potrf_dmma", 0, (double)ncols * ncols * ncols / 3.0 + (double)(m - ncols) * ncols * (double)m);
     ctx->prof_mute++;
     struct Unmute { smcp_ctx *c; ~Unmute() { c->prof_mute--; } } unmute{ctx};
     CUDA_TRY(cudaMemsetAsync(info_dev, 0, sizeof(int), ctx->stream));

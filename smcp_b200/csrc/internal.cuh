@@ -56,6 +56,7 @@ struct smcp_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;                 // look-ahead stream of the dense Cholesky (panels + broadcasts)
     std::vector<cudaEvent_t> potrf_ev;              // fork/join events of the look-ahead pipeline
+    const char *potrf_family = nullptr;             // profile family of the next d_potrf (default "potrf_dmma")
     int prof_mute = 0;                              // > 0: nested LaunchScopes do not time (an outer scope does)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;       // user timer
     cudaEvent_t pev0 = nullptr, pev1 = nullptr;     // profiling events
@@ -187,6 +188,10 @@ struct smcp_sym {
     size_t big_ws_stride = 0;
     int *big_info = nullptr;       // one flag per lane
     unsigned *thin_counters = nullptr;   // one arrival counter per lane (thin_down_kernel)
+    double *thin_dinv = nullptr;         // inverted diagonal blocks of R = chol(Y_aa) per top-set supernode (thin inverse Hessian)
+    std::vector<size_t> thin_dinv_off;
+    std::vector<uint64_t> thin_dinv_gen; // scaling point (raa_gen) the cached blocks belong to
+    uint64_t raa_gen_next = 0, raa_gen_cur = 0;
     std::vector<std::vector<int>> big_up, big_down;   // indices into `big` by height (leaves first) / by depth (root first)
     int big_nlanes = 1;            // lanes the top set may use (1 = everything on the main stream)
     int big_lane = 0;              // lane the next big_* call works in
@@ -210,6 +215,7 @@ struct smcp_hess {
     double *Yaa = nullptr;     // nupd: Y_{alpha alpha}, full symmetric
     double *Raa = nullptr;     // nupd: chol(Y_aa) (lazily, for the inverse map)
     bool have_Raa = false;
+    uint64_t raa_gen = 0;          // generation of Raa (keys caches derived from it: smcp_sym::thin_dinv)
     double *phi_up = nullptr, *phi_dn = nullptr, *psi_up = nullptr, *psi_dn = nullptr;   // chain path: segment propagators of the two sweeps
     bool have_phi = false;
     bool chain_ok = true;      // the segment propagators of this scaling point are tame enough for the segment-parallel sweeps
