@@ -441,6 +441,10 @@ int big_llt(smcp_sym *s, const BigNode &q, double *X, int64_t b) {
 // chain of launch latencies (956 launches, 5.3 ms; the host cannot even issue them faster).  Here the nn-wide
 // algebra of a supernode is done by the threads that own the rows: 3 launches up, 1 down.
 #define THIN_NN 8
+static bool dinv_on() {
+    static const bool off = getenv("SMCP_B200_NO_DINV") && atoi(getenv("SMCP_B200_NO_DINV")) != 0;
+    return !off;
+}
 static bool thin_on() {
     static const bool off = getenv("SMCP_B200_NO_THIN") && atoi(getenv("SMCP_B200_NO_THIN")) != 0;
     return !off;
@@ -470,90 +474,39 @@ __device__ __forceinline__ void thin_dsolve(const double *Lnn, int nn, double (&
     }
 }
 
-// Forward Hessian, leaves-to-root pass, part 1: row i of alpha (one thread) forms F_an(i, :) (block + children),
-// K_an(i, :) = F_an(i, :) - Lt(i, :) F_nn and W(:, i) = D^-1 K_an(i, :)^T; CTA 0 also forms M_nn = D^-1 F_nn D^-1.
-__global__ void __launch_bounds__(128) thin_up_rows_kernel(BigArgs r, const double *__restrict__ blk, const double *__restrict__ Lb,
-                                                           double *__restrict__ FanOld, double *__restrict__ Kan, double *__restrict__ W,
-                                                           double *__restrict__ Mnn) {
-    __shared__ double Fnn[THIN_NN * THIN_NN], Lnn[THIN_NN * THIN_NN], T1[THIN_NN * THIN_NN];
+// Forward Hessian, leaves-to-root pass of a thin supernode in ONE launch over alpha x alpha (32 x 32 per CTA).  Every CTA
+// forms F_nn (block + children) and, for its 32 rows i and 32 rows j of alpha, F_an (block + children) and
+// K_an = F_an - Lt F_nn (a few hundred numbers: cheaper than a launch that would hand them over), then
+//     U'(i, j) = children(i, j) - Lt(i, :) F_an(j, :)^T - K_an(i, :) Lt(j, :)^T.
+// The CTAs of the first tile column leave W(:, i) = D^-1 K_an(i, :)^T for the product M_an = Y_aa W^T that follows;
+// the CTA that finishes LAST (every CTA has read the block's nn x nn part by then) stores M_nn = D^-1 F_nn D^-1 into it.
+__global__ void __launch_bounds__(256) thin_up_kernel(BigArgs r, const double *__restrict__ Lb, double *__restrict__ blk, double *__restrict__ U,
+                                                      double *__restrict__ W, unsigned *__restrict__ counter) {
+    __shared__ double Li[THIN_NN][33], Lj[THIN_NN][33], Fi[THIN_NN][33], Fj[THIN_NN][33], Ki[THIN_NN][33];
+    __shared__ double Fnn[THIN_NN * THIN_NN], Lnn[THIN_NN * THIN_NN], T1[THIN_NN * THIN_NN], Msm[THIN_NN * THIN_NN];
+    __shared__ bool last_s;
     const int nn = r.nn, na = r.na, nj = r.nj, tid = threadIdx.x;
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
     if (tid < nn * nn) {
         const int a = tid % nn, b = tid / nn;
         const int hi = max(a, b), lo = min(a, b);
         Fnn[a + b * THIN_NN] = blk[hi + (long long)lo * nj] + big_children(r, a, b, false);
         Lnn[a + b * THIN_NN] = (a >= b) ? Lb[a + (long long)b * nj] : 0.0;
     }
-    __syncthreads();
-    const int i = blockIdx.x * 128 + tid;
-    if (i < na) {
-        double fan[THIN_NN], kan[THIN_NN], lt[THIN_NN];
-#pragma unroll
-        for (int k = 0; k < THIN_NN; ++k) {
-            if (k < nn) {
-                fan[k] = blk[(nn + i) + (long long)k * nj] + big_children(r, nn + i, k, false);
-                lt[k] = Lb[(nn + i) + (long long)k * nj];
-            } else { fan[k] = 0.0; lt[k] = 0.0; }
-        }
-#pragma unroll
-        for (int k = 0; k < THIN_NN; ++k) {
-            double t = fan[k];
-            if (k < nn) {
-#pragma unroll
-                for (int l = 0; l < THIN_NN; ++l)
-                    if (l < nn) t = fma(-lt[l], Fnn[l + k * THIN_NN], t);
-            }
-            kan[k] = t;
-        }
-#pragma unroll
-        for (int k = 0; k < THIN_NN; ++k)
-            if (k < nn) {
-                FanOld[i + (long long)k * na] = fan[k];
-                Kan[i + (long long)k * na] = kan[k];
-            }
-        thin_dsolve(Lnn, nn, kan);
-#pragma unroll
-        for (int k = 0; k < THIN_NN; ++k)
-            if (k < nn) W[k + (long long)i * nn] = kan[k];
-    }
-    if (blockIdx.x == 0) {
-        // T1 = D^-1 F_nn (columns), M = T1 D^-1 (rows)
-        if (tid < nn) {
-            double c[THIN_NN];
-#pragma unroll
-            for (int a = 0; a < THIN_NN; ++a) c[a] = (a < nn) ? Fnn[a + tid * THIN_NN] : 0.0;
-            thin_dsolve(Lnn, nn, c);
-#pragma unroll
-            for (int a = 0; a < THIN_NN; ++a)
-                if (a < nn) T1[a + tid * THIN_NN] = c[a];
-        }
-        __syncthreads();
-        if (tid < nn) {
-            double c[THIN_NN];
-#pragma unroll
-            for (int b = 0; b < THIN_NN; ++b) c[b] = (b < nn) ? T1[tid + b * THIN_NN] : 0.0;
-            thin_dsolve(Lnn, nn, c);
-#pragma unroll
-            for (int b = 0; b < THIN_NN; ++b)
-                if (b < nn) Mnn[tid + b * nn] = c[b];
-        }
-    }
-}
-
-// part 2: U'(i, j) = children(i, j) - Lt(i, :) F_an(j, :)^T - K_an(i, :) Lt(j, :)^T over alpha x alpha (32 x 32 per CTA);
-// CTA (0, 0) stores M_nn (symmetrised, lower) into the block.
-__global__ void __launch_bounds__(256) thin_up_update_kernel(BigArgs r, const double *__restrict__ Lb, const double *__restrict__ FanOld,
-                                                             const double *__restrict__ Kan, const double *__restrict__ Mnn,
-                                                             double *__restrict__ blk, double *__restrict__ U) {
-    __shared__ double Li[THIN_NN][33], Lj[THIN_NN][33], Fj[THIN_NN][33], Ki[THIN_NN][33];
-    const int nn = r.nn, na = r.na, nj = r.nj, tid = threadIdx.x;
-    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
     for (int idx = tid; idx < 32 * nn; idx += 256) {
         const int rr = idx & 31, k = idx >> 5;
-        const bool vi = i0 + rr < na, vj = j0 + rr < na;
-        Li[k][rr] = vi ? Lb[(nn + i0 + rr) + (long long)k * nj] : 0.0;
-        Ki[k][rr] = vi ? Kan[(i0 + rr) + (long long)k * na] : 0.0;
-        Lj[k][rr] = vj ? Lb[(nn + j0 + rr) + (long long)k * nj] : 0.0;
-        Fj[k][rr] = vj ? FanOld[(j0 + rr) + (long long)k * na] : 0.0;
+        const int i = i0 + rr, j = j0 + rr;
+        Li[k][rr] = (i < na) ? Lb[(nn + i) + (long long)k * nj] : 0.0;
+        Fi[k][rr] = (i < na) ? blk[(nn + i) + (long long)k * nj] + big_children(r, nn + i, k, false) : 0.0;
+        Lj[k][rr] = (j < na) ? Lb[(nn + j) + (long long)k * nj] : 0.0;
+        Fj[k][rr] = (j < na) ? blk[(nn + j) + (long long)k * nj] + big_children(r, nn + j, k, false) : 0.0;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 32 * nn; idx += 256) {
+        const int rr = idx & 31, k = idx >> 5;
+        double t = Fi[k][rr];
+        for (int l = 0; l < nn; ++l) t = fma(-Li[l][rr], Fnn[l + k * THIN_NN], t);
+        Ki[k][rr] = t;
     }
     __syncthreads();
     const int tx = tid & 31, ty = tid >> 5;
@@ -569,11 +522,50 @@ __global__ void __launch_bounds__(256) thin_up_update_kernel(BigArgs r, const do
                 U[i + (long long)j * na] = v;
             }
         }
+        if (blockIdx.y == 0 && ty == 0) {
+            double w[THIN_NN];
+#pragma unroll
+            for (int k = 0; k < THIN_NN; ++k) w[k] = (k < nn) ? Ki[k][tx] : 0.0;
+            thin_dsolve(Lnn, nn, w);
+#pragma unroll
+            for (int k = 0; k < THIN_NN; ++k)
+                if (k < nn) W[k + (long long)i * nn] = w[k];
+        }
     }
-    if (blockIdx.x == 0 && blockIdx.y == 0 && tid < nn * nn) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned done = atomicAdd(counter, 1u);
+        last_s = (done == gridDim.x * gridDim.y - 1);
+    }
+    __syncthreads();
+    if (!last_s) return;
+    // T1 = D^-1 F_nn (columns), M = T1 D^-1 (rows), stored symmetrised (lower; the upper part of the block is zero)
+    if (tid < nn) {
+        double c[THIN_NN];
+#pragma unroll
+        for (int a = 0; a < THIN_NN; ++a) c[a] = (a < nn) ? Fnn[a + tid * THIN_NN] : 0.0;
+        thin_dsolve(Lnn, nn, c);
+#pragma unroll
+        for (int a = 0; a < THIN_NN; ++a)
+            if (a < nn) T1[a + tid * THIN_NN] = c[a];
+    }
+    __syncthreads();
+    if (tid < nn) {
+        double c[THIN_NN];
+#pragma unroll
+        for (int b = 0; b < THIN_NN; ++b) c[b] = (b < nn) ? T1[tid + b * THIN_NN] : 0.0;
+        thin_dsolve(Lnn, nn, c);
+#pragma unroll
+        for (int b = 0; b < THIN_NN; ++b)
+            if (b < nn) Msm[tid + b * THIN_NN] = c[b];
+    }
+    __syncthreads();
+    if (tid < nn * nn) {
         const int a = tid % nn, b = tid / nn;
-        blk[a + (long long)b * nj] = (a >= b) ? 0.5 * (Mnn[a + b * nn] + Mnn[b + a * nn]) : 0.0;
+        blk[a + (long long)b * nj] = (a >= b) ? 0.5 * (Msm[a + b * THIN_NN] + Msm[b + a * THIN_NN]) : 0.0;
     }
+    if (tid == 0) *counter = 0u;
 }
 
 // Forward Hessian, root-to-leaves pass of a thin supernode in ONE launch: a CTA owns 16 rows of alpha,
@@ -596,6 +588,7 @@ __global__ void __launch_bounds__(512) thin_down_kernel(int nn, int na, int nj, 
     if (i < na) {
         const int *ai = aaidx + i;
         const double *Lt = Lb + nn;
+#pragma unroll 4
         for (int k = k0; k < k1; ++k) {
             const double z = Xb[ai[(long long)k * na]];
 #pragma unroll
@@ -684,6 +677,7 @@ __global__ void __launch_bounds__(512) thin_hinv_local_kernel(int nn, int na, in
     if (i < na) {
         const int *ai = aaidx + i;
         const double *Lt = Lb + nn;
+#pragma unroll 4
         for (int k = k0; k < k1; ++k) {
             const double z = Xb[ai[(long long)k * na]];
 #pragma unroll
@@ -822,17 +816,20 @@ int big_hess_up(smcp_sym *s, const BigNode &q, const double *Lt, const double *Y
     const double *Lb = Lt + q.boff, *Ltan = Lb + nn, *Yaa = Yaa_all + q.uoff;
     double *F = WS(0), *T1 = WS(1), *T2 = WS(2);
     if (nn <= THIN_NN && na >= 1 && thin_on()) {
-        double *FanOld = WS(0), *Kan = FanOld + (size_t)na * nn, *W = Kan + (size_t)na * nn, *Mnn = W + (size_t)na * nn;
-        const BigArgs ra = big_args(s, q, b);
-        {
-            LaunchScope ls_(ctx, "thin_up_rows");
-            thin_up_rows_kernel<<<(unsigned)((na + 127) / 128), 128, 0, ctx->stream>>>(ra, blk, Lb, FanOld, Kan, W, Mnn);
+        double *W = WS(0);
+        if (!s->thin_counters) {
+            CUDA_TRY(cudaMalloc(&s->thin_counters, 64 * sizeof(unsigned)));
+            CUDA_TRY(cudaMemset(s->thin_counters, 0, 64 * sizeof(unsigned)));
+            s->allocs.push_back(s->thin_counters);
         }
         {
-            LaunchScope ls_(ctx, "thin_up_update");
-            thin_up_update_kernel<<<dim3((unsigned)((na + 31) / 32), (unsigned)((na + 31) / 32)), 256, 0, ctx->stream>>>(ra, Lb, FanOld, Kan, Mnn, blk, Uk);
+            LaunchScope ls_(ctx, "thin_up");
+            thin_up_kernel<<<dim3((unsigned)((na + 31) / 32), (unsigned)((na + 31) / 32)), 256, 0, ctx->stream>>>(big_args(s, q, b), Lb, blk, Uk, W,
+                                                                                                                  s->thin_counters + s->big_lane);
         }
-        if (G(s, false, false, Yaa, na, W, nn, blk + nn, nj, na, nn, na, 1.0, 0)) return -1;        // M_an = Y_aa W^T
+        // M_an = Y_aa W^T.  Y_aa is stored full and exactly symmetric (the alpha x alpha gather mirrors the lower entries), so
+        // it is read as its transpose: a warp then owns a row and streams one contiguous column (na / 8 CTAs instead of na / 32)
+        if (G(s, true, false, Yaa, na, W, nn, blk + nn, nj, na, nn, na, 1.0, 0)) return -1;
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
@@ -847,12 +844,35 @@ int big_hess_up(smcp_sym *s, const BigNode &q, const double *Lt, const double *Y
         ELEM(big_copy_mat_kernel, (long long)na * na, Faa, nj, Uk, na, na, na, 0);
     }
     // M_nn = D^{-1} F_nn D^{-1}
-    if (d_trsm_left_lower(ctx, false, Lb, nj, nn, F, nj, nn)) return -1;          // L^-1 F
-    big_transpose(s, F, nj, nn, nn, T1, nn);
-    if (d_trsm_left_lower(ctx, false, Lb, nj, nn, T1, nn, nn)) return -1;         // L^-1 F L^-T
-    if (d_trsm_left_lower(ctx, true, Lb, nj, nn, T1, nn, nn)) return -1;          // L^-T (.)
-    big_transpose(s, T1, nn, nn, nn, T2, nn);
-    if (d_trsm_left_lower(ctx, true, Lb, nj, nn, T2, nn, nn)) return -1;          // D^-1 F D^-1
+    if (nn >= 256 && dinv_on()) {
+        // wide supernode (the root of rand_SDP: 1186 columns): D^-1 = L^-T L^-1 is formed ONCE per scaling point
+        // (one triangular solve on the identity + one product) and every Hessian is two DMMA products instead of
+        // four triangular solves with nn right-hand sides and two transposes (1.4 ms -> 0.4 ms at nn = 1186)
+        const size_t idx = (size_t)(&q - s->big.data());
+        if (s->big_dinv_off.empty()) {
+            size_t tot = 0;
+            for (const BigNode &t : s->big) { s->big_dinv_off.push_back(tot); if (t.nn >= 256) tot += (size_t)t.nn * t.nn; }
+            s->big_dinv_gen.assign(s->big.size(), 0);
+            CUDA_TRY(cudaMalloc(&s->big_dinv, std::max<size_t>(tot, 1) * sizeof(double)));
+            s->allocs.push_back(s->big_dinv);
+        }
+        double *Dinv = s->big_dinv + s->big_dinv_off[idx];
+        if (s->big_dinv_gen[idx] != s->lt_gen_cur) {
+            ELEM(big_identity_kernel, (long long)nn * nn, T1, nn, nn);
+            if (d_trsm_left_lower(ctx, false, Lb, nj, nn, T1, nn, nn)) return -1;                  // L^-1
+            if (G(s, true, true, T1, nn, T1, nn, Dinv, nn, nn, nn, nn, 1.0, 0)) return -1;         // D^-1 = L^-T L^-1 (full)
+            s->big_dinv_gen[idx] = s->lt_gen_cur;
+        }
+        if (G(s, true, true, Dinv, nn, F, nj, T1, nn, nn, nn, nn, 1.0, 0)) return -1;              // D^-1 F   (both symmetric)
+        if (G(s, false, true, T1, nn, Dinv, nn, T2, nn, nn, nn, nn, 1.0, 0)) return -1;            // (D^-1 F) D^-1
+    } else {
+        if (d_trsm_left_lower(ctx, false, Lb, nj, nn, F, nj, nn)) return -1;          // L^-1 F
+        big_transpose(s, F, nj, nn, nn, T1, nn);
+        if (d_trsm_left_lower(ctx, false, Lb, nj, nn, T1, nn, nn)) return -1;         // L^-1 F L^-T
+        if (d_trsm_left_lower(ctx, true, Lb, nj, nn, T1, nn, nn)) return -1;          // L^-T (.)
+        big_transpose(s, T1, nn, nn, nn, T2, nn);
+        if (d_trsm_left_lower(ctx, true, Lb, nj, nn, T2, nn, nn)) return -1;          // D^-1 F D^-1
+    }
     if (na) {
         // M_an = Y_aa K_an D^{-1}: W = D^{-1} K_an^T, M_an = Y_aa W^T
         double *W = T1;

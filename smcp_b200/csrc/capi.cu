@@ -1328,7 +1328,7 @@ extern "C" int smcp_kkt_factor(smcp_op *op, int32_t *info_host) {
     {
         RegionScope rs(ctx, "kkt_factor");
         if (d_potrf(ctx, op->H, op->m, op->m, op->m, op->info_dev, 0, 1)) return -1;
-        if (potrs_cluster_for(op->m) && d_potrs_prepare(ctx, op->H, op->m, op->m, op->Dinv)) return -1;
+        if ((potrs_cluster_for(op->m) || potrs_wave_for(ctx, op->m)) && d_potrs_prepare(ctx, op->H, op->m, op->m, op->Dinv)) return -1;
     }
     CUDA_TRY(cudaMemcpyAsync(info_host, op->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1346,7 +1346,7 @@ extern "C" int smcp_kkt_factor_dist(smcp_op *op, int rank, int nranks, int32_t *
     {
         RegionScope rs(ctx, "kkt_factor");
         if (d_potrf(ctx, op->H, op->m, op->m, op->m, op->info_dev, rank, nranks)) return -1;
-        if (potrs_cluster_for(op->m) && d_potrs_prepare(ctx, op->H, op->m, op->m, op->Dinv)) return -1;
+        if ((potrs_cluster_for(op->m) || potrs_wave_for(ctx, op->m)) && d_potrs_prepare(ctx, op->H, op->m, op->m, op->Dinv)) return -1;
     }
     CUDA_TRY(cudaMemcpyAsync(info_host, op->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1362,7 +1362,7 @@ extern "C" int smcp_kkt_factor_block(smcp_op *op, int64_t block, int rank, int n
     {
         RegionScope rs(ctx, "kkt_factor");
         if (d_potrf(ctx, op->H, op->m, op->m, op->m, op->info_dev, rank, nranks, block)) return -1;
-        if (potrs_cluster_for(op->m) && d_potrs_prepare(ctx, op->H, op->m, op->m, op->Dinv)) return -1;
+        if ((potrs_cluster_for(op->m) || potrs_wave_for(ctx, op->m)) && d_potrs_prepare(ctx, op->H, op->m, op->m, op->Dinv)) return -1;
     }
     CUDA_TRY(cudaMemcpyAsync(info_host, op->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1455,7 +1455,9 @@ extern "C" int smcp_kkt_solve(smcp_op *op, double *host_y) {
     CUDA_TRY(cudaMemcpyAsync(op->yv, host_y, (size_t)op->m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     {
         RegionScope rs(ctx, "kkt_solve");
-        if (potrs_cluster_for(op->m) ? d_potrs_cluster(ctx, op->H, op->m, op->Dinv, op->yv) : d_potrs(ctx, op->H, op->m, op->yv)) return -1;
+        if (potrs_cluster_for(op->m) ? d_potrs_cluster(ctx, op->H, op->m, op->Dinv, op->yv)
+                                     : potrs_wave_for(ctx, op->m) ? d_potrs_wave(ctx, op->H, op->m, op->Dinv, op->yv)
+                                                                  : d_potrs(ctx, op->H, op->m, op->yv)) return -1;
     }
     CUDA_TRY(cudaMemcpyAsync(host_y, op->yv, (size_t)op->m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));

@@ -290,6 +290,7 @@ int k_hess_prep(smcp_hess *h, const double *L, const double *Y) {
     if (h->sym->small) return ks_hess_prep(h, L, Y);
     smcp_sym *s = h->sym;
     if (sym_ensure(s, 1, false)) return -1;
+    h->lt_gen = ++s->lt_gen_next;
     TreeArgs a = {};
     a.L0 = L;
     a.Y0 = Y;
@@ -367,6 +368,7 @@ int k_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
     const bool big = use_big(s, batch);
     if (big || bigb) a.skipflag = s->big_flag;
     int threads = pick_threads(s, big || bigb);
+    s->lt_gen_cur = h->lt_gen;
     if (!inv) {
         const bool many = batch >= 32;
         if (launch_tree<OP_HFWD_UP>(s, a, s->up, batch, threads, many ? "hessian_up_batch" : "hessian_up")) return -1;

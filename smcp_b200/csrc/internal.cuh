@@ -56,6 +56,9 @@ struct smcp_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;                 // look-ahead stream of the dense Cholesky (panels + broadcasts)
     std::vector<cudaEvent_t> potrf_ev;              // fork/join events of the look-ahead pipeline
+    void *wave_buf = nullptr;                       // potrs_wave_kernel: published block solutions + flags
+    size_t wave_cap = 0;
+    unsigned wave_epoch = 0;
     const char *potrf_family = nullptr;             // profile family of the next d_potrf (default "potrf_dmma")
     int prof_mute = 0;                              // > 0: nested LaunchScopes do not time (an outer scope does)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;       // user timer
@@ -192,6 +195,10 @@ struct smcp_sym {
     std::vector<size_t> thin_dinv_off;
     std::vector<uint64_t> thin_dinv_gen; // scaling point (raa_gen) the cached blocks belong to
     uint64_t raa_gen_next = 0, raa_gen_cur = 0;
+    double *big_dinv = nullptr;          // (L_nn L_nn^T)^-1 of the wide top-set supernodes (forward Hessian), per scaling point
+    std::vector<size_t> big_dinv_off;
+    std::vector<uint64_t> big_dinv_gen;
+    uint64_t lt_gen_next = 0, lt_gen_cur = 0;
     std::vector<std::vector<int>> big_up, big_down;   // indices into `big` by height (leaves first) / by depth (root first)
     int big_nlanes = 1;            // lanes the top set may use (1 = everything on the main stream)
     int big_lane = 0;              // lane the next big_* call works in
@@ -215,6 +222,7 @@ struct smcp_hess {
     double *Yaa = nullptr;     // nupd: Y_{alpha alpha}, full symmetric
     double *Raa = nullptr;     // nupd: chol(Y_aa) (lazily, for the inverse map)
     bool have_Raa = false;
+    uint64_t lt_gen = 0;           // generation of Lt (keys smcp_sym::big_dinv)
     uint64_t raa_gen = 0;          // generation of Raa (keys caches derived from it: smcp_sym::thin_dinv)
     double *phi_up = nullptr, *phi_dn = nullptr, *psi_up = nullptr, *psi_dn = nullptr;   // chain path: segment propagators of the two sweeps
     bool have_phi = false;
@@ -286,6 +294,8 @@ int d_trsm_left_lower(smcp_ctx *ctx, bool trans, const double *L, int64_t ldl, i
 // Schur complement in the trailing block; nranks > 1: block-cyclic columns with NCCL panel broadcasts
 int d_potrf(smcp_ctx *ctx, double *H, int64_t ld, int64_t m, int64_t ncols, int32_t *info_dev, int rank, int nranks, int64_t block = 0);
 int d_potrs(smcp_ctx *ctx, const double *H, int64_t m, double *y_dev);
+bool potrs_wave_for(const smcp_ctx *ctx, int64_t m);
+int d_potrs_wave(smcp_ctx *ctx, const double *H, int64_t m, const double *Dinv, double *y_dev);
 // potrs as one thread-block-cluster launch on the inverted 64 x 64 diagonal blocks (potrs_cluster.cu)
 bool potrs_cluster_enabled();
 bool potrs_cluster_for(int64_t m);

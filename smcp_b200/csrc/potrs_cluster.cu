@@ -197,6 +197,205 @@ __global__ void __launch_bounds__(PC_T, 1) potrs_cluster_kernel(PotrsArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// potrs for factors that do NOT fit in L2 (m = 10^4: 400 MB per sweep): the whole grid as a flag-driven wavefront.
+// Block rows (64 rows) are owned cyclically by the CTAs of a co-resident grid (cooperative launch, one CTA per SM).
+// Step b of the forward sweep: every CTA has ALREADY loaded its tiles L(blk, b), blk > b, into registers; it then waits
+// for the flag of x_b (written to global memory by the owner of block b), subtracts L(blk, b) x_b from the blocks it
+// owns, and the owner of block b + 1 applies the inverted diagonal block (trtri64_kernel) and publishes x_{b+1}.  The
+// dependent chain per step is flag -> 64 x 64 product -> 64 x 64 product -> flag (~3 us); the factor is streamed once
+// per sweep by all SMs (the cluster kernel above streams it through 16 SMs: 5.1 ms at m = 10^4; the launch chain of
+// dense.cu: 3.6 ms in 160 launches).  The backward sweep mirrors it by block columns; forward and backward results
+// use different flag values and buffers, so no grid barrier separates the sweeps.  Fixed summation order.
+// ---------------------------------------------------------------------------------------
+struct WaveArgs {
+    const double *L;
+    long long ld;
+    int m;
+    const double *Dinv;
+    double *y;
+    double *xf, *xb;        // nb x 64 each: published forward / backward block solutions
+    unsigned *flag;         // nb: 1 = forward x ready, 2 = backward x ready
+    unsigned base;          // flag values of this launch are base + 1, base + 2 (the array is never cleared)
+};
+#define PW_T 256
+#define PW_MAXOWN 4
+
+__device__ __forceinline__ unsigned pw_ld_acquire(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void pw_st_release(unsigned *p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <bool BWD>
+__device__ __forceinline__ void wave_sweep(const WaveArgs &a, double *ys, double *xs, double *part, int tid) {
+    const int G = (int)gridDim.x, rk = (int)blockIdx.x;
+    const int nb = (a.m + 63) / 64;
+    const int r = tid & 63, g = tid >> 6;
+    double *xg = BWD ? a.xb : a.xf;
+    const unsigned ready = a.base + (BWD ? 2u : 1u);
+    // the first block of the sweep has no predecessor: its owner publishes it straight away
+    {
+        const int b0 = BWD ? nb - 1 : 0;
+        if (b0 % G == rk) {
+            const double *D = a.Dinv + (long long)b0 * 4096;
+            tile_gemv<BWD>(D, 64, 64, 64, ys + (b0 / G) * 64, part, tid);
+            __syncthreads();
+            if (tid < 64) {
+                const int kb0 = min(64, a.m - 64 * b0);
+                const double xv = (tid < kb0) ? (part[tid] + part[64 + tid]) + (part[128 + tid] + part[192 + tid]) : 0.0;
+                ys[(b0 / G) * 64 + tid] = xv;
+                xg[(long long)b0 * 64 + tid] = xv;
+            }
+            __syncthreads();
+            if (tid == 0) { __threadfence(); pw_st_release(a.flag + b0, ready); }
+        }
+    }
+    for (int q = 0; q + 1 < nb; ++q) {
+        const int b = BWD ? nb - 1 - q : q;
+        const int kb = min(64, a.m - 64 * b);
+        const int nxt = BWD ? b - 1 : b + 1;
+        // owned blocks on the far side of b, nearest first
+        int tb[PW_MAXOWN], nt = 0;
+        if (BWD) {
+            // largest owned block below b, then steps of G
+            int blk = (b - 1) - (((b - 1) - rk) % G + G) % G;
+            for (; blk >= 0 && nt < PW_MAXOWN; blk -= G) tb[nt++] = blk;
+        } else {
+            int blk = (b + 1) + ((rk - (b + 1)) % G + G) % G;
+            for (; blk < nb && nt < PW_MAXOWN; blk += G) tb[nt++] = blk;
+        }
+        if (!nt) continue;                                   // uniform per CTA; this CTA has nothing left in this sweep
+        double v[PW_MAXOWN][16];
+#pragma unroll
+        for (int t = 0; t < PW_MAXOWN; ++t) {
+            if (t < nt) {
+                const int blk = tb[t];
+                const int rows = min(64, a.m - 64 * blk);
+                const double *T = BWD ? a.L + 64LL * b + 64LL * blk * a.ld : a.L + 64LL * blk + 64LL * b * a.ld;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int c = 16 * g + e;
+                    v[t][e] = (r < rows && c < kb) ? (BWD ? T[c + (long long)r * a.ld] : T[r + (long long)c * a.ld]) : 0.0;
+                }
+            }
+        }
+        // (a forward flag may already carry the backward value: the backward x_b exists only after every consumer of the
+        // forward x_b has finished its forward sweep, but accept both to be safe -- the forward buffer is never reused)
+        if (tid == 0) {
+            for (;;) {
+                const unsigned f = pw_ld_acquire(a.flag + b);
+                if (f == ready || (!BWD && f == a.base + 2u)) break;
+            }
+        }
+        __syncthreads();
+        if (tid < 64) xs[tid] = __ldcg(xg + (long long)b * 64 + tid);
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < PW_MAXOWN; ++t) {
+            if (t < nt) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int e = 0; e < 16; e += 2) {
+                    s0 = fma(v[t][e], xs[16 * g + e], s0);
+                    s1 = fma(v[t][e + 1], xs[16 * g + e + 1], s1);
+                }
+                part[t * 256 + g * 64 + r] = s0 + s1;
+            }
+        }
+        __syncthreads();
+        {
+            const int t = tid >> 6, rr = tid & 63;
+            if (t < nt) {
+                const double *pp = part + t * 256;
+                ys[(tb[t] / G) * 64 + rr] -= (pp[rr] + pp[64 + rr]) + (pp[128 + rr] + pp[192 + rr]);
+            }
+        }
+        __syncthreads();
+        if (nxt % G == rk) {
+            // the next block is complete: x = Dinv y (backward: Dinv^T y), publish
+            const double *D = a.Dinv + (long long)nxt * 4096;
+            tile_gemv<BWD>(D, 64, 64, 64, ys + (nxt / G) * 64, part, tid);
+            __syncthreads();
+            if (tid < 64) {
+                const int kbn = min(64, a.m - 64 * nxt);
+                const double xv = (tid < kbn) ? (part[tid] + part[64 + tid]) + (part[128 + tid] + part[192 + tid]) : 0.0;
+                ys[(nxt / G) * 64 + tid] = xv;
+                xg[(long long)nxt * 64 + tid] = xv;
+            }
+            __syncthreads();
+            if (tid == 0) { __threadfence(); pw_st_release(a.flag + nxt, ready); }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PW_T, 1) potrs_wave_kernel(WaveArgs a) {
+    extern __shared__ double pwsm[];
+    const int G = (int)gridDim.x, rk = (int)blockIdx.x, tid = threadIdx.x;
+    const int nb = (a.m + 63) / 64;
+    const int nloc = (nb + G - 1) / G;
+    double *ys = pwsm;                    // nloc x 64: the blocks of y this CTA owns
+    double *xs = ys + nloc * 64;          // 64: x of the current step
+    double *part = xs + 64;               // PW_MAXOWN x 4 x 64 partial sums
+    for (int idx = tid; idx < nloc * 64; idx += PW_T) {
+        const int b = (idx >> 6) * G + rk;
+        const long long i = 64LL * b + (idx & 63);
+        ys[idx] = (b < nb && i < a.m) ? a.y[i] : 0.0;
+    }
+    __syncthreads();
+    wave_sweep<false>(a, ys, xs, part, tid);
+    __syncthreads();
+    wave_sweep<true>(a, ys, xs, part, tid);
+    __syncthreads();
+    for (int idx = tid; idx < nloc * 64; idx += PW_T) {
+        const int b = (idx >> 6) * G + rk;
+        const long long i = 64LL * b + (idx & 63);
+        if (b < nb && i < a.m) a.y[i] = ys[idx];
+    }
+}
+
+bool potrs_wave_for(const smcp_ctx *ctx, int64_t m) {
+    static const bool off = getenv("SMCP_B200_POTRS_NO_WAVE") && atoi(getenv("SMCP_B200_POTRS_NO_WAVE")) != 0;
+    const int64_t nb = (m + 63) / 64;
+    return !off && potrs_cluster_enabled() && m > 4096 && nb <= (int64_t)PW_MAXOWN * ctx->num_sms;
+}
+
+int d_potrs_wave(smcp_ctx *ctx, const double *H, int64_t m, const double *Dinv, double *y_dev) {
+    if (m <= 0) return 0;
+    const int64_t nb = (m + 63) / 64;
+    const int G = (int)std::min<int64_t>(nb, ctx->num_sms);
+    const int nloc = (int)((nb + G - 1) / G);
+    const size_t need = (size_t)nb * 128 * sizeof(double) + (size_t)nb * sizeof(unsigned) + 64;
+    if (need > ctx->wave_cap) {
+        if (ctx->wave_buf) cudaFree(ctx->wave_buf);
+        ctx->wave_buf = nullptr;
+        ctx->wave_cap = 0;
+        CUDA_TRY(cudaMalloc(&ctx->wave_buf, need));
+        CUDA_TRY(cudaMemsetAsync(ctx->wave_buf, 0, need, ctx->stream));
+        ctx->wave_cap = need;
+        ctx->wave_epoch = 0;
+    }
+    WaveArgs a;
+    a.L = H; a.ld = m; a.m = (int)m; a.Dinv = Dinv; a.y = y_dev;
+    a.xf = (double *)ctx->wave_buf;
+    a.xb = a.xf + nb * 64;
+    a.flag = (unsigned *)(a.xb + nb * 64);
+    if (ctx->wave_epoch > 0xfffffff0u) {
+        CUDA_TRY(cudaMemsetAsync(ctx->wave_buf, 0, need, ctx->stream));
+        ctx->wave_epoch = 0;
+    }
+    a.base = ctx->wave_epoch;
+    ctx->wave_epoch += 2;
+    const size_t smem = (size_t)(nloc * 64 + 64 + PW_MAXOWN * 256) * sizeof(double);
+    void *args[] = {&a};
+    LaunchScope ls(ctx, "potrs", 1, 8.0 * (double)m * (double)m);
+    CUDA_TRY(cudaLaunchCooperativeKernel((void *)potrs_wave_kernel, dim3((unsigned)G), dim3(PW_T), args, smem, ctx->stream));
+    return 0;
+}
+
 int d_potrs_prepare(smcp_ctx *ctx, const double *H, int64_t ld, int64_t m, double *Dinv) {
     if (m <= 0) return 0;
     LaunchScope ls(ctx, "potrs_trtri");

@@ -163,7 +163,7 @@ def test_schur_not_pd_raises():
     assert info[0] == 1
 
 
-@pytest.mark.parametrize("m", [1, 31, 33, 63, 64, 65, 127, 129, 200, 333, 1000, 1537, 2500])
+@pytest.mark.parametrize("m", [1, 31, 33, 63, 64, 65, 127, 129, 200, 333, 1000, 1537, 2500, 4200, 5003])
 def test_dense_potrf_potrs(m):
     """lapack.potrf / potrs replacement on its own, against numpy."""
     from smcp_b200.device import _ck
