@@ -1042,6 +1042,71 @@ int big_projinv(smcp_sym *s, const BigNode &q, double *X, int64_t b) {
     return 0;
 }
 
+// Completion of a thin supernode after the partial factorisation and the backward solve (W = X_aa^-1 X_an): the
+// trailing nn x nn block Delta = M^T M (M lower: a Cholesky factorisation run from the last row up), L_nn = M^-1,
+// L_an = -W L_nn, and the verdict of the factorisation -- one launch instead of nine (two of them cooperative
+// launches for a 1 x 1 "matrix").  Every CTA redoes the nn x nn part (nn <= 8), a thread owns a row of alpha.
+__global__ void __launch_bounds__(128) thin_compl_tail_kernel(int nn, int na, int nj, const double *__restrict__ T, const double *__restrict__ W,
+                                                              double *__restrict__ bout, const int *__restrict__ info, int *__restrict__ fail) {
+    __shared__ double Ms[THIN_NN * THIN_NN], Ls[THIN_NN * THIN_NN];
+    __shared__ int bad_s;
+    const int tid = threadIdx.x;
+    if (tid < THIN_NN * THIN_NN) {
+        const int a = tid % THIN_NN, b = tid / THIN_NN;
+        Ms[tid] = (a < nn && b < nn && a >= b) ? T[(na + a) + (long long)(na + b) * nj] : 0.0;
+        Ls[tid] = 0.0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int bad = 0;
+        // in place: M(j, i), i <= j, from the last row up; Delta(j, i) = sum_{k >= j} M(k, j) M(k, i)
+        for (int j = nn - 1; j >= 0; --j) {
+            double d = Ms[j + j * THIN_NN];
+            for (int k2 = j + 1; k2 < nn; ++k2) d = fma(-Ms[k2 + j * THIN_NN], Ms[k2 + j * THIN_NN], d);
+            if (!(d > 0.0)) { bad = 1; d = 1.0; }
+            const double mjj = sqrt(d);
+            Ms[j + j * THIN_NN] = mjj;
+            for (int i = 0; i < j; ++i) {
+                double t = Ms[j + i * THIN_NN];
+                for (int k2 = j + 1; k2 < nn; ++k2) t = fma(-Ms[k2 + j * THIN_NN], Ms[k2 + i * THIN_NN], t);
+                Ms[j + i * THIN_NN] = t / mjj;
+            }
+        }
+        // L_nn = M^-1 (lower), column by column
+        for (int c = 0; c < nn; ++c) {
+            for (int r2 = c; r2 < nn; ++r2) {
+                double t = (r2 == c) ? 1.0 : 0.0;
+                for (int p2 = c; p2 < r2; ++p2) t = fma(-Ms[r2 + p2 * THIN_NN], Ls[p2 + c * THIN_NN], t);
+                Ls[r2 + c * THIN_NN] = t / Ms[r2 + r2 * THIN_NN];
+            }
+        }
+        bad_s = bad;
+    }
+    __syncthreads();
+    const int i = blockIdx.x * 128 + tid;
+    if (i < na) {
+        double w[THIN_NN];
+#pragma unroll
+        for (int k2 = 0; k2 < THIN_NN; ++k2) w[k2] = (k2 < nn) ? W[i + (long long)k2 * na] : 0.0;
+#pragma unroll
+        for (int j = 0; j < THIN_NN; ++j)
+            if (j < nn) {
+                double t = 0.0;
+#pragma unroll
+                for (int k2 = 0; k2 < THIN_NN; ++k2)
+                    if (k2 >= j && k2 < nn) t = fma(w[k2], Ls[k2 + j * THIN_NN], t);
+                bout[(nn + i) + (long long)j * nj] = -t;
+            }
+    }
+    if (blockIdx.x == 0) {
+        if (tid < nn * nn) {
+            const int a = tid % nn, b = tid / nn;
+            bout[a + (long long)b * nj] = (a >= b) ? Ls[a + b * THIN_NN] : 0.0;
+        }
+        if (tid == 0 && (bad_s || *info)) *fail = 1;
+    }
+}
+
 // ---- completion (independent per supernode, out of place) ---------------------------------------
 int big_completion(smcp_sym *s, const BigNode &q, double *X, const double *Xin, int64_t b) {
     smcp_ctx *ctx = s->ctx;
@@ -1056,9 +1121,15 @@ int big_completion(smcp_sym *s, const BigNode &q, double *X, const double *Xin, 
     ELEM(big_compl_front_kernel, (long long)nj * nj, s->d.aaidx + q.uoff, Xi, bin, T, nn, na, nj);
     if (na) {
         if (front_potrf(ctx, T, nj, nj, na, BIG_INFO)) return -1;
-        big_flag_kernel<<<1, 1, 0, ctx->stream>>>(BIG_INFO, s->fail + b);
+        if (!(nn <= THIN_NN && thin_on())) big_flag_kernel<<<1, 1, 0, ctx->stream>>>(BIG_INFO, s->fail + b);   // thin: in the tail kernel
         big_transpose(s, T + na, nj, nn, na, Z, na);                                                // Z = R^-1 X_an
         if (d_trsm_left_lower(ctx, true, T, nj, na, Z, na, nn)) return -1;                          // W = X_aa^-1 X_an
+    }
+    if (nn <= THIN_NN && na >= 1 && thin_on()) {
+        LaunchScope ls_(ctx, "thin_compl_tail");
+        thin_compl_tail_kernel<<<(unsigned)((na + 127) / 128), 128, 0, ctx->stream>>>(nn, na, nj, T, Z, bout, BIG_INFO, s->fail + b);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
     }
     ELEM(big_reverse_kernel, (long long)nn * nn, T + na + (size_t)na * nj, nj, T0, nn, 0);
     if (front_potrf(ctx, T0, nn, nn, nn, BIG_INFO)) return -1;
