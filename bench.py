@@ -177,7 +177,7 @@ def measured_fp64_peak():
 # the chordal families carry the number of matrices processed (16*|Vp| bytes each)
 BYTE_FAMILIES = {"potrs", "amap_dense", "amap", "aadj", "potrf_panel", "gemm_thin", "scm_kstream"}
 FLOP_FAMILIES = {"potrf_tile", "trsm_slab", "gemm_smallk", "potrf_dmma", "front_potrf"}
-NO_MODEL = {"front_elem", "thin_up", "thin_down", "thin_compl_tail", "thin_hinv_local", "thin_hinv_sweep", "thin_trsm", "front_elem_batch", "setup", "scm_position", "scm_sparse", "chordal_trsm", "front_trsm_diag",
+NO_MODEL = {"front_elem", "thin_up", "thin_down", "thin_compl_tail", "thin_chol", "thin_hinv_local", "thin_hinv_sweep", "thin_trsm", "front_elem_batch", "setup", "scm_position", "scm_sparse", "chordal_trsm", "front_trsm_diag",
             "level1", "reduce", "scatter_cols"}
 
 

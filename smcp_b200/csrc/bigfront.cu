@@ -23,6 +23,18 @@
 #include <algorithm>
 #include <cstdlib>
 
+// thin supernodes: at most THIN_NN columns (the thin_* kernels below); SMCP_B200_NO_THIN / SMCP_B200_NO_DINV switch the
+// round-2 shortcuts off for A/B measurements
+#define THIN_NN 8
+static bool dinv_on() {
+    static const bool off = getenv("SMCP_B200_NO_DINV") && atoi(getenv("SMCP_B200_NO_DINV")) != 0;
+    return !off;
+}
+static bool thin_on() {
+    static const bool off = getenv("SMCP_B200_NO_THIN") && atoi(getenv("SMCP_B200_NO_THIN")) != 0;
+    return !off;
+}
+
 // ---------------------------------------------------------------------------------------
 // elementwise kernels
 // ---------------------------------------------------------------------------------------
@@ -405,6 +417,114 @@ int big_lanes_end(smcp_sym *s) {
     return lanes_join(s->ctx);
 }
 
+// Cholesky of a thin supernode's frontal matrix in ONE launch: every CTA factors F_nn (block + children, nn <= 8) itself,
+// forms L_an(i, :) = F_an(i, :) L_nn^-T for its 32 rows i and 32 rows j of alpha and writes the 32 x 32 tile
+// U(i, j) = children(i, j) - L_an(i, :) L_an(j, :)^T of the update matrix (lower triangle; zero above, like the generic
+// path).  The CTA that finishes last -- every CTA has read the block by then -- overwrites the block with L_nn, L_an
+// and raises the verdict.  Generic path: front assembly, a cooperative partial factorisation with nn pivots, flag,
+// two copies (5 launches).
+__global__ void __launch_bounds__(256) thin_chol_kernel(BigArgs r, double *__restrict__ blk, double *__restrict__ U, int *__restrict__ fail,
+                                                        unsigned *__restrict__ counter) {
+    __shared__ double Li[THIN_NN][33], Lj[THIN_NN][33];
+    __shared__ double Lnn[THIN_NN * THIN_NN];
+    __shared__ int bad_s;
+    __shared__ bool last_s;
+    const int nn = r.nn, na = r.na, nj = r.nj, tid = threadIdx.x;
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    if (tid < THIN_NN * THIN_NN) {
+        const int a = tid % THIN_NN, b = tid / THIN_NN;
+        Lnn[tid] = (a < nn && b < nn && a >= b) ? blk[a + (long long)b * nj] + big_children(r, a, b, true) : 0.0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int bad = 0;
+        for (int c = 0; c < nn; ++c) {
+            double d = Lnn[c + c * THIN_NN];
+            if (!(d > 0.0)) { bad = 1; d = 1.0; }
+            const double l = sqrt(d);
+            Lnn[c + c * THIN_NN] = l;
+            for (int a = c + 1; a < nn; ++a) Lnn[a + c * THIN_NN] /= l;
+            for (int b = c + 1; b < nn; ++b)
+                for (int a = b; a < nn; ++a) Lnn[a + b * THIN_NN] = fma(-Lnn[a + c * THIN_NN], Lnn[b + c * THIN_NN], Lnn[a + b * THIN_NN]);
+        }
+        bad_s = bad;
+    }
+    __syncthreads();
+    // rows of L_an: x L_nn^T = f  (forward over the columns)
+    if (tid < 64) {
+        const int rr = tid & 31;
+        const int row = (tid < 32 ? i0 : j0) + rr;
+        double x[THIN_NN];
+#pragma unroll
+        for (int k2 = 0; k2 < THIN_NN; ++k2)
+            x[k2] = (k2 < nn && row < na) ? blk[(nn + row) + (long long)k2 * nj] + big_children(r, nn + row, k2, true) : 0.0;
+#pragma unroll
+        for (int k2 = 0; k2 < THIN_NN; ++k2)
+            if (k2 < nn) {
+                double t = x[k2];
+#pragma unroll
+                for (int p2 = 0; p2 < THIN_NN; ++p2)
+                    if (p2 < k2) t = fma(-x[p2], Lnn[k2 + p2 * THIN_NN], t);
+                x[k2] = t / Lnn[k2 + k2 * THIN_NN];
+            }
+#pragma unroll
+        for (int k2 = 0; k2 < THIN_NN; ++k2) {
+            if (tid < 32) Li[k2][rr] = x[k2];
+            else Lj[k2][rr] = x[k2];
+        }
+    }
+    __syncthreads();
+    const int tx = tid & 31, ty = tid >> 5;
+    const int i = i0 + tx;
+    if (i < na) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int jj = ty + 8 * q, j = j0 + jj;
+            if (j < na) {
+                double v = 0.0;
+                if (i >= j) {
+                    v = big_children(r, nn + i, nn + j, true);
+                    for (int k2 = 0; k2 < nn; ++k2) v = fma(-Li[k2][tx], Lj[k2][jj], v);
+                }
+                U[i + (long long)j * na] = v;
+            }
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned done = atomicAdd(counter, 1u);
+        last_s = (done == gridDim.x * gridDim.y - 1);
+    }
+    __syncthreads();
+    if (!last_s) return;
+    // the block: L_an rows (recomputed from the still untouched input), then L_nn
+    for (int row = tid; row < na; row += 256) {
+        double x[THIN_NN];
+#pragma unroll
+        for (int k2 = 0; k2 < THIN_NN; ++k2)
+            x[k2] = (k2 < nn) ? blk[(nn + row) + (long long)k2 * nj] + big_children(r, nn + row, k2, true) : 0.0;
+#pragma unroll
+        for (int k2 = 0; k2 < THIN_NN; ++k2)
+            if (k2 < nn) {
+                double t = x[k2];
+#pragma unroll
+                for (int p2 = 0; p2 < THIN_NN; ++p2)
+                    if (p2 < k2) t = fma(-x[p2], Lnn[k2 + p2 * THIN_NN], t);
+                x[k2] = t / Lnn[k2 + k2 * THIN_NN];
+                blk[(nn + row) + (long long)k2 * nj] = x[k2];
+            }
+    }
+    if (tid < nn * nn) {
+        const int a = tid % nn, b = tid / nn;
+        blk[a + (long long)b * nj] = (a >= b) ? Lnn[a + b * THIN_NN] : 0.0;
+    }
+    if (tid == 0) {
+        if (bad_s) *fail = 1;
+        *counter = 0u;
+    }
+}
+
 // ---- cholesky --------------------------------------------------------------------------
 int big_cholesky(smcp_sym *s, const BigNode &q, double *X, int64_t b) {
     smcp_ctx *ctx = s->ctx;
@@ -412,6 +532,18 @@ int big_cholesky(smcp_sym *s, const BigNode &q, double *X, int64_t b) {
     double *blk = X + (size_t)b * s->d.nblk + q.boff;
     double *Uk = s->upd + (size_t)b * s->d.nupd + q.uoff;
     double *F = WS(0);
+    if (nn <= THIN_NN && na >= 1 && thin_on()) {
+        if (!s->thin_counters) {
+            CUDA_TRY(cudaMalloc(&s->thin_counters, 64 * sizeof(unsigned)));
+            CUDA_TRY(cudaMemset(s->thin_counters, 0, 64 * sizeof(unsigned)));
+            s->allocs.push_back(s->thin_counters);
+        }
+        LaunchScope ls_(ctx, "thin_chol");
+        thin_chol_kernel<<<dim3((unsigned)((na + 31) / 32), (unsigned)((na + 31) / 32)), 256, 0, ctx->stream>>>(big_args(s, q, b), blk, Uk, s->fail + b,
+                                                                                                                s->thin_counters + s->big_lane);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     ELEM(big_front_lower_kernel, (long long)nj * nj, big_args(s, q, b), blk, F);
     if (front_potrf(ctx, F, nj, nj, nn, BIG_INFO)) return -1;
     big_flag_kernel<<<1, 1, 0, ctx->stream>>>(BIG_INFO, s->fail + b);
@@ -440,15 +572,6 @@ int big_llt(smcp_sym *s, const BigNode &q, double *X, int64_t b) {
 // per supernode (16 up, 6 down) of which all but two touch nj x nn = a few thousand numbers: the sweep is a
 // chain of launch latencies (956 launches, 5.3 ms; the host cannot even issue them faster).  Here the nn-wide
 // algebra of a supernode is done by the threads that own the rows: 3 launches up, 1 down.
-#define THIN_NN 8
-static bool dinv_on() {
-    static const bool off = getenv("SMCP_B200_NO_DINV") && atoi(getenv("SMCP_B200_NO_DINV")) != 0;
-    return !off;
-}
-static bool thin_on() {
-    static const bool off = getenv("SMCP_B200_NO_THIN") && atoi(getenv("SMCP_B200_NO_THIN")) != 0;
-    return !off;
-}
 
 // w <- (L L^T)^-1 w, L = Lnn (nn x nn lower, ld THIN_NN) in shared memory
 __device__ __forceinline__ void thin_dsolve(const double *Lnn, int nn, double (&w)[THIN_NN]) {
