@@ -246,6 +246,10 @@ def config_of(workload, world=None):
         cfg["nnz_per_constraint"] = "round(%g |V|)" % w["density"]
     else:
         cfg["bandwidth"] = w["bw"]
+    if world is not None:
+        # identical in both arms (b200 / reference) so that the driver sees the same config
+        cfg["l2"] = "working set > L2 per iteration (H alone is %d MB)" % (8 * w["m"] ** 2 // 2 ** 20)
+        cfg["parallelism"] = "schur-columns block-cyclic x%d (blocks of %d columns)" % (world, DIST_BLOCK)
     return cfg
 
 
@@ -474,9 +478,7 @@ def run_b200(args):
     if rank != 0:
         return
     cpu = cpu_baseline(args.workload) if world == 1 else None       # host baseline: rank 0 at N = 1 only
-    cfg = config_of(args.workload)
-    cfg["l2"] = "working set > L2 per iteration (H alone is %d MB)" % (8 * main["m"] ** 2 // 2 ** 20)
-    cfg["parallelism"] = "schur-columns block-cyclic x%d (blocks of %d columns)" % (world, DIST_BLOCK)
+    cfg = config_of(args.workload, world)
     out = {
         "metric": "s_per_ipm_iteration", "value": main["dev_s"], "unit": "s/iter", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": main["dev_s"] * 1e3, "higher_is_better": False,
@@ -664,7 +666,7 @@ def run_reference(args):
         vals.append(cpu["value"])
     v = float(np.mean(vals))
     cpu["value"] = v
-    cfg = config_of(args.workload)
+    cfg = config_of(args.workload, world)
     out = {"impl": "reference", "metric": "s_per_ipm_iteration", "value": v, "unit": "s/iter",
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * 1e3,
            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",

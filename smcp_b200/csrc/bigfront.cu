@@ -30,6 +30,10 @@ static bool dinv_on() {
     static const bool off = getenv("SMCP_B200_NO_DINV") && atoi(getenv("SMCP_B200_NO_DINV")) != 0;
     return !off;
 }
+static bool side_on() {
+    static const bool off = getenv("SMCP_B200_NO_SIDE") && atoi(getenv("SMCP_B200_NO_SIDE")) != 0;
+    return !off;
+}
 static bool thin_on() {
     static const bool off = getenv("SMCP_B200_NO_THIN") && atoi(getenv("SMCP_B200_NO_THIN")) != 0;
     return !off;
@@ -939,7 +943,15 @@ int big_hess_up(smcp_sym *s, const BigNode &q, const double *Lt, const double *Y
     const double *Lb = Lt + q.boff, *Ltan = Lb + nn, *Yaa = Yaa_all + q.uoff;
     double *F = WS(0), *T1 = WS(1), *T2 = WS(2);
     if (nn <= THIN_NN && na >= 1 && thin_on()) {
-        double *W = WS(0);
+        // W of this supernode outlives the launch on its lane (the product below runs on a side stream): own slot
+        const size_t tidx = (size_t)(&q - s->big.data());
+        if (s->thin_w_off.empty()) {
+            size_t tot = 0;
+            for (const BigNode &t : s->big) { s->thin_w_off.push_back(tot); if (t.nn <= THIN_NN) tot += (size_t)t.na * t.nn; }
+            CUDA_TRY(cudaMalloc(&s->thin_w, std::max<size_t>(tot, 1) * sizeof(double)));
+            s->allocs.push_back(s->thin_w);
+        }
+        double *W = s->thin_w + s->thin_w_off[tidx];
         if (!s->thin_counters) {
             CUDA_TRY(cudaMalloc(&s->thin_counters, 64 * sizeof(unsigned)));
             CUDA_TRY(cudaMemset(s->thin_counters, 0, 64 * sizeof(unsigned)));
@@ -952,7 +964,35 @@ int big_hess_up(smcp_sym *s, const BigNode &q, const double *Lt, const double *Y
         }
         // M_an = Y_aa W^T.  Y_aa is stored full and exactly symmetric (the alpha x alpha gather mirrors the lower entries), so
         // it is read as its transpose: a warp then owns a row and streams one contiguous column (na / 8 CTAs instead of na / 32)
-        if (G(s, true, false, Yaa, na, W, nn, blk + nn, nj, na, nn, na, 1.0, 0)) return -1;
+        // Nothing in the rest of the leaves-to-root pass reads M_an (the parents take the update matrix): the product
+        // leaves the chain of dependent launches and runs on a side stream; big_thin_join() waits for all of them before
+        // the root-to-leaves pass
+        if (ctx->prof || !side_on()) {
+            if (G(s, true, false, Yaa, na, W, nn, blk + nn, nj, na, nn, na, 1.0, 0)) return -1;
+        } else {
+            if (s->thin_side.empty()) {
+                for (int i = 0; i < 4; ++i) {
+                    cudaStream_t st;
+                    CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+                    s->thin_side.push_back(st);
+                }
+                for (size_t i = 0; i < 2 * s->big.size(); ++i) {
+                    cudaEvent_t e;
+                    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                    s->thin_ev.push_back(e);
+                }
+            }
+            cudaStream_t side = s->thin_side[tidx % s->thin_side.size()];
+            CUDA_TRY(cudaEventRecord(s->thin_ev[2 * tidx], ctx->stream));
+            CUDA_TRY(cudaStreamWaitEvent(side, s->thin_ev[2 * tidx], 0));
+            cudaStream_t saved = ctx->stream;
+            ctx->stream = side;
+            const int rc = G(s, true, false, Yaa, na, W, nn, blk + nn, nj, na, nn, na, 1.0, 0);
+            ctx->stream = saved;
+            if (rc) return -1;
+            CUDA_TRY(cudaEventRecord(s->thin_ev[2 * tidx + 1], side));
+            s->thin_pending.push_back((int)tidx);
+        }
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
@@ -1006,6 +1046,13 @@ int big_hess_up(smcp_sym *s, const BigNode &q, const double *Lt, const double *Y
     }
     ELEM(big_sym_store_kernel, (long long)nn * nn, T2, nn, blk, nj, nn, 0.0, 1.0);
     CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// the side-stream products of big_hess_up must have landed before anything reads M_an
+int big_thin_join(smcp_sym *s) {
+    for (int idx : s->thin_pending) CUDA_TRY(cudaStreamWaitEvent(s->ctx->stream, s->thin_ev[2 * (size_t)idx + 1], 0));
+    s->thin_pending.clear();
     return 0;
 }
 

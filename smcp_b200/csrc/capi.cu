@@ -132,7 +132,12 @@ extern "C" int smcp_ctx_create(int device, smcp_ctx **out) {
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     ctx->num_sms = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    {
+        // the look-ahead stream carries the critical path of the blocked Cholesky (next panel + its broadcast): its CTAs go first
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_hi));
+    }
     CUDA_TRY(cudaEventCreate(&ctx->ev0));
     CUDA_TRY(cudaEventCreate(&ctx->ev1));
     CUDA_TRY(cudaEventCreate(&ctx->pev0));
@@ -207,6 +212,7 @@ extern "C" int smcp_ctx_destroy(smcp_ctx *ctx) {
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);
     if (ctx->gridbar) cudaFree(ctx->gridbar);
+    if (ctx->wave_buf) cudaFree(ctx->wave_buf);
     if (ctx->trs_dinv) cudaFree(ctx->trs_dinv);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaEventDestroy(ctx->ev0);
@@ -394,6 +400,9 @@ extern "C" int smcp_sym_create(smcp_ctx *ctx, const smcp_sym_desc *D, smcp_sym *
 extern "C" int smcp_sym_destroy(smcp_sym *s) {
     if (!s) return 0;
     cudaStreamSynchronize(s->ctx->stream);
+    for (cudaStream_t st : s->thin_side) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (cudaEvent_t e : s->thin_ev) cudaEventDestroy(e);
+    if (s->tree_side) { cudaStreamSynchronize(s->tree_side); cudaStreamDestroy(s->tree_side); cudaEventDestroy(s->tree_ev[0]); cudaEventDestroy(s->tree_ev[1]); }
     for (void *p : s->allocs) cudaFree(p);
     if (s->counter) cudaFree(s->counter);
     if (s->done) cudaFree(s->done);

@@ -185,6 +185,43 @@ static int big_sweep(smcp_sym *s, const std::vector<std::vector<int>> &levels, F
     return 0;
 }
 
+// The tree kernel of an operation whose top-set part does not depend on it (completion, chol(Y_aa), the local phase of
+// the inverse Hessian: all per-supernode independent) runs on a side stream next to the concurrent lanes of the top set;
+// side_join() makes the main stream wait for it.  Off while profiling (per-launch events) and with SMCP_B200_NO_SIDE=1.
+struct SideScope {
+    smcp_sym *s;
+    cudaStream_t saved = nullptr;
+    bool on = false;
+    SideScope(smcp_sym *sym, bool enable) : s(sym) {
+        static const bool off = getenv("SMCP_B200_NO_SIDE") && atoi(getenv("SMCP_B200_NO_SIDE")) != 0;
+        smcp_ctx *ctx = s->ctx;
+        if (!enable || off || ctx->prof || ctx->lanes_active) return;
+        if (!s->tree_side) {
+            if (cudaStreamCreateWithFlags(&s->tree_side, cudaStreamNonBlocking) != cudaSuccess) { s->tree_side = nullptr; return; }
+            cudaEventCreateWithFlags(&s->tree_ev[0], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&s->tree_ev[1], cudaEventDisableTiming);
+        }
+        cudaEventRecord(s->tree_ev[0], ctx->stream);
+        cudaStreamWaitEvent(s->tree_side, s->tree_ev[0], 0);
+        saved = ctx->stream;
+        ctx->stream = s->tree_side;
+        on = true;
+    }
+    ~SideScope() {
+        if (!on) return;
+        cudaEventRecord(s->tree_ev[1], s->tree_side);
+        s->ctx->stream = saved;
+        s->tree_pending = true;
+    }
+};
+static int side_join(smcp_sym *s) {
+    if (s->tree_pending) {
+        CUDA_TRY(cudaStreamWaitEvent(s->ctx->stream, s->tree_ev[1], 0));
+        s->tree_pending = false;
+    }
+    return 0;
+}
+
 int k_cholesky(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
     RegionScope rs(s->ctx, batch > 1 ? "op_cholesky_batch" : "op_cholesky");
     if (s->small) return ks_cholesky(s, x, batch, info_host);
@@ -248,7 +285,10 @@ int k_completion(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
     a.Xin = s->tmp;
     const bool big = use_big(s, batch);
     if (big) a.skipflag = s->big_flag;
-    if (launch_tree<OP_COMPL>(s, a, flat_sched(s), batch, pick_threads(s, big), batch > 1 ? "completion_batch" : "completion")) return -1;
+    {
+        SideScope side(s, big);
+        if (launch_tree<OP_COMPL>(s, a, flat_sched(s), batch, pick_threads(s, big), batch > 1 ? "completion_batch" : "completion")) return -1;
+    }
     if (big) {
         // The completion of a supernode depends on the INPUT matrix only, so with several
         // ranks (replicas of the same solve) the supernodes of the top set are shared out round-robin and
@@ -270,6 +310,7 @@ int k_completion(smcp_sym *s, double *x, int64_t batch, int32_t *info_host) {
             }
         }
         if (big_lanes_end(s) || rc) return -1;
+        if (side_join(s)) return -1;
         if (nr > 1) {
             if (comm_group_start()) return -1;
             int idx = 0;
@@ -321,7 +362,10 @@ int k_hess_prep_inv(smcp_hess *h) {
     a.Raa = h->Raa;
     const bool big = use_big(s, 1);
     if (big) a.skipflag = s->big_flag;
-    if (launch_tree<OP_HPREP_INV>(s, a, flat_sched(s), 1, pick_threads(s, big), "hessian_prep_inv")) return -1;
+    {
+        SideScope side(s, big);
+        if (launch_tree<OP_HPREP_INV>(s, a, flat_sched(s), 1, pick_threads(s, big), "hessian_prep_inv")) return -1;
+    }
     if (big) {
         // independent per supernode as well: chol(Y_aa) of the top set shared out over the ranks
         smcp_ctx *ctx = s->ctx;
@@ -337,6 +381,7 @@ int k_hess_prep_inv(smcp_hess *h) {
             ++idx;
         }
         if (big_lanes_end(s) || rc) return -1;
+        if (side_join(s)) return -1;
         if (nr > 1) {
             if (comm_group_start()) return -1;
             idx = 0;
@@ -376,6 +421,7 @@ int k_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
         if (big)
             for (int64_t b = 0; b < batch; ++b) {
                 if (big_sweep(s, s->big_up, [&](const BigNode &q) { return big_hess_up(s, q, h->Lt, h->Yaa, U, b); })) return -1;
+                if (big_thin_join(s)) return -1;
                 if (big_sweep(s, s->big_down, [&](const BigNode &q) { return big_hess_down(s, q, h->Lt, U, b); })) return -1;
             }
         return launch_tree<OP_HFWD_DOWN>(s, a, s->down, batch, threads, many ? "hessian_down_batch" : "hessian_down");
@@ -384,7 +430,11 @@ int k_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
         if (k_hess_prep_inv(h)) return -1;
         h->have_Raa = true;
     }
-    if (launch_tree<OP_HINV>(s, a, s->up, batch, threads, batch >= 32 ? "hessian_inv_batch" : "hessian_inv")) return -1;
+    {
+        // the small supernodes' sweep and the top set's local phase touch disjoint data (the top set is closed under ancestors)
+        SideScope side(s, big && batch == 1);
+        if (launch_tree<OP_HINV>(s, a, s->up, batch, threads, batch >= 32 ? "hessian_inv_batch" : "hessian_inv")) return -1;
+    }
     if (big) {
         // top set: the per-supernode part first (independent: shared out over the ranks of a replicated solve,
         // results exchanged by grouped broadcasts of nj x nn doubles per supernode), then the leaves-to-root sweep
@@ -404,6 +454,7 @@ int k_hess_apply(smcp_hess *h, double *U, int64_t batch, int inv) {
                 ++idx;
             }
             if (big_lanes_end(s) || rc) return -1;
+            if (side_join(s)) return -1;
             if (nr > 1) {
                 if (comm_group_start()) return -1;
                 idx = 0;

@@ -786,7 +786,11 @@ int d_potrf(smcp_ctx *ctx, double *H, int64_t ld, int64_t m, int64_t ncols, int3
         if (!potrf_tile_fits(ctx, m - c0, w, !full_mode)) { smcp_set_error("d_potrf: panel too tall for the tile kernel"); return -2; }
         return potrf_tile(ctx, H + c0 + c0 * ld, ld, m - c0, w, !full_mode, info_dev, (int)c0);
     };
-    if (nranks == 1) {
+    // one GPU: the look-ahead schedule of the block-cyclic path -- panel q+1 on the second (high-priority) stream, on at most
+    // SMCP_B200_POTRF_LA SMs (default 48; 0 = plain loop), while the main stream applies panel q to the rest.
+    // m = 10^4: 25.6 -> 23.5 ms (gpurun_out/r02_v31_potrf_la.log)
+    static const int la_ctas = getenv("SMCP_B200_POTRF_LA") ? atoi(getenv("SMCP_B200_POTRF_LA")) : 48;
+    if (nranks == 1 && !(la_ctas > 0 && ld == m && ncols == m && ctx->stream2)) {
         for (int64_t q = 0; q < nblocks; ++q) {
             const int64_t c0 = q * block, w = blk_w(q), c1 = c0 + w;
             if (factor_block(q)) return -1;
@@ -815,7 +819,7 @@ int d_potrf(smcp_ctx *ctx, double *H, int64_t ld, int64_t m, int64_t ncols, int3
     {
         StreamSwap sw(ctx, sA);
         if (rank == 0 && factor_block(0)) return -1;
-        if (comm_bcast(ctx, H, (size_t)blk_w(0) * ld, 0, sA)) return -1;
+        if (nranks > 1 && comm_bcast(ctx, H, (size_t)blk_w(0) * ld, 0, sA)) return -1;
         if (two) CUDA_TRY(cudaEventRecord(E[0], sA));
     }
     for (int64_t q = 0; q < nblocks; ++q) {
@@ -831,9 +835,12 @@ int d_potrf(smcp_ctx *ctx, double *H, int64_t ld, int64_t m, int64_t ncols, int3
             if (two && q >= 1) CUDA_TRY(cudaStreamWaitEvent(sA, F[q - 1], 0));
             if ((q + 1) % nranks == rank) {
                 if (launch_gemm(ctx, false, false, P1, ld, P1, ld, H + c1 + c1 * ld, ld, m - c1, w1, w, -1.0, 1, 1, 0, "potrf_syrk_dmma")) return -1;
-                if (factor_block(q + 1)) return -1;
+                if (nranks == 1) ctx->potrf_grid_cap = la_ctas;
+                const int rcf = factor_block(q + 1);
+                ctx->potrf_grid_cap = 0;
+                if (rcf) return -1;
             }
-            if (comm_bcast(ctx, H + c1 * ld, (size_t)w1 * ld, (int)((q + 1) % nranks), sA)) return -1;
+            if (nranks > 1 && comm_bcast(ctx, H + c1 * ld, (size_t)w1 * ld, (int)((q + 1) % nranks), sA)) return -1;
             if (two) CUDA_TRY(cudaEventRecord(E[q + 1], sA));
         }
         if (c2 < m) {

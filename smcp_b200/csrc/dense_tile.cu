@@ -433,6 +433,7 @@ int potrf_tile(smcp_ctx *ctx, double *H, int64_t ld, int64_t mm, int64_t npiv, b
     // (a CTA then owns more tiles; the arithmetic of a tile does not depend on who owns it)
     int64_t gcap = ctx->num_sms;
     if (ctx->lanes_active > 1) gcap = std::max<int64_t>(ctx->num_sms / ctx->lanes_active, (ntiles + PT_MAXOWN - 1) / PT_MAXOWN);
+    if (ctx->potrf_grid_cap > 0) gcap = std::max<int64_t>(std::min<int64_t>(gcap, ctx->potrf_grid_cap), (ntiles + PT_MAXOWN - 1) / PT_MAXOWN);
     const unsigned grid = (unsigned)std::min<int64_t>(std::min<int64_t>(gcap, ctx->num_sms), ntiles);
     void *args[] = {&a};
     LaunchScope ls(ctx, "potrf_tile", 1, (double)npiv * npiv * npiv / 3.0);

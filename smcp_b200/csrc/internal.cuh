@@ -59,6 +59,7 @@ struct smcp_ctx {
     void *wave_buf = nullptr;                       // potrs_wave_kernel: published block solutions + flags
     size_t wave_cap = 0;
     unsigned wave_epoch = 0;
+    int potrf_grid_cap = 0;                         // > 0: potrf_tile uses at most this many CTAs (look-ahead panel next to a GEMM)
     const char *potrf_family = nullptr;             // profile family of the next d_potrf (default "potrf_dmma")
     int prof_mute = 0;                              // > 0: nested LaunchScopes do not time (an outer scope does)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;       // user timer
@@ -195,6 +196,14 @@ struct smcp_sym {
     std::vector<size_t> thin_dinv_off;
     std::vector<uint64_t> thin_dinv_gen; // scaling point (raa_gen) the cached blocks belong to
     uint64_t raa_gen_next = 0, raa_gen_cur = 0;
+    cudaStream_t tree_side = nullptr;    // side stream of the tree kernels that overlap with the top-set lanes (chordal.cu)
+    cudaEvent_t tree_ev[2] = {nullptr, nullptr};
+    bool tree_pending = false;
+    double *thin_w = nullptr;            // W = D^-1 K_an^T of every thin supernode (forward Hessian)
+    std::vector<size_t> thin_w_off;
+    std::vector<cudaStream_t> thin_side; // side streams of the M_an products
+    std::vector<cudaEvent_t> thin_ev;    // 2 per top-set supernode: thin_up done / product done
+    std::vector<int> thin_pending;
     double *big_dinv = nullptr;          // (L_nn L_nn^T)^-1 of the wide top-set supernodes (forward Hessian), per scaling point
     std::vector<size_t> big_dinv_off;
     std::vector<uint64_t> big_dinv_gen;
@@ -274,6 +283,7 @@ int big_cholesky(smcp_sym *s, const BigNode &q, double *X, int64_t b);
 int big_llt(smcp_sym *s, const BigNode &q, double *X, int64_t b);
 int big_hess_up(smcp_sym *s, const BigNode &q, const double *Lt, const double *Yaa_all, double *X, int64_t b);
 int big_hess_down(smcp_sym *s, const BigNode &q, const double *Lt, double *X, int64_t b);
+int big_thin_join(smcp_sym *s);
 int big_hess_inv_local(smcp_sym *s, const BigNode &q, const double *Lt, const double *Raa_all, const double *X, int64_t b, double *KS);
 int big_hess_inv_sweep(smcp_sym *s, const BigNode &q, const double *Lt, double *X, int64_t b, const double *KS);
 int big_projinv(smcp_sym *s, const BigNode &q, double *X, int64_t b);
