@@ -64,6 +64,32 @@ __device__ __forceinline__ double big_children(const BigArgs &r, int i, int j, b
     return acc;
 }
 
+// children's contributions to the entries (i, j[0..3]) of a frontal matrix: the row lookup is done once per child and the
+// four column lookups / gathers are independent loads (big_children does two dependent lookups per entry)
+__device__ __forceinline__ void big_children_row4(const BigArgs &r, int i, const int (&j)[4], const bool (&live)[4], bool lower_stored,
+                                                  double (&acc)[4]) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[e] = 0.0;
+    for (int q = 0; q < r.nch; ++q) {
+        const int *invq = r.inv + (long long)q * r.nj;
+        const int a = invq[i];
+        if (a < 0) continue;
+        const int c = r.ch[q], nac = r.na_all[c];
+        const double *Uc = r.ub + r.updptr[c];
+        int b[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) b[e] = live[e] ? invq[j[e]] : -1;
+        double u[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            u[e] = 0.0;
+            if (b[e] >= 0) u[e] = lower_stored ? Uc[max(a, b[e]) + (long long)min(a, b[e]) * nac] : Uc[a + (long long)b[e] * nac];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] += u[e];
+    }
+}
+
 #define BIG_LOOP(total) for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < (total); idx += (long long)gridDim.x * blockDim.x)
 
 // F (nj x nj, lower) = [blk_nn(lower) ; blk_an ; 0] + children (lower-stored); upper <- 0        (cholesky)
@@ -481,13 +507,19 @@ __global__ void __launch_bounds__(256) thin_chol_kernel(BigArgs r, double *__res
     const int tx = tid & 31, ty = tid >> 5;
     const int i = i0 + tx;
     if (i < na) {
+        int jc[4];
+        bool live[4];
+        double ch[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { jc[q] = nn + j0 + ty + 8 * q; live[q] = j0 + ty + 8 * q < na && i >= j0 + ty + 8 * q; }
+        big_children_row4(r, nn + i, jc, live, true, ch);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int jj = ty + 8 * q, j = j0 + jj;
             if (j < na) {
                 double v = 0.0;
                 if (i >= j) {
-                    v = big_children(r, nn + i, nn + j, true);
+                    v = ch[q];
                     for (int k2 = 0; k2 < nn; ++k2) v = fma(-Li[k2][tx], Lj[k2][jj], v);
                 }
                 U[i + (long long)j * na] = v;
@@ -639,11 +671,17 @@ __global__ void __launch_bounds__(256) thin_up_kernel(BigArgs r, const double *_
     const int tx = tid & 31, ty = tid >> 5;
     const int i = i0 + tx;
     if (i < na) {
+        int jc[4];
+        bool live[4];
+        double ch[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { jc[q] = nn + j0 + ty + 8 * q; live[q] = j0 + ty + 8 * q < na; }
+        big_children_row4(r, nn + i, jc, live, false, ch);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int jj = ty + 8 * q, j = j0 + jj;
             if (j < na) {
-                double v = big_children(r, nn + i, nn + j, false);
+                double v = ch[q];
                 for (int k = 0; k < nn; ++k) v = fma(-Li[k][tx], Fj[k][jj], v);
                 for (int k = 0; k < nn; ++k) v = fma(-Ki[k][tx], Lj[k][jj], v);
                 U[i + (long long)j * na] = v;
@@ -910,6 +948,12 @@ __global__ void __launch_bounds__(256) thin_hinv_sweep_kernel(BigArgs r, const d
     const int tx = tid & 31, ty = tid >> 5;
     const int i = i0 + tx;
     if (i < na) {
+        int jc[4];
+        bool live[4];
+        double ch[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { jc[q] = nn + j0 + ty + 8 * q; live[q] = j0 + ty + 8 * q < na; }
+        big_children_row4(r, nn + i, jc, live, false, ch);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int jj = ty + 8 * q, j = j0 + jj;
@@ -917,7 +961,7 @@ __global__ void __launch_bounds__(256) thin_hinv_sweep_kernel(BigArgs r, const d
                 double v = 0.0;
                 for (int k = 0; k < nn; ++k) v = fma(Li[k][tx], Kj[k][jj], v);
                 for (int k = 0; k < nn; ++k) v = fma(Fi[k][tx], Lj[k][jj], v);
-                U[i + (long long)j * na] = v + big_children(r, nn + i, nn + j, false);
+                U[i + (long long)j * na] = v + ch[q];
             }
         }
         if (blockIdx.y == 0 && ty < nn) {
