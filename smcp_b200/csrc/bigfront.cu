@@ -26,6 +26,7 @@
 // thin supernodes: at most THIN_NN columns (the thin_* kernels below); SMCP_B200_NO_THIN / SMCP_B200_NO_DINV switch the
 // round-2 shortcuts off for A/B measurements
 #define THIN_NN 8
+#define THIN_TS 64         // tile of the alpha x alpha passes (thin_up / thin_hinv_sweep / thin_chol): 64 x 64 per CTA of 256 threads
 static bool dinv_on() {
     static const bool off = getenv("SMCP_B200_NO_DINV") && atoi(getenv("SMCP_B200_NO_DINV")) != 0;
     return !off;
@@ -455,12 +456,12 @@ int big_lanes_end(smcp_sym *s) {
 // two copies (5 launches).
 __global__ void __launch_bounds__(256) thin_chol_kernel(BigArgs r, double *__restrict__ blk, double *__restrict__ U, int *__restrict__ fail,
                                                         unsigned *__restrict__ counter) {
-    __shared__ double Li[THIN_NN][33], Lj[THIN_NN][33];
+    __shared__ double Li[THIN_NN][THIN_TS + 1], Lj[THIN_NN][THIN_TS + 1];
     __shared__ double Lnn[THIN_NN * THIN_NN];
     __shared__ int bad_s;
     __shared__ bool last_s;
     const int nn = r.nn, na = r.na, nj = r.nj, tid = threadIdx.x;
-    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    const int i0 = blockIdx.x * THIN_TS, j0 = blockIdx.y * THIN_TS;
     if (tid < THIN_NN * THIN_NN) {
         const int a = tid % THIN_NN, b = tid / THIN_NN;
         Lnn[tid] = (a < nn && b < nn && a >= b) ? blk[a + (long long)b * nj] + big_children(r, a, b, true) : 0.0;
@@ -481,9 +482,9 @@ __global__ void __launch_bounds__(256) thin_chol_kernel(BigArgs r, double *__res
     }
     __syncthreads();
     // rows of L_an: x L_nn^T = f  (forward over the columns)
-    if (tid < 64) {
-        const int rr = tid & 31;
-        const int row = (tid < 32 ? i0 : j0) + rr;
+    if (tid < 2 * THIN_TS) {
+        const int rr = tid % THIN_TS;
+        const int row = (tid < THIN_TS ? i0 : j0) + rr;
         double x[THIN_NN];
 #pragma unroll
         for (int k2 = 0; k2 < THIN_NN; ++k2)
@@ -499,30 +500,39 @@ __global__ void __launch_bounds__(256) thin_chol_kernel(BigArgs r, double *__res
             }
 #pragma unroll
         for (int k2 = 0; k2 < THIN_NN; ++k2) {
-            if (tid < 32) Li[k2][rr] = x[k2];
+            if (tid < THIN_TS) Li[k2][rr] = x[k2];
             else Lj[k2][rr] = x[k2];
         }
     }
     __syncthreads();
     const int tx = tid & 31, ty = tid >> 5;
-    const int i = i0 + tx;
-    if (i < na) {
-        int jc[4];
-        bool live[4];
-        double ch[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { jc[q] = nn + j0 + ty + 8 * q; live[q] = j0 + ty + 8 * q < na && i >= j0 + ty + 8 * q; }
-        big_children_row4(r, nn + i, jc, live, true, ch);
+    for (int ri = 0; ri < THIN_TS / 32; ++ri) {
+        const int ii = tx + 32 * ri, i = i0 + ii;
+        if (i >= na) continue;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int jj = ty + 8 * q, j = j0 + jj;
-            if (j < na) {
-                double v = 0.0;
-                if (i >= j) {
-                    v = ch[q];
-                    for (int k2 = 0; k2 < nn; ++k2) v = fma(-Li[k2][tx], Lj[k2][jj], v);
+        for (int qg = 0; qg < THIN_TS / 32; ++qg) {
+            int jc[4];
+            bool live[4];
+            double ch[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = j0 + ty + 8 * (4 * qg + q);
+                jc[q] = nn + j;
+                live[q] = j < na && i >= j;
+            }
+            big_children_row4(r, nn + i, jc, live, true, ch);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int jj = ty + 8 * (4 * qg + q), j = j0 + jj;
+                if (j < na) {
+                    double v = 0.0;
+                    if (i >= j) {
+                        v = ch[q];
+                        for (int k2 = 0; k2 < nn; ++k2) v = fma(-Li[k2][ii], Lj[k2][jj], v);
+                    }
+                    U[i + (long long)j * na] = v;
                 }
-                U[i + (long long)j * na] = v;
             }
         }
     }
@@ -575,7 +585,7 @@ int big_cholesky(smcp_sym *s, const BigNode &q, double *X, int64_t b) {
             s->allocs.push_back(s->thin_counters);
         }
         LaunchScope ls_(ctx, "thin_chol");
-        thin_chol_kernel<<<dim3((unsigned)((na + 31) / 32), (unsigned)((na + 31) / 32)), 256, 0, ctx->stream>>>(big_args(s, q, b), blk, Uk, s->fail + b,
+        thin_chol_kernel<<<dim3((unsigned)((na + THIN_TS - 1) / THIN_TS), (unsigned)((na + THIN_TS - 1) / THIN_TS)), 256, 0, ctx->stream>>>(big_args(s, q, b), blk, Uk, s->fail + b,
                                                                                                                 s->thin_counters + s->big_lane);
         CUDA_TRY(cudaGetLastError());
         return 0;
@@ -641,19 +651,19 @@ __device__ __forceinline__ void thin_dsolve(const double *Lnn, int nn, double (&
 // the CTA that finishes LAST (every CTA has read the block's nn x nn part by then) stores M_nn = D^-1 F_nn D^-1 into it.
 __global__ void __launch_bounds__(256) thin_up_kernel(BigArgs r, const double *__restrict__ Lb, double *__restrict__ blk, double *__restrict__ U,
                                                       double *__restrict__ W, unsigned *__restrict__ counter) {
-    __shared__ double Li[THIN_NN][33], Lj[THIN_NN][33], Fi[THIN_NN][33], Fj[THIN_NN][33], Ki[THIN_NN][33];
+    __shared__ double Li[THIN_NN][THIN_TS + 1], Lj[THIN_NN][THIN_TS + 1], Fi[THIN_NN][THIN_TS + 1], Fj[THIN_NN][THIN_TS + 1], Ki[THIN_NN][THIN_TS + 1];
     __shared__ double Fnn[THIN_NN * THIN_NN], Lnn[THIN_NN * THIN_NN], T1[THIN_NN * THIN_NN], Msm[THIN_NN * THIN_NN];
     __shared__ bool last_s;
     const int nn = r.nn, na = r.na, nj = r.nj, tid = threadIdx.x;
-    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    const int i0 = blockIdx.x * THIN_TS, j0 = blockIdx.y * THIN_TS;
     if (tid < nn * nn) {
         const int a = tid % nn, b = tid / nn;
         const int hi = max(a, b), lo = min(a, b);
         Fnn[a + b * THIN_NN] = blk[hi + (long long)lo * nj] + big_children(r, a, b, false);
         Lnn[a + b * THIN_NN] = (a >= b) ? Lb[a + (long long)b * nj] : 0.0;
     }
-    for (int idx = tid; idx < 32 * nn; idx += 256) {
-        const int rr = idx & 31, k = idx >> 5;
+    for (int idx = tid; idx < THIN_TS * nn; idx += 256) {
+        const int rr = idx % THIN_TS, k = idx / THIN_TS;
         const int i = i0 + rr, j = j0 + rr;
         Li[k][rr] = (i < na) ? Lb[(nn + i) + (long long)k * nj] : 0.0;
         Fi[k][rr] = (i < na) ? blk[(nn + i) + (long long)k * nj] + big_children(r, nn + i, k, false) : 0.0;
@@ -661,36 +671,41 @@ __global__ void __launch_bounds__(256) thin_up_kernel(BigArgs r, const double *_
         Fj[k][rr] = (j < na) ? blk[(nn + j) + (long long)k * nj] + big_children(r, nn + j, k, false) : 0.0;
     }
     __syncthreads();
-    for (int idx = tid; idx < 32 * nn; idx += 256) {
-        const int rr = idx & 31, k = idx >> 5;
+    for (int idx = tid; idx < THIN_TS * nn; idx += 256) {
+        const int rr = idx % THIN_TS, k = idx / THIN_TS;
         double t = Fi[k][rr];
         for (int l = 0; l < nn; ++l) t = fma(-Li[l][rr], Fnn[l + k * THIN_NN], t);
         Ki[k][rr] = t;
     }
     __syncthreads();
     const int tx = tid & 31, ty = tid >> 5;
-    const int i = i0 + tx;
-    if (i < na) {
-        int jc[4];
-        bool live[4];
-        double ch[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { jc[q] = nn + j0 + ty + 8 * q; live[q] = j0 + ty + 8 * q < na; }
-        big_children_row4(r, nn + i, jc, live, false, ch);
+    for (int ri = 0; ri < THIN_TS / 32; ++ri) {
+        const int ii = tx + 32 * ri, i = i0 + ii;
+        if (i >= na) continue;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int jj = ty + 8 * q, j = j0 + jj;
-            if (j < na) {
-                double v = ch[q];
-                for (int k = 0; k < nn; ++k) v = fma(-Li[k][tx], Fj[k][jj], v);
-                for (int k = 0; k < nn; ++k) v = fma(-Ki[k][tx], Lj[k][jj], v);
-                U[i + (long long)j * na] = v;
+        for (int qg = 0; qg < THIN_TS / 32; ++qg) {
+            int jc[4];
+            bool live[4];
+            double ch[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { jc[q] = nn + j0 + ty + 8 * (4 * qg + q); live[q] = j0 + ty + 8 * (4 * qg + q) < na; }
+            big_children_row4(r, nn + i, jc, live, false, ch);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int jj = ty + 8 * (4 * qg + q), j = j0 + jj;
+                if (j < na) {
+                    double v = ch[q];
+                    for (int k = 0; k < nn; ++k) v = fma(-Li[k][ii], Fj[k][jj], v);
+                    for (int k = 0; k < nn; ++k) v = fma(-Ki[k][ii], Lj[k][jj], v);
+                    U[i + (long long)j * na] = v;
+                }
             }
         }
         if (blockIdx.y == 0 && ty == 0) {
             double w[THIN_NN];
 #pragma unroll
-            for (int k = 0; k < THIN_NN; ++k) w[k] = (k < nn) ? Ki[k][tx] : 0.0;
+            for (int k = 0; k < THIN_NN; ++k) w[k] = (k < nn) ? Ki[k][ii] : 0.0;
             thin_dsolve(Lnn, nn, w);
 #pragma unroll
             for (int k = 0; k < THIN_NN; ++k)
@@ -926,46 +941,51 @@ __global__ void __launch_bounds__(512) thin_hinv_local_kernel(int nn, int na, in
 // also store F_an + children into the block, CTA (0, 0) the symmetrised K_nn + children.
 __global__ void __launch_bounds__(256) thin_hinv_sweep_kernel(BigArgs r, const double *__restrict__ Lb, const double *__restrict__ Knn,
                                                               const double *__restrict__ Kan, double *__restrict__ blk, double *__restrict__ U) {
-    __shared__ double Li[THIN_NN][33], Lj[THIN_NN][33], Kj[THIN_NN][33], Fi[THIN_NN][33], Ks[THIN_NN * THIN_NN];
+    __shared__ double Li[THIN_NN][THIN_TS + 1], Lj[THIN_NN][THIN_TS + 1], Kj[THIN_NN][THIN_TS + 1], Fi[THIN_NN][THIN_TS + 1], Ks[THIN_NN * THIN_NN];
     const int nn = r.nn, na = r.na, nj = r.nj, tid = threadIdx.x;
-    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    const int i0 = blockIdx.x * THIN_TS, j0 = blockIdx.y * THIN_TS;
     if (tid < nn * nn) Ks[(tid % nn) + (tid / nn) * THIN_NN] = Knn[tid];
-    for (int idx = tid; idx < 32 * nn; idx += 256) {
-        const int rr = idx & 31, k = idx >> 5;
+    for (int idx = tid; idx < THIN_TS * nn; idx += 256) {
+        const int rr = idx % THIN_TS, k = idx / THIN_TS;
         const bool vi = i0 + rr < na, vj = j0 + rr < na;
         Li[k][rr] = vi ? Lb[(nn + i0 + rr) + (long long)k * nj] : 0.0;
         Lj[k][rr] = vj ? Lb[(nn + j0 + rr) + (long long)k * nj] : 0.0;
         Kj[k][rr] = vj ? Kan[(j0 + rr) + (long long)k * na] : 0.0;
     }
     __syncthreads();
-    for (int idx = tid; idx < 32 * nn; idx += 256) {
-        const int rr = idx & 31, k = idx >> 5;
+    for (int idx = tid; idx < THIN_TS * nn; idx += 256) {
+        const int rr = idx % THIN_TS, k = idx / THIN_TS;
         double t = (i0 + rr < na) ? Kan[(i0 + rr) + (long long)k * na] : 0.0;
         for (int c = 0; c < nn; ++c) t = fma(Li[c][rr], Ks[c + k * THIN_NN], t);
         Fi[k][rr] = t;
     }
     __syncthreads();
     const int tx = tid & 31, ty = tid >> 5;
-    const int i = i0 + tx;
-    if (i < na) {
-        int jc[4];
-        bool live[4];
-        double ch[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { jc[q] = nn + j0 + ty + 8 * q; live[q] = j0 + ty + 8 * q < na; }
-        big_children_row4(r, nn + i, jc, live, false, ch);
+    for (int ri = 0; ri < THIN_TS / 32; ++ri) {
+        const int ii = tx + 32 * ri, i = i0 + ii;
+        if (i >= na) continue;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int jj = ty + 8 * q, j = j0 + jj;
-            if (j < na) {
-                double v = 0.0;
-                for (int k = 0; k < nn; ++k) v = fma(Li[k][tx], Kj[k][jj], v);
-                for (int k = 0; k < nn; ++k) v = fma(Fi[k][tx], Lj[k][jj], v);
-                U[i + (long long)j * na] = v + ch[q];
+        for (int qg = 0; qg < THIN_TS / 32; ++qg) {
+            int jc[4];
+            bool live[4];
+            double ch[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { jc[q] = nn + j0 + ty + 8 * (4 * qg + q); live[q] = j0 + ty + 8 * (4 * qg + q) < na; }
+            big_children_row4(r, nn + i, jc, live, false, ch);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int jj = ty + 8 * (4 * qg + q), j = j0 + jj;
+                if (j < na) {
+                    double v = 0.0;
+                    for (int k = 0; k < nn; ++k) v = fma(Li[k][ii], Kj[k][jj], v);
+                    for (int k = 0; k < nn; ++k) v = fma(Fi[k][ii], Lj[k][jj], v);
+                    U[i + (long long)j * na] = v + ch[q];
+                }
             }
         }
         if (blockIdx.y == 0 && ty < nn) {
-            for (int k = ty; k < nn; k += 8) blk[(nn + i) + (long long)k * nj] = Fi[k][tx] + big_children(r, nn + i, k, false);
+            for (int k = ty; k < nn; k += 8) blk[(nn + i) + (long long)k * nj] = Fi[k][ii] + big_children(r, nn + i, k, false);
         }
     }
     if (blockIdx.x == 0 && blockIdx.y == 0 && tid < nn * nn) {
@@ -1003,7 +1023,7 @@ int big_hess_up(smcp_sym *s, const BigNode &q, const double *Lt, const double *Y
         }
         {
             LaunchScope ls_(ctx, "thin_up");
-            thin_up_kernel<<<dim3((unsigned)((na + 31) / 32), (unsigned)((na + 31) / 32)), 256, 0, ctx->stream>>>(big_args(s, q, b), Lb, blk, Uk, W,
+            thin_up_kernel<<<dim3((unsigned)((na + THIN_TS - 1) / THIN_TS), (unsigned)((na + THIN_TS - 1) / THIN_TS)), 256, 0, ctx->stream>>>(big_args(s, q, b), Lb, blk, Uk, W,
                                                                                                                   s->thin_counters + s->big_lane);
         }
         // M_an = Y_aa W^T.  Y_aa is stored full and exactly symmetric (the alpha x alpha gather mirrors the lower entries), so
@@ -1213,7 +1233,7 @@ int big_hess_inv_sweep(smcp_sym *s, const BigNode &q, const double *Lt, double *
     double *Zaa = WS(1), *Man = WS(2);
     if (nn <= THIN_NN && na >= 1 && thin_on()) {
         LaunchScope ls_(ctx, "thin_hinv_sweep");
-        thin_hinv_sweep_kernel<<<dim3((unsigned)((na + 31) / 32), (unsigned)((na + 31) / 32)), 256, 0, ctx->stream>>>(big_args(s, q, b), Lt + q.boff, Mnn,
+        thin_hinv_sweep_kernel<<<dim3((unsigned)((na + THIN_TS - 1) / THIN_TS), (unsigned)((na + THIN_TS - 1) / THIN_TS)), 256, 0, ctx->stream>>>(big_args(s, q, b), Lt + q.boff, Mnn,
                                                                                                                       Kan, blk, Uk);
         CUDA_TRY(cudaGetLastError());
         return 0;

@@ -213,6 +213,7 @@ extern "C" int smcp_ctx_destroy(smcp_ctx *ctx) {
     if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);
     if (ctx->gridbar) cudaFree(ctx->gridbar);
     if (ctx->wave_buf) cudaFree(ctx->wave_buf);
+    if (ctx->potrf_pt) cudaFree(ctx->potrf_pt);
     if (ctx->trs_dinv) cudaFree(ctx->trs_dinv);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaEventDestroy(ctx->ev0);

@@ -644,6 +644,25 @@ struct StreamSwap {      // run the launch helpers (which use ctx->stream) on an
 };
 }  // namespace
 
+// Pt(k, i) = P(i, k): the factored panel (rows x w, rows contiguous) as a K-major operand, so that its trailing update
+// C -= P P^T runs through the TMA-fed GEMM (26.6 instead of ~21 TFLOP/s); 2 x 8 x rows x w bytes per panel, ~15 us
+__global__ void panel_transpose_kernel(const double *__restrict__ P, long long ldp, long long rows, int w, double *__restrict__ Pt, long long ldt) {
+    __shared__ double tile[32][33];
+    const long long i0 = (long long)blockIdx.x * 32;
+    const int k0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const long long i = i0 + threadIdx.x;
+        const int k = k0 + r;
+        tile[r][threadIdx.x] = (i < rows && k < w) ? P[i + (long long)k * ldp] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int k = k0 + threadIdx.x;
+        const long long i = i0 + r;
+        if (i < rows && k < w) Pt[k + i * ldt] = tile[threadIdx.x][r];
+    }
+}
+
 // factor the column block [c0, c0+w) of H (rows c0..mrows): two 64-column panels
 static int potrf_block(smcp_ctx *ctx, double *H, int64_t ld, int64_t mrows, int64_t c0, int64_t w, int32_t *info_dev, size_t pp_smem) {
     for (int64_t k0 = c0; k0 < c0 + w; k0 += NB) {
@@ -816,10 +835,29 @@ int d_potrf(smcp_ctx *ctx, double *H, int64_t ld, int64_t m, int64_t ncols, int3
         CUDA_TRY(cudaEventRecord(fork, sB));
         CUDA_TRY(cudaStreamWaitEvent(sA, fork, 0));
     }
+    // one GPU: K-major copies of the panels (two buffers: panel q+1 is transposed while panel q is still being applied)
+    static const bool pt_off = getenv("SMCP_B200_POTRF_NO_PT") && atoi(getenv("SMCP_B200_POTRF_NO_PT")) != 0;
+    const bool use_pt = nranks == 1 && !pt_off && (block % 2) == 0;
+    double *PT[2] = {nullptr, nullptr};
+    if (use_pt) {
+        if (grow((void **)&ctx->potrf_pt, &ctx->potrf_pt_cap, (size_t)2 * block * m * sizeof(double))) return -1;
+        PT[0] = ctx->potrf_pt;
+        PT[1] = ctx->potrf_pt + (size_t)block * m;
+    }
+    auto transpose_panel = [&](int64_t q) -> int {
+        const int64_t c0 = q * block, w = blk_w(q), c1 = c0 + w;
+        if (c1 >= m) return 0;
+        LaunchScope ls(ctx, "potrf_panel_t");
+        panel_transpose_kernel<<<dim3((unsigned)((m - c1 + 31) / 32), (unsigned)((w + 31) / 32)), dim3(32, 8), 0, ctx->stream>>>(
+            H + c1 + c0 * ld, ld, m - c1, (int)w, PT[q & 1], w);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    };
     {
         StreamSwap sw(ctx, sA);
         if (rank == 0 && factor_block(0)) return -1;
         if (nranks > 1 && comm_bcast(ctx, H, (size_t)blk_w(0) * ld, 0, sA)) return -1;
+        if (use_pt && transpose_panel(0)) return -1;
         if (two) CUDA_TRY(cudaEventRecord(E[0], sA));
     }
     for (int64_t q = 0; q < nblocks; ++q) {
@@ -834,11 +872,16 @@ int d_potrf(smcp_ctx *ctx, double *H, int64_t ld, int64_t m, int64_t ncols, int3
             StreamSwap sw(ctx, sA);
             if (two && q >= 1) CUDA_TRY(cudaStreamWaitEvent(sA, F[q - 1], 0));
             if ((q + 1) % nranks == rank) {
-                if (launch_gemm(ctx, false, false, P1, ld, P1, ld, H + c1 + c1 * ld, ld, m - c1, w1, w, -1.0, 1, 1, 0, "potrf_syrk_dmma")) return -1;
+                if (use_pt) {
+                    if (launch_gemm(ctx, true, true, PT[q & 1], w, PT[q & 1], w, H + c1 + c1 * ld, ld, m - c1, w1, w, -1.0, 1, 1, 0, "potrf_syrk_dmma")) return -1;
+                } else {
+                    if (launch_gemm(ctx, false, false, P1, ld, P1, ld, H + c1 + c1 * ld, ld, m - c1, w1, w, -1.0, 1, 1, 0, "potrf_syrk_dmma")) return -1;
+                }
                 if (nranks == 1) ctx->potrf_grid_cap = la_ctas;
                 const int rcf = factor_block(q + 1);
                 ctx->potrf_grid_cap = 0;
                 if (rcf) return -1;
+                if (use_pt && transpose_panel(q + 1)) return -1;
             }
             if (nranks > 1 && comm_bcast(ctx, H + c1 * ld, (size_t)w1 * ld, (int)((q + 1) % nranks), sA)) return -1;
             if (two) CUDA_TRY(cudaEventRecord(E[q + 1], sA));
@@ -848,7 +891,10 @@ int d_potrf(smcp_ctx *ctx, double *H, int64_t ld, int64_t m, int64_t ncols, int3
             const double *P2 = H + c2 + c0 * ld;
             const int64_t qb = c2 / block;
             const int jb0 = (int)(((rank - qb) % nranks + nranks) % nranks);
-            if (launch_gemm_cyc(ctx, false, false, P2, ld, P2, ld, H + c2 + c2 * ld, ld, m - c2, m - c2, w, -1.0, 1, 1, 0,
+            if (use_pt) {
+                const double *T2 = PT[q & 1] + (size_t)(c2 - c1) * w;
+                if (launch_gemm(ctx, true, true, T2, w, T2, w, H + c2 + c2 * ld, ld, m - c2, m - c2, w, -1.0, 1, 1, 0, "potrf_syrk_dmma")) return -1;
+            } else if (launch_gemm_cyc(ctx, false, false, P2, ld, P2, ld, H + c2 + c2 * ld, ld, m - c2, m - c2, w, -1.0, 1, 1, 0,
                                 "potrf_syrk_dmma", jb0, nranks, tpb)) return -1;
         }
         if (two) CUDA_TRY(cudaEventRecord(F[q], sB));

@@ -59,6 +59,8 @@ struct smcp_ctx {
     void *wave_buf = nullptr;                       // potrs_wave_kernel: published block solutions + flags
     size_t wave_cap = 0;
     unsigned wave_epoch = 0;
+    double *potrf_pt = nullptr;                     // K-major copies of the Cholesky panels (single-GPU look-ahead path)
+    size_t potrf_pt_cap = 0;
     int potrf_grid_cap = 0;                         // > 0: potrf_tile uses at most this many CTAs (look-ahead panel next to a GEMM)
     const char *potrf_family = nullptr;             // profile family of the next d_potrf (default "potrf_dmma")
     int prof_mute = 0;                              // > 0: nested LaunchScopes do not time (an outer scope does)
