@@ -293,7 +293,7 @@ class DeviceBackend:
         fl = 4.0 * nn ** 3 + 6.0 * na * nn ** 2 + 6.0 * na ** 2 * nn
         thr_flops = float(os.environ.get("SMCP_B200_BIG_FLOPS", "2e6"))
         thr_nj = int(os.environ.get("SMCP_B200_BIG_NJ", "0"))
-        thr_compl = float(os.environ.get("SMCP_B200_BIG_COMPL_FLOPS", "6e6" if thr_flops > 0 else "0"))
+        thr_compl = float(os.environ.get("SMCP_B200_BIG_COMPL_FLOPS", "6e5" if thr_flops > 0 else "0"))   # = bigfront.cu
         has_big = symb.nsn > 0 and ((thr_flops > 0 and fl.max() >= thr_flops) or (thr_nj > 0 and nj.max() >= thr_nj)
                                     or (thr_flops > 0 and thr_compl > 0 and (na ** 3).max() / 3.0 >= thr_compl))
         self.batched_probes = not (has_big and (nj.max() > 8 or thr_nj > 0))
@@ -307,11 +307,13 @@ class DeviceBackend:
         self._pool = []
         # chordal-matrix buffers are recycled through this pool; fill it up front so that no
         # cudaMalloc (a synchronising driver call) happens inside the IPM iterations
-        if symb.nblk * 8 * 40 <= (256 << 20):
-            for _ in range(40):
-                p = C.c_void_p()
-                _ck(lib, lib.smcp_csp_alloc(h, 1, C.byref(p)))
-                self._pool.append(p)
+        # (up to 40 buffers within 8 GB: rand_SDP n = 2000 has 12 MB per matrix; without the pool the first iterations
+        # with extra centering steps stalled 70-120 ms each in cudaMalloc, gpurun_out/r02_v36_C3.log)
+        nprefill = int(min(40, (8 << 30) // max(1, symb.nblk * 8)))
+        for _ in range(nprefill):
+            p = C.c_void_p()
+            _ck(lib, lib.smcp_csp_alloc(h, 1, C.byref(p)))
+            self._pool.append(p)
         self._op = None
         self._tok = None
         self.m = 0
