@@ -177,7 +177,7 @@ def measured_fp64_peak():
 # the chordal families carry the number of matrices processed (16*|Vp| bytes each)
 BYTE_FAMILIES = {"potrs", "amap_dense", "amap", "aadj", "potrf_panel", "gemm_thin", "scm_kstream"}
 FLOP_FAMILIES = {"potrf_tile", "trsm_slab", "gemm_smallk", "potrf_dmma", "front_potrf"}
-NO_MODEL = {"front_elem", "thin_up", "thin_down", "thin_compl_tail", "thin_chol", "thin_hinv_local", "thin_hinv_sweep", "thin_trsm", "front_elem_batch", "setup", "scm_position", "scm_sparse", "chordal_trsm", "front_trsm_diag",
+NO_MODEL = {"front_elem", "trsm_cluster", "potrs_trtri", "potrf_panel_t", "thin_up", "thin_down", "thin_compl_tail", "thin_chol", "thin_hinv_local", "thin_hinv_sweep", "thin_trsm", "front_elem_batch", "setup", "scm_position", "scm_sparse", "chordal_trsm", "front_trsm_diag",
             "level1", "reduce", "scatter_cols"}
 
 
@@ -395,6 +395,11 @@ def measure_workload(workload, W, K, ctx, rank, world, pg, local, do_solve, hbm,
     hbm_peak, hbm_src = hbm
     top = max(fam.items(), key=lambda kv: kv[1]["ms"])[0] if fam else None
     out["roofline"] = roofline_of(top, fam[top], nvp, hbm_peak, hbm_src, fp64_peak) if top else None
+    if out["roofline"] is not None:
+        out["roofline"]["share_of_summed_kernel_time"] = fam[top]["ms"] / dev_ms if dev_ms > 0 else None
+        out["roofline"]["how"] = ("family with the largest summed kernel time in the per-launch profile pass (CUDA events around "
+                                  "every launch on the library stream; the concurrent lanes of the top set run one after the other "
+                                  "in that pass, each launch with the whole GPU to itself)")
     per_family = {}
     for nm, f in fam.items():
         if f["ms"] >= 0.03 * dev_ms:

@@ -1465,8 +1465,8 @@ extern "C" int smcp_kkt_solve(smcp_op *op, double *host_y) {
     CUDA_TRY(cudaMemcpyAsync(op->yv, host_y, (size_t)op->m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     {
         RegionScope rs(ctx, "kkt_solve");
-        if (potrs_cluster_for(op->m) ? d_potrs_cluster(ctx, op->H, op->m, op->Dinv, op->yv)
-                                     : potrs_wave_for(ctx, op->m) ? d_potrs_wave(ctx, op->H, op->m, op->Dinv, op->yv)
+        if (potrs_wave_for(ctx, op->m) ? d_potrs_wave(ctx, op->H, op->m, op->Dinv, op->yv)
+                                       : potrs_cluster_for(op->m) ? d_potrs_cluster(ctx, op->H, op->m, op->Dinv, op->yv)
                                                                   : d_potrs(ctx, op->H, op->m, op->yv)) return -1;
     }
     CUDA_TRY(cudaMemcpyAsync(host_y, op->yv, (size_t)op->m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -198,7 +198,8 @@ __global__ void __launch_bounds__(PC_T, 1) potrs_cluster_kernel(PotrsArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
-// potrs for factors that do NOT fit in L2 (m = 10^4: 400 MB per sweep): the whole grid as a flag-driven wavefront.
+// potrs from m = 512 on (and the only sensible form once the factor does not fit in L2: m = 10^4 is 400 MB per sweep): the
+// whole grid as a flag-driven wavefront.
 // Block rows (64 rows) are owned cyclically by the CTAs of a co-resident grid (cooperative launch, one CTA per SM).
 // Step b of the forward sweep: every CTA has ALREADY loaded its tiles L(blk, b), blk > b, into registers; it then waits
 // for the flag of x_b (written to global memory by the owner of block b), subtracts L(blk, b) x_b from the blocks it
@@ -359,8 +360,11 @@ __global__ void __launch_bounds__(PW_T, 1) potrs_wave_kernel(WaveArgs a) {
 
 bool potrs_wave_for(const smcp_ctx *ctx, int64_t m) {
     static const bool off = getenv("SMCP_B200_POTRS_NO_WAVE") && atoi(getenv("SMCP_B200_POTRS_NO_WAVE")) != 0;
+    // from m = 512 on the wavefront beats the 16-CTA cluster kernel as well (m = 1000: 0.22 -> 0.13 ms, m = 4000: 1.75 -> 0.43 ms,
+    // gpurun_out/r02_v39_potrs_wave_min.log); SMCP_B200_POTRS_WAVE_MIN moves the switch
+    static const int64_t wave_min = getenv("SMCP_B200_POTRS_WAVE_MIN") ? atoll(getenv("SMCP_B200_POTRS_WAVE_MIN")) : 512;
     const int64_t nb = (m + 63) / 64;
-    return !off && potrs_cluster_enabled() && m > 4096 && nb <= (int64_t)PW_MAXOWN * ctx->num_sms;
+    return !off && potrs_cluster_enabled() && m >= wave_min && nb <= (int64_t)PW_MAXOWN * ctx->num_sms;
 }
 
 int d_potrs_wave(smcp_ctx *ctx, const double *H, int64_t m, const double *Dinv, double *y_dev) {
