@@ -1478,6 +1478,128 @@ __global__ void __launch_bounds__(256) thin_trsm_bwd_kernel(int nn, int na, int 
     }
 }
 
+int big_trsm_node(smcp_sym *s, const BigNode &q, const double *L, double *B, int64_t ldb, int64_t nrhs, int trans);
+// A RUN of consecutive thin supernodes in ONE launch: a right-hand side never interacts with another one, so the warp that
+// owns a column walks the whole run by itself (forward: in post-order, backward: reversed) -- no dependency between warps,
+// no launch per supernode (rand_SDP: 75 launches of ~20 us per direction -> 3).  desc[i] = {nn, na, nj, r0} (int4),
+// off[i] = {offset of the block in blkval, offset of the separator rows in rowidx}.
+__global__ void __launch_bounds__(256) thin_trsm_run_kernel(const int4 *__restrict__ desc, const longlong2 *__restrict__ off, int i0, int i1, int trans,
+                                                            const double *__restrict__ L, const int *__restrict__ rowidx, double *__restrict__ B,
+                                                            long long ldb, long long nrhs) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long c = (long long)blockIdx.x * 8 + warp;
+    if (c >= nrhs) return;
+    double *bc = B + c * ldb;
+    for (int q = 0; q < i1 - i0; ++q) {
+        const int i = trans ? i1 - 1 - q : i0 + q;
+        const int4 d = desc[i];
+        const int nn = d.x, na = d.y, nj = d.z, r0 = d.w;
+        const double *blk = L + off[i].x;
+        const double *Lan = blk + nn;
+        const int *rows = rowidx + off[i].y;
+        double x[THIN_NN];
+        if (!trans) {
+            // every lane solves the nn x nn system of its column (same arithmetic), lane 0 stores it
+#pragma unroll
+            for (int a = 0; a < THIN_NN; ++a) x[a] = (a < nn) ? bc[r0 + a] : 0.0;
+            __syncwarp();
+#pragma unroll
+            for (int a = 0; a < THIN_NN; ++a)
+                if (a < nn) {
+                    double t = x[a];
+#pragma unroll
+                    for (int b = 0; b < THIN_NN; ++b)
+                        if (b < a) t = fma(-__ldg(blk + a + (long long)b * nj), x[b], t);
+                    x[a] = t / __ldg(blk + a + (long long)a * nj);
+                    if (lane == 0) bc[r0 + a] = x[a];
+                }
+            for (int r = lane; r < na; r += 32) {
+                double t = 0.0;
+#pragma unroll
+                for (int a = 0; a < THIN_NN; ++a)
+                    if (a < nn) t = fma(Lan[r + (long long)a * nj], x[a], t);
+                bc[rows[r]] -= t;
+            }
+        } else {
+            double acc[THIN_NN];
+#pragma unroll
+            for (int a = 0; a < THIN_NN; ++a) acc[a] = 0.0;
+            for (int r = lane; r < na; r += 32) {
+                const double v = bc[rows[r]];
+#pragma unroll
+                for (int a = 0; a < THIN_NN; ++a)
+                    if (a < nn) acc[a] = fma(Lan[r + (long long)a * nj], v, acc[a]);
+            }
+#pragma unroll
+            for (int a = 0; a < THIN_NN; ++a)
+                if (a < nn)
+                    for (int o = 16; o > 0; o >>= 1) acc[a] += __shfl_down_sync(0xffffffffu, acc[a], o);
+            if (lane == 0) {
+#pragma unroll
+                for (int a = 0; a < THIN_NN; ++a) x[a] = (a < nn) ? bc[r0 + a] - acc[a] : 0.0;
+#pragma unroll
+                for (int a = THIN_NN - 1; a >= 0; --a)
+                    if (a < nn) {
+                        double t = x[a];
+#pragma unroll
+                        for (int b = THIN_NN - 1; b >= 0; --b)
+                            if (b > a && b < nn) t = fma(-__ldg(blk + b + (long long)a * nj), x[b], t);
+                        x[a] = t / __ldg(blk + a + (long long)a * nj);
+                        bc[r0 + a] = x[a];
+                    }
+            }
+        }
+        // the next supernode of the run reads what this one wrote (other lanes' rows)
+        __syncwarp();
+    }
+}
+
+// the top set against many right-hand sides: runs of thin supernodes through thin_trsm_run_kernel, the others one by one
+int big_trsm_all(smcp_sym *s, const double *L, double *B, int64_t ldb, int64_t nrhs, int trans) {
+    smcp_ctx *ctx = s->ctx;
+    const int nb = (int)s->big.size();
+    static const bool run_off = getenv("SMCP_B200_NO_TRSM_RUN") && atoi(getenv("SMCP_B200_NO_TRSM_RUN")) != 0;
+    if (!thin_on() || run_off) {
+        if (trans) { for (int i = nb - 1; i >= 0; --i) if (big_trsm_node(s, s->big[i], L, B, ldb, nrhs, 1)) return -1; }
+        else { for (int i = 0; i < nb; ++i) if (big_trsm_node(s, s->big[i], L, B, ldb, nrhs, 0)) return -1; }
+        return 0;
+    }
+    if (!s->thin_desc) {
+        std::vector<int4> d(nb);
+        std::vector<longlong2> o(nb);
+        for (int i = 0; i < nb; ++i) {
+            const BigNode &q = s->big[i];
+            d[i] = make_int4(q.nn, q.na, q.nj, q.r0);
+            o[i] = make_longlong2(q.boff, q.rowoff + q.nn);
+        }
+        CUDA_TRY(cudaMalloc(&s->thin_desc, (size_t)nb * sizeof(int4)));
+        CUDA_TRY(cudaMalloc(&s->thin_off, (size_t)nb * sizeof(longlong2)));
+        CUDA_TRY(cudaMemcpy(s->thin_desc, d.data(), (size_t)nb * sizeof(int4), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(s->thin_off, o.data(), (size_t)nb * sizeof(longlong2), cudaMemcpyHostToDevice));
+        s->allocs.push_back(s->thin_desc);
+        s->allocs.push_back(s->thin_off);
+    }
+    auto thin = [&](int i) { return s->big[i].nn <= THIN_NN && s->big[i].na >= 1; };
+    // maximal runs [a, b) of thin supernodes, in sweep order
+    std::vector<std::pair<int, int>> segs;       // (begin, end); begin == end - 1 and not thin: a single generic node
+    for (int i = 0; i < nb;) {
+        int j = i + 1;
+        if (thin(i)) while (j < nb && thin(j)) ++j;
+        segs.push_back({i, j});
+        i = j;
+    }
+    if (trans) std::reverse(segs.begin(), segs.end());
+    for (auto &sg : segs) {
+        if (thin(sg.first)) {
+            LaunchScope ls_(ctx, "thin_trsm");
+            thin_trsm_run_kernel<<<(unsigned)((nrhs + 7) / 8), 256, 0, ctx->stream>>>((const int4 *)s->thin_desc, (const longlong2 *)s->thin_off, sg.first,
+                                                                                      sg.second, trans, L, s->d.rowidx, B, ldb, nrhs);
+            CUDA_TRY(cudaGetLastError());
+        } else if (big_trsm_node(s, s->big[sg.first], L, B, ldb, nrhs, trans)) return -1;
+    }
+    return 0;
+}
+
 int big_trsm_node(smcp_sym *s, const BigNode &q, const double *L, double *B, int64_t ldb, int64_t nrhs, int trans) {
     smcp_ctx *ctx = s->ctx;
     const int nn = q.nn, na = q.na, nj = q.nj;

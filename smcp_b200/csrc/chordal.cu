@@ -339,13 +339,17 @@ int k_hess_prep(smcp_hess *h, const double *L, const double *Y) {
     a.Yaa_out = h->Yaa;
     const bool big = use_big(s, 1);
     if (big) a.skipflag = s->big_flag;
-    if (launch_tree<OP_HPREP>(s, a, flat_sched(s), 1, pick_threads(s, big), "hessian_prep")) return -1;
+    {
+        SideScope side(s, big);
+        if (launch_tree<OP_HPREP>(s, a, flat_sched(s), 1, pick_threads(s, big), "hessian_prep")) return -1;
+    }
     if (big)
         {
             // independent per supernode
             std::vector<std::vector<int>> all(1);
             for (int i = 0; i < (int)s->big.size(); ++i) all[0].push_back(i);
             if (big_sweep(s, all, [&](const BigNode &q) { return big_hess_prep(s, q, L, Y, h->Lt, h->Yaa); })) return -1;
+            if (side_join(s)) return -1;
         }
     return 0;
 }
@@ -612,16 +616,12 @@ int k_trsm(smcp_sym *s, const double *L, double *B, int64_t ldb, int64_t nrhs, i
     // solves and DMMA products of bigfront.cu; the top set is closed under ancestors, so in the forward
     // sweep it comes after everything else and in the backward sweep before
     const bool big = !s->big.empty() && nrhs >= 32;
-    if (big && trans)
-        for (auto it = s->big.rbegin(); it != s->big.rend(); ++it)
-            if (big_trsm_node(s, *it, L, B, ldb, nrhs, 1)) return -1;
+    if (big && trans && big_trsm_all(s, L, B, ldb, nrhs, 1)) return -1;
     {
         LaunchScope ls(ctx, "chordal_trsm");
         trsm_kernel<<<grid, 128, smem, ctx->stream>>>(s->d, L, B, ldb, (int)nrhs, trans, cols, big ? s->big_flag : nullptr, use_smem);
     }
-    if (big && !trans)
-        for (const BigNode &q : s->big)
-            if (big_trsm_node(s, q, L, B, ldb, nrhs, 0)) return -1;
+    if (big && !trans && big_trsm_all(s, L, B, ldb, nrhs, 0)) return -1;
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

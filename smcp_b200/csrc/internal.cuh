@@ -201,6 +201,7 @@ struct smcp_sym {
     cudaStream_t tree_side = nullptr;    // side stream of the tree kernels that overlap with the top-set lanes (chordal.cu)
     cudaEvent_t tree_ev[2] = {nullptr, nullptr};
     bool tree_pending = false;
+    void *thin_desc = nullptr, *thin_off = nullptr;   // per top-set supernode {nn, na, nj, r0} / {block offset, separator rows offset}
     double *thin_w = nullptr;            // W = D^-1 K_an^T of every thin supernode (forward Hessian)
     std::vector<size_t> thin_w_off;
     std::vector<cudaStream_t> thin_side; // side streams of the M_an products
@@ -296,6 +297,7 @@ int big_lanes_begin(smcp_sym *s);          // returns the number of lanes (>= 1)
 void big_lane_pick(smcp_sym *s, int lane);
 int big_lanes_end(smcp_sym *s);
 int big_trsm_node(smcp_sym *s, const BigNode &q, const double *L, double *B, int64_t ldb, int64_t nrhs, int trans);
+int big_trsm_all(smcp_sym *s, const double *L, double *B, int64_t ldb, int64_t nrhs, int trans);
 int big_hess_fwd_batched(smcp_sym *s, const double *Lt, const double *Yaa_all, double *U, int64_t batch);
 
 // blocked triangular solves (front.cu)
