@@ -586,6 +586,67 @@ __global__ void trsm_kernel(SymDev S, const double *L, double *B, long long ldb,
     }
 }
 
+// Many right-hand sides: a column never interacts with another one, so a WARP owns a column for the whole sweep (its n
+// entries in shared memory) and needs no block barrier at all -- trsm_kernel above walks the supernodes with 2 nn + 1
+// __syncthreads each (2.5 ms per sweep over the 731 small supernodes of the rand_SDP n = 2000 pattern, a latency chain).
+#define TW_WARPS 4
+__global__ void __launch_bounds__(32 * TW_WARPS) trsm_warp_kernel(SymDev S, const double *__restrict__ L, double *__restrict__ B, long long ldb,
+                                                                  long long nrhs, int trans, const int *__restrict__ skipflag) {
+    extern __shared__ double tw_sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long c = (long long)blockIdx.x * TW_WARPS + warp;
+    if (c >= nrhs) return;
+    double *b = tw_sm + (size_t)warp * S.n;
+    double *Bg = B + c * ldb;
+    for (int r = lane; r < S.n; r += 32) b[r] = Bg[r];
+    __syncwarp();
+    if (!trans) {
+        for (int k = 0; k < S.nsn; ++k) {
+            if (skipflag && skipflag[k]) continue;
+            const int nn = S.nn[k], na = S.na[k], nj = nn + na;
+            const double *blk = L + S.blkptr[k];
+            const int *rows = S.rowidx + S.rowptr[k];
+            const int r0 = rows[0];
+            for (int j = 0; j < nn; ++j) {
+                const double xj = b[r0 + j] / blk[j + (long long)j * nj];
+                __syncwarp();
+                if (lane == 0) b[r0 + j] = xj;
+                for (int r = j + 1 + lane; r < nn; r += 32) b[r0 + r] = fma(-blk[r + (long long)j * nj], xj, b[r0 + r]);
+                __syncwarp();
+            }
+            for (int i = lane; i < na; i += 32) {
+                double t = 0.0;
+                for (int r = 0; r < nn; ++r) t = fma(blk[nn + i + (long long)r * nj], b[r0 + r], t);
+                b[rows[nn + i]] -= t;
+            }
+            __syncwarp();
+        }
+    } else {
+        for (int k = S.nsn - 1; k >= 0; --k) {
+            if (skipflag && skipflag[k]) continue;
+            const int nn = S.nn[k], na = S.na[k], nj = nn + na;
+            const double *blk = L + S.blkptr[k];
+            const int *rows = S.rowidx + S.rowptr[k];
+            const int r0 = rows[0];
+            for (int r = 0; r < nn; ++r) {
+                double t = 0.0;
+                for (int i = lane; i < na; i += 32) t = fma(blk[nn + i + (long long)r * nj], b[rows[nn + i]], t);
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                if (lane == 0) b[r0 + r] -= t;
+            }
+            __syncwarp();
+            for (int j = nn - 1; j >= 0; --j) {
+                const double xj = b[r0 + j] / blk[j + (long long)j * nj];
+                __syncwarp();
+                if (lane == 0) b[r0 + j] = xj;
+                for (int i = lane; i < j; i += 32) b[r0 + i] = fma(-blk[j + (long long)i * nj], xj, b[r0 + i]);
+                __syncwarp();
+            }
+        }
+    }
+    for (int r = lane; r < S.n; r += 32) Bg[r] = b[r];
+}
+
 int k_trsm(smcp_sym *s, const double *L, double *B, int64_t ldb, int64_t nrhs, int trans) {
     RegionScope rs(s->ctx, "op_trsm");
     smcp_ctx *ctx = s->ctx;
@@ -617,7 +678,18 @@ int k_trsm(smcp_sym *s, const double *L, double *B, int64_t ldb, int64_t nrhs, i
     // sweep it comes after everything else and in the backward sweep before
     const bool big = !s->big.empty() && nrhs >= 32;
     if (big && trans && big_trsm_all(s, L, B, ldb, nrhs, 1)) return -1;
-    {
+    static const bool warp_off = getenv("SMCP_B200_NO_TRSM_WARP") && atoi(getenv("SMCP_B200_NO_TRSM_WARP")) != 0;
+    const size_t tw_smem = (size_t)TW_WARPS * s->d.n * sizeof(double);
+    if (!warp_off && nrhs >= 64 && tw_smem <= 96 * 1024) {
+        static size_t tw_attr = 0;
+        if (tw_smem > tw_attr) {
+            CUDA_TRY(cudaFuncSetAttribute(trsm_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            tw_attr = 96 * 1024;
+        }
+        LaunchScope ls(ctx, "chordal_trsm");
+        trsm_warp_kernel<<<(unsigned)((nrhs + TW_WARPS - 1) / TW_WARPS), 32 * TW_WARPS, tw_smem, ctx->stream>>>(s->d, L, B, ldb, nrhs, trans,
+                                                                                                         big ? s->big_flag : nullptr);
+    } else {
         LaunchScope ls(ctx, "chordal_trsm");
         trsm_kernel<<<grid, 128, smem, ctx->stream>>>(s->d, L, B, ldb, (int)nrhs, trans, cols, big ? s->big_flag : nullptr, use_smem);
     }

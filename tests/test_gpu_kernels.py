@@ -133,6 +133,22 @@ def test_trsm(setup):
         assert relerr(got, ref) < 1e-10
 
 
+def test_trsm_many_rhs(setup):
+    """The dense inverse of the sparse-constraint technique solves with n right-hand sides: warp-per-column sweep over
+    the small supernodes (trsm_warp_kernel), runs of thin top-set supernodes in one launch (thin_trsm_run_kernel)."""
+    from oracle import supernodal as sn
+    symb, dev, s, l, y = setup
+    rng = np.random.default_rng(4)
+    n = symb.n
+    B = rng.standard_normal((n, 70))
+    Lb = dev.set_blk(l)
+    for trans in ("N", "T"):
+        ref = B.copy()
+        sn.trsm(symb, l, ref, trans)
+        got = dev.trsm(Lb, B, trans)
+        assert relerr(got, ref) < 1e-10
+
+
 def test_completion(setup):
     from oracle import supernodal as sn
     symb, dev, s, l, y = setup
