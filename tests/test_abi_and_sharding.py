@@ -156,3 +156,18 @@ def test_sharded_schur_gloo_world2(tmp_path):
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
     assert "OK" in out.stdout
+
+
+def test_bench_arms_print_the_same_config():
+    """bench.py: the b200 arm and the reference arm describe the workload with identical `config` objects
+    (the driver compares them), for every N, and BASELINE.json's headline configuration is the default."""
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import bench
+    assert bench.DEFAULT == "rand_n2000_m10000"
+    for world in (1, 2, 8):
+        a, b = bench.config_of(bench.DEFAULT, world), bench.config_of(bench.DEFAULT, world)
+        assert a == b and a["workload"] == bench.DEFAULT and a["n"] == 2000 and a["m"] == 10000
+        assert "l2" in a and ("x%d " % world) in a["parallelism"]
+    assert "model" not in bench.config_of(bench.DEFAULT, 1)
