@@ -187,3 +187,33 @@ def test_base_completion_is_max_det(oracle_backend):
     bad[0, 0] = -1.0
     with pytest.raises(ArithmeticError):
         S.completion(sp.csc_matrix(np.tril(bad)))
+
+
+def test_c_trsm_matches_numpy():
+    """oracle/csn.c (the compiled chordal trsm of bench.py's CPU baseline) against its specification
+    oracle/supernodal.py:trsm, both directions, on a pattern with fill and mixed supernode sizes."""
+    import scipy.sparse as sp
+    from oracle import csn, supernodal as sn
+    from smcp_b200 import symbolic as sy
+    if not csn.available():
+        pytest.skip("oracle/_ref/csn.so not built (make -C oracle)")
+    n = 300
+    rng = np.random.default_rng(5)
+    e = rng.integers(0, n, size=(4 * n, 2))
+    I = np.concatenate([np.maximum(e[:, 0], e[:, 1]), np.arange(n)])
+    J = np.concatenate([np.minimum(e[:, 0], e[:, 1]), np.arange(n)])
+    Lp = sp.tril(sp.coo_matrix((np.ones(len(I)), (I, J)), shape=(n, n))).tocsc()
+    Lp.sort_indices()
+    cp, ri = Lp.indptr.astype(np.int64), Lp.indices.astype(np.int64)
+    out = sy.embed(n, cp, ri, sy.min_degree(n, cp, ri))
+    symb = sy.Symbolic(n, out[0], out[1])
+    L = rng.standard_normal(symb.nblk) * 0.05
+    L[symb.diag_blk] = 1.0 + rng.random(len(symb.diag_blk))
+    for k in (1, 7, 40):
+        B = rng.standard_normal((n, k))
+        for tr in ("N", "T"):
+            ref = B.copy()
+            sn.trsm(symb, L, ref, tr)
+            got = np.ascontiguousarray(B.copy())
+            csn.trsm(symb, L, got, tr)
+            assert np.linalg.norm(got - ref) <= 1e-12 * np.linalg.norm(ref)
