@@ -482,7 +482,13 @@ def run_b200(args):
         sec = measure_workload(sec_name, W, K, ctx, rank, world, pg, local, not args.no_solve, hbm, fp64_peak)
     if rank != 0:
         return
-    cpu = cpu_baseline(args.workload) if world == 1 else None       # host baseline: rank 0 at N = 1 only
+    cpu = None
+    if world == 1:                                                  # host baseline: rank 0 at N = 1 only
+        try:
+            cpu = cpu_baseline(args.workload)
+        except Exception as exc:                                    # never lose the GPU line over the CPU arm
+            cpu = {"value": None, "unit": "s/iter", "cores": None, "kind": "port", "sample": None,
+                   "error": "%s: %s" % (type(exc).__name__, exc)}
     cfg = config_of(args.workload, world)
     out = {
         "metric": "s_per_ipm_iteration", "value": main["dev_s"], "unit": "s/iter", "n_gpus": world,
@@ -596,7 +602,13 @@ def cpu_baseline(workload, budget_s=25.0):
             S = max(1, min(Ns, 24))
             cols = md + np.unique(np.linspace(0, Ns - 1, S).astype(int))
             use_ref = oref.available()
-            use_c = csn.available()
+            use_c = False
+            if csn.available():
+                try:
+                    csn._load()
+                    use_c = True
+                except Exception:
+                    use_c = False          # e.g. no OpenMP runtime on this host: the NumPy trsm is used
             H = np.zeros((m, m), order="F") if not use_ref else None
             if use_ref:
                 # persistent cvxopt-ABI objects like the reference's solver holds them (H, Av, Ip, Jp are
