@@ -332,7 +332,9 @@ def measure_workload(workload, W, K, ctx, rank, world, pg, local, do_solve, hbm,
     # CUDA events on the library's stream bracket the K timed iterations: `value` (concurrent lanes make
     # the sum of kernel durations larger than the elapsed device time, so the sum is reported separately)
     timer.marks[W] = mark_start
-    timer.marks[W + K] = lambda: snap.__setitem__("span_ms", ctx.timer_stop())
+    snap["span"] = {}
+    for it_ in range(W + 1, W + K + 1):      # elapsed device time since the start mark, re-read at every later iteration
+        timer.marks[it_] = (lambda i=it_: snap["span"].__setitem__(i, ctx.timer_stop()))
     solvers._iteration_hook = timer
     sampler = ClockSampler(local)
     sampler.start()
@@ -343,8 +345,15 @@ def measure_workload(workload, W, K, ctx, rank, world, pg, local, do_solve, hbm,
     barrier()
     clocks = sampler.stop()
     iters = sol["iterations"]
-    assert iters >= W + K, "solver stopped after %d iterations (< warmup+steps)" % iters
+    K_req = K
+    last = max(timer.t) if timer.t else 0
+    if last < W + K:
+        # the problem converged before warmup + steps iterations: time the iterations there are and say so
+        K = last - W
+        if K < 1:
+            raise SystemExit("bench: the solver stopped after %d iterations, fewer than warmup + 1 = %d" % (iters, W + 1))
     e2e_s = (timer.t[W + K] - timer.t[W]) / K
+    snap["span_ms"] = snap["span"][W + K]
     # counters: maxiters = W + K stops the loop there; after it only the final residual evaluation runs
     h2d = (TRAFFIC["h2d"] - snap["traffic"]["h2d"]) // K
     d2h = (TRAFFIC["d2h"] - snap["traffic"]["d2h"]) // K
@@ -388,7 +397,7 @@ def measure_workload(workload, W, K, ctx, rank, world, pg, local, do_solve, hbm,
         pg.all_reduce(t, op=pg.ReduceOp.MAX)
         e2e_s, dev_s, sp_s, ksum_s = float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
-    out = {"e2e_s": e2e_s, "dev_s": dev_s, "ksum_s": ksum_s, "h2d": int(h2d), "d2h": int(d2h), "launches": int(n_launch), "ops": ops_ms,
+    out = {"steps": int(K), "steps_requested": int(K_req), "e2e_s": e2e_s, "dev_s": dev_s, "ksum_s": ksum_s, "h2d": int(h2d), "d2h": int(d2h), "launches": int(n_launch), "ops": ops_ms,
            "clocks": clocks, "status": sol["status"], "iterations": int(iters), "n": n, "m": m, "nvp": int(nvp)}
     if rank != 0:
         return out
@@ -492,11 +501,12 @@ def run_b200(args):
     cfg = config_of(args.workload, world)
     out = {
         "metric": "s_per_ipm_iteration", "value": main["dev_s"], "unit": "s/iter", "n_gpus": world,
-        "steps": K, "warmup": W, "ms_per_step": main["dev_s"] * 1e3, "higher_is_better": False,
+        "steps": main["steps"], "warmup": W, "ms_per_step": main["dev_s"] * 1e3, "higher_is_better": False,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": cfg,
         "e2e": {"value": main["e2e_s"], "unit": "s/iter", "h2d_bytes_per_step": main["h2d"], "d2h_bytes_per_step": main["d2h"]},
         "gpu_launches": main["launches"],
+        "steps_requested": main["steps_requested"],
         "kernel_time_sum_s_per_iter": main["ksum_s"],
         "clocks": main["clocks"],
         "roofline": main["roofline"],
