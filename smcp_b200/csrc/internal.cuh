@@ -59,6 +59,7 @@ struct smcp_ctx {
     void *wave_buf = nullptr;                       // potrs_wave_kernel: published block solutions + flags
     size_t wave_cap = 0;
     unsigned wave_epoch = 0;
+    int64_t wave_nb = -1;                           // block count the flag layout of wave_buf belongs to
     double *potrf_pt = nullptr;                     // K-major copies of the Cholesky panels (single-GPU look-ahead path)
     size_t potrf_pt_cap = 0;
     int potrf_grid_cap = 0;                         // > 0: potrf_tile uses at most this many CTAs (look-ahead panel next to a GEMM)

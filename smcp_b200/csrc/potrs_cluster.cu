@@ -387,9 +387,12 @@ int d_potrs_wave(smcp_ctx *ctx, const double *H, int64_t m, const double *Dinv, 
     a.xf = (double *)ctx->wave_buf;
     a.xb = a.xf + nb * 64;
     a.flag = (unsigned *)(a.xb + nb * 64);
-    if (ctx->wave_epoch > 0xfffffff0u) {
+    // the flag array sits behind the two solution buffers, so its place depends on the order of the matrix: start from
+    // clean flags whenever the order changes (and before the epoch counter wraps)
+    if (ctx->wave_epoch > 0xfffffff0u || ctx->wave_nb != nb) {
         CUDA_TRY(cudaMemsetAsync(ctx->wave_buf, 0, need, ctx->stream));
         ctx->wave_epoch = 0;
+        ctx->wave_nb = nb;
     }
     a.base = ctx->wave_epoch;
     ctx->wave_epoch += 2;
